@@ -1,0 +1,211 @@
+// HBM-bound layer ops of the DLA-34 / ResNet-DCN forward, NHWC bf16, 16-byte (8-channel) vectors.
+//
+// Replaces (reference file:line under CenterNet/models/backbones/):
+//   pose_dla_dcn.py:243      nn.MaxPool2d(stride, stride)            -> maxpool_kernel
+//   pose_dla_dcn.py:466-488  depthwise bilinear ConvTranspose2d + `layers[i] + layers[i-1]` -> dw_deconv_kernel
+//   input / output layout changes around the NHWC bf16 engine        -> nchw_to_nhwc / nhwc_to_nchw kernels
+#include "cnb_common.cuh"
+
+namespace cnb {
+namespace {
+
+__device__ __forceinline__ float2 bf2_to_f2(u32 v) {
+  __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&v);
+  return __bfloat1622float2(h);
+}
+__device__ __forceinline__ u32 f2_to_bf2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<u32*>(&h);
+}
+__device__ __forceinline__ u32 bf2_max(u32 a, u32 b) {
+  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<u32*>(&r);
+}
+
+// ---- NCHW fp32 -> NHWC bf16 with zero channel padding (C -> Cp, Cp % 8 == 0) -------------------------
+// one thread per (pixel, 8-channel group); reads are coalesced along W for each channel plane
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int C,
+                                    int HW, int Cp) {
+  const int groups = Cp / 8;
+  const long long total = (long long)B * HW * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix_all = i % ((long long)B * HW);   // pixel fastest -> coalesced plane reads
+    const int g = (int)(i / ((long long)B * HW));
+    const int b = (int)(pix_all / HW);
+    const int pix = (int)(pix_all % HW);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = g * 8 + j;
+      v[j] = c < C ? __ldg(x + ((size_t)b * C + c) * HW + pix) : 0.f;
+    }
+    uint4 o = make_uint4(f2_to_bf2(v[0], v[1]), f2_to_bf2(v[2], v[3]), f2_to_bf2(v[4], v[5]), f2_to_bf2(v[6], v[7]));
+    *reinterpret_cast<uint4*>(y + ((size_t)b * HW + pix) * Cp + g * 8) = o;
+  }
+}
+
+// ---- NHWC bf16 (channel slice) -> NCHW fp32 -------------------------------------------------------------
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int B, int C,
+                                    int HW, int cstride, int coffset) {
+  const long long total = (long long)B * C * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int pix = (int)(i % HW);
+    const long long bc = i / HW;
+    const int c = (int)(bc % C), b = (int)(bc / C);
+    y[i] = __bfloat162float(x[((size_t)b * HW + pix) * cstride + coffset + c]);
+  }
+}
+
+// ---- MaxPool2d(k, stride=k), floor mode -----------------------------------------------------------------
+__global__ void maxpool_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H,
+                               int W, int C, int xcs, int xco, int ycs, int yco, int k) {
+  const int Ho = H / k, Wo = W / k, groups = C / 8;
+  const long long total = (long long)B * Ho * Wo * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    long long p = i / groups;
+    const int ox = (int)(p % Wo);
+    p /= Wo;
+    const int oy = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    uint4 m;
+    bool first = true;
+    for (int dy = 0; dy < k; ++dy)
+      for (int dx = 0; dx < k; ++dx) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(
+            x + ((size_t)(b * H + oy * k + dy) * W + ox * k + dx) * xcs + xco + g * 8));
+        if (first) {
+          m = v;
+          first = false;
+        } else {
+          m.x = bf2_max(m.x, v.x); m.y = bf2_max(m.y, v.y); m.z = bf2_max(m.z, v.z); m.w = bf2_max(m.w, v.w);
+        }
+      }
+    *reinterpret_cast<uint4*>(y + ((size_t)(b * Ho + oy) * Wo + ox) * ycs + yco + g * 8) = m;
+  }
+}
+
+// ---- depthwise ConvTranspose2d(C, C, 2f, stride=f, padding=f/2, groups=C, bias=False) [+ add] -----------
+// out[oy,ox,c] = sum_{ky,kx} w[c,ky,kx] * in[iy,ix,c]  with  oy = iy*f - f/2 + ky  (<= 2x2 contributing inputs)
+// w is passed re-laid-out as [2f*2f][C] fp32 so that 8 channels of one tap are contiguous.
+__global__ void dw_deconv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wt,
+                                 const __nv_bfloat16* __restrict__ add, __nv_bfloat16* __restrict__ y, int B,
+                                 int H, int W, int C, int f) {
+  const int Ho = H * f, Wo = W * f, groups = C / 8, ks = 2 * f, pad = f / 2;
+  const long long total = (long long)B * Ho * Wo * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    long long p = i / groups;
+    const int ox = (int)(p % Wo);
+    p /= Wo;
+    const int oy = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    // contributing input rows: iy with 0 <= oy + pad - iy*f < 2f
+    const int ty = oy + pad, tx = ox + pad;
+    const int iy_hi = ty / f, ix_hi = tx / f;
+    for (int a = 0; a < 2; ++a) {
+      const int iy = iy_hi - a;
+      const int ky = ty - iy * f;
+      if (iy < 0 || iy >= H || ky < 0 || ky >= ks) continue;
+      for (int c2 = 0; c2 < 2; ++c2) {
+        const int ix = ix_hi - c2;
+        const int kx = tx - ix * f;
+        if (ix < 0 || ix >= W || kx < 0 || kx >= ks) continue;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + ((size_t)(b * H + iy) * W + ix) * C + g * 8));
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(wt + (size_t)(ky * ks + kx) * C + g * 8));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(wt + (size_t)(ky * ks + kx) * C + g * 8 + 4));
+        const float2 a0 = bf2_to_f2(v.x), a1 = bf2_to_f2(v.y), a2 = bf2_to_f2(v.z), a3 = bf2_to_f2(v.w);
+        acc[0] += w0.x * a0.x; acc[1] += w0.y * a0.y; acc[2] += w0.z * a1.x; acc[3] += w0.w * a1.y;
+        acc[4] += w1.x * a2.x; acc[5] += w1.y * a2.y; acc[6] += w1.z * a3.x; acc[7] += w1.w * a3.y;
+      }
+    }
+    const size_t o = ((size_t)(b * Ho + oy) * Wo + ox) * C + g * 8;
+    if (add) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(add + o));
+      const float2 a0 = bf2_to_f2(v.x), a1 = bf2_to_f2(v.y), a2 = bf2_to_f2(v.z), a3 = bf2_to_f2(v.w);
+      acc[0] += a0.x; acc[1] += a0.y; acc[2] += a1.x; acc[3] += a1.y;
+      acc[4] += a2.x; acc[5] += a2.y; acc[6] += a3.x; acc[7] += a3.y;
+    }
+    *reinterpret_cast<uint4*>(y + o) = make_uint4(f2_to_bf2(acc[0], acc[1]), f2_to_bf2(acc[2], acc[3]),
+                                                  f2_to_bf2(acc[4], acc[5]), f2_to_bf2(acc[6], acc[7]));
+  }
+}
+
+// [C,1,ks,ks] fp32 -> [ks*ks][C] fp32
+__global__ void dw_weight_relayout_kernel(const float* __restrict__ w, float* __restrict__ wt, int C, int kk) {
+  const int total = C * kk;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % C, t = i / C;
+    wt[i] = w[(size_t)c * kk + t];
+  }
+}
+
+inline int grid_for(long long total, int threads = 256) {
+  long long g = (total + threads - 1) / threads;
+  const long long cap = 148LL * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+}  // namespace cnb
+
+using namespace cnb;
+
+extern "C" int cnb_nchw_f32_to_nhwc_bf16(const float* x, void* y, int B, int C, int H, int W, int C_pad,
+                                         cnb_stream_t s) {
+  CNB_CHECK_ARG(x && y && B >= 1 && C >= 1 && H >= 1 && W >= 1, "nchw_to_nhwc: bad argument");
+  CNB_CHECK_ARG(C_pad >= C && C_pad % 8 == 0, "nchw_to_nhwc: C_pad must be >= C and a multiple of 8");
+  const long long total = (long long)B * H * W * (C_pad / 8);
+  nchw_to_nhwc_kernel<<<grid_for(total), 256, 0, (cudaStream_t)s>>>(x, (__nv_bfloat16*)y, B, C, H * W, C_pad);
+  CNB_LAUNCH_CHECK();
+  return CNB_OK;
+}
+
+extern "C" int cnb_nhwc_bf16_to_nchw_f32(const void* x, float* y, int B, int C, int H, int W, int x_cstride,
+                                         int x_coffset, cnb_stream_t s) {
+  CNB_CHECK_ARG(x && y && B >= 1 && C >= 1 && H >= 1 && W >= 1 && x_cstride >= C, "nhwc_to_nchw: bad argument");
+  const long long total = (long long)B * C * H * W;
+  nhwc_to_nchw_kernel<<<grid_for(total), 256, 0, (cudaStream_t)s>>>((const __nv_bfloat16*)x, y, B, C, H * W,
+                                                                    x_cstride, x_coffset);
+  CNB_LAUNCH_CHECK();
+  return CNB_OK;
+}
+
+extern "C" int cnb_maxpool2d(const void* x, void* y, int B, int H, int W, int C, int x_cstride, int x_coffset,
+                             int y_cstride, int y_coffset, int k, cnb_stream_t s) {
+  CNB_CHECK_ARG(x && y && B >= 1 && H >= k && W >= k && k >= 1, "maxpool2d: bad argument");
+  CNB_CHECK_ARG(C % 8 == 0 && x_cstride % 8 == 0 && x_coffset % 8 == 0 && y_cstride % 8 == 0 && y_coffset % 8 == 0,
+                "maxpool2d: channel counts/strides/offsets must be multiples of 8");
+  const long long total = (long long)B * (H / k) * (W / k) * (C / 8);
+  maxpool_kernel<<<grid_for(total), 256, 0, (cudaStream_t)s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, B, H, W,
+                                                               C, x_cstride, x_coffset, y_cstride, y_coffset, k);
+  CNB_LAUNCH_CHECK();
+  return CNB_OK;
+}
+
+extern "C" int cnb_dw_deconv_relayout_weights(const float* w, float* wt, int C, int f, cnb_stream_t s) {
+  CNB_CHECK_ARG(w && wt && C >= 1 && f >= 1, "dw_deconv_relayout_weights: bad argument");
+  const int kk = 4 * f * f;
+  dw_weight_relayout_kernel<<<grid_for((long long)C * kk), 256, 0, (cudaStream_t)s>>>(w, wt, C, kk);
+  CNB_LAUNCH_CHECK();
+  return CNB_OK;
+}
+
+extern "C" int cnb_dw_deconv_up(const void* x, const float* wt, const void* add, void* y, int B, int H, int W,
+                                int C, int f, cnb_stream_t s) {
+  CNB_CHECK_ARG(x && wt && y && B >= 1 && H >= 1 && W >= 1, "dw_deconv_up: bad argument");
+  CNB_CHECK_ARG(C % 8 == 0 && f >= 1 && f % 2 == 0, "dw_deconv_up: C %% 8 == 0 and even upsampling factor required");
+  const long long total = (long long)B * H * f * W * f * (C / 8);
+  dw_deconv_kernel<<<grid_for(total), 256, 0, (cudaStream_t)s>>>((const __nv_bfloat16*)x, wt,
+                                                                 (const __nv_bfloat16*)add, (__nv_bfloat16*)y, B, H,
+                                                                 W, C, f);
+  CNB_LAUNCH_CHECK();
+  return CNB_OK;
+}

@@ -1,0 +1,60 @@
+"""Seeded synthetic inputs of the shapes SURVEY.md section 8(d) names (no dataset, no network).
+
+Heat maps are *tie-free by construction* (a per-image random permutation of distinct values)
+because ``torch.topk`` leaves the order of equal scores unspecified (SURVEY.md section 7,
+hard part 3) and bit-exact index parity is only defined on distinct scores.
+"""
+import numpy as np
+
+
+def distinct_uniform_heat(B, C, H, W, seed=1234, lo=0.0, hi=1.0):
+    """[B,C,H,W] float32, every image a permutation of N distinct values in (lo, hi)."""
+    rng = np.random.default_rng(seed)
+    N = C * H * W
+    base = (lo + (hi - lo) * (np.arange(1, N + 1, dtype=np.float64) / (N + 1))).astype(np.float32)
+    assert len(np.unique(base)) == N, "value grid collapses in float32; narrow the range"
+    out = np.empty((B, N), dtype=np.float32)
+    for b in range(B):
+        out[b] = base[rng.permutation(N)]
+    return out.reshape(B, C, H, W)
+
+
+def gaussian_bump_heat(B, C, H, W, n_obj=64, seed=1234, floor=0.05):
+    """COCO-shaped heat: <= n_obj Gaussian bumps per image (peak values distinct, < 1) drawn with
+    max-composition on a distinct-valued noise floor <= ``floor`` (cf. utils/gaussian.py:41-58)."""
+    rng = np.random.default_rng(seed)
+    heat = distinct_uniform_heat(B, C, H, W, seed=seed + 1, lo=0.0, hi=floor)
+    yy, xx = np.mgrid[0:H, 0:W]
+    for b in range(B):
+        peaks = 0.3 + 0.69 * (rng.permutation(n_obj) + 1.0) / (n_obj + 1.0)
+        for k in range(n_obj):
+            c = int(rng.integers(0, C))
+            cy, cx = int(rng.integers(0, H)), int(rng.integers(0, W))
+            rad = int(rng.integers(1, 8))
+            sigma = (2 * rad + 1) / 6.0
+            g = (peaks[k] * np.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / (2 * sigma * sigma))).astype(np.float32)
+            g[(np.abs(xx - cx) > rad) | (np.abs(yy - cy) > rad)] = 0
+            np.maximum(heat[b, c], g, out=heat[b, c])
+    return heat
+
+
+def ctdet_maps(B, C=80, H=128, W=128, seed=1234, kind="uniform"):
+    """(heat, wh, reg) for ``ctdet_decode`` -- SURVEY.md section 8(d) config 2."""
+    rng = np.random.default_rng(seed + 7)
+    heat = (distinct_uniform_heat(B, C, H, W, seed) if kind == "uniform"
+            else gaussian_bump_heat(B, C, H, W, seed=seed))
+    wh = (30.0 * rng.random((B, 2, H, W))).astype(np.float32)
+    reg = rng.random((B, 2, H, W)).astype(np.float32)
+    return heat, wh, reg
+
+
+def multi_pose_maps(B, J=17, H=128, W=128, seed=1234):
+    """(heat, wh, kps, reg, hm_hp, hp_offset) for ``multi_pose_decode`` -- config 5."""
+    rng = np.random.default_rng(seed + 11)
+    heat = distinct_uniform_heat(B, 1, H, W, seed)
+    hm_hp = distinct_uniform_heat(B, J, H, W, seed + 3)
+    wh = (30.0 * rng.random((B, 2, H, W))).astype(np.float32)
+    kps = (3.0 * rng.standard_normal((B, 2 * J, H, W))).astype(np.float32)
+    reg = rng.random((B, 2, H, W)).astype(np.float32)
+    hp_offset = rng.random((B, 2, H, W)).astype(np.float32)
+    return heat, wh, kps, reg, hm_hp, hp_offset

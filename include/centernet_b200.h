@@ -1,0 +1,175 @@
+/*
+ * centernet_b200 -- C ABI of the B200-native CenterNet hot path (libcenternet_b200.so).
+ *
+ * The reference (tteepe/CenterNet-pytorch-lightning) is pure Python and has no FFI of its own;
+ * its plugin surface is Python duck typing.  Each entry point below is what a
+ * ctypes binding for the corresponding reference function binds to (INTEGRATION.md shows the stubs).
+ *
+ * Conventions
+ *   - every pointer is a raw CUDA *device* pointer unless the function name ends in `_host`;
+ *   - the caller owns all memory (nothing is allocated inside, except by the `_host` variants which
+ *     keep a cached device staging arena per process);
+ *   - calls are stream-ordered and asynchronous on `stream` (a cudaStream_t; NULL = legacy default);
+ *   - stateless / re-entrant per stream; return 0 on success, a negative cnb_status otherwise, and
+ *     cnb_last_error() returns a thread-local message for the last failure; never exit()/abort();
+ *   - activations between conv layers are NHWC bf16; network input is NCHW fp32 and the head maps
+ *     handed to decode are NCHW fp32 (the contract of decode/ctdet.py:6).
+ */
+#ifndef CENTERNET_B200_H_
+#define CENTERNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* cnb_stream_t; /* cudaStream_t */
+
+enum cnb_status {
+  CNB_OK = 0,
+  CNB_ERR_INVALID = -1,   /* bad argument / unsupported shape */
+  CNB_ERR_WORKSPACE = -2, /* workspace too small */
+  CNB_ERR_CUDA = -3,      /* CUDA runtime error (message in cnb_last_error) */
+  CNB_ERR_NO_DEVICE = -4
+};
+
+int cnb_version(void);
+const char* cnb_last_error(void);
+/* number of kernels launched by this library in this process (bench.py's gpu_launches) */
+unsigned long long cnb_launch_count(void);
+
+/* ---------------------------------------------------------------- decode ------------------- */
+/* Replaces CenterNet/decode/ctdet.py:6-38 `ctdet_decode(heat, wh, reg=None, K=100)` including
+ * utils/decode.py:5-10 `_nms`, :13-28 `_topk`, :59-63 `_transpose_and_gather_feat`.
+ * heat [B,C,H,W] fp32 (already sigmoided, >= 0), wh/reg [B,2,H,W] fp32 (reg may be NULL -> +0.5),
+ * out [B,K,6] fp32 = (x1,y1,x2,y2,score,cls).  Ties: (score desc, flat index asc). */
+size_t cnb_ctdet_decode_workspace_bytes(int B, int C, int H, int W, int K);
+int cnb_ctdet_decode(const float* heat, const float* wh, const float* reg, float* out,
+                     int B, int C, int H, int W, int K,
+                     void* workspace, size_t workspace_bytes, cnb_stream_t stream);
+/* same, host buffers: H2D of the three maps, decode, D2H of out, synchronous on return */
+int cnb_ctdet_decode_host(const float* heat, const float* wh, const float* reg, float* out,
+                          int B, int C, int H, int W, int K);
+
+/* Replaces CenterNet/decode/multi_pose.py:7-96 `multi_pose_decode` (+ utils/decode.py:31-40
+ * `_topk_channel`).  heat [B,1,H,W], wh/reg/hp_offset [B,2,H,W], kps [B,2J,H,W], hm_hp [B,J,H,W];
+ * reg and hp_offset may be NULL (-> +0.5); hm_hp is required (the reference raises NameError without
+ * it, multi_pose.py:94).  out [B,K,3J+6] = bbox(4) score(1) kps(2J) cls(1) hm_score(J). */
+size_t cnb_multi_pose_decode_workspace_bytes(int B, int J, int H, int W, int K);
+int cnb_multi_pose_decode(const float* heat, const float* wh, const float* kps, const float* reg,
+                          const float* hm_hp, const float* hp_offset, float* out,
+                          int B, int J, int H, int W, int K,
+                          void* workspace, size_t workspace_bytes, cnb_stream_t stream);
+
+/* ---------------------------------------------------------------- losses ------------------- */
+/* Replaces utils/decode.py:43-45 `sigmoid_clamped` + utils/losses.py:14-39 `_neg_loss` (FocalLoss)
+ * forward AND backward in one pass over (logits, gt):
+ *   p = clamp(sigmoid(x), 1e-4, 1-1e-4);  loss = -(sum pos + sum neg)/num_pos  (or -sum neg).
+ * workspace: cnb_focal_loss_workspace_bytes(n) bytes (per-CTA partials; deterministic reduction).
+ * loss_out: 3 device floats = { loss, gnorm, num_pos } with gnorm = 1/num_pos (1 if num_pos == 0).
+ * If dlogits != NULL it receives the UNNORMALISED gradient g:  dloss/dlogits = g * gnorm  (num_pos is
+ * only known after the reduction; the caller folds gnorm into its upstream gradient, no host sync;
+ * the clamp passes zero gradient outside [1e-4, 1-1e-4], as torch.clamp does).  If prob_out != NULL
+ * the clamped sigmoid is written there (what the reference stores in output["heatmap"]).
+ * All pointers 16-byte aligned. */
+size_t cnb_focal_loss_workspace_bytes(long long n);
+int cnb_focal_loss_fwd_bwd(const float* logits, const float* gt, float* prob_out, float* dlogits,
+                           float* loss_out, long long n,
+                           void* workspace, size_t workspace_bytes, cnb_stream_t stream);
+/* pred already sigmoid-clamped: the literal FocalLoss()(pred, gt) call (losses.py:42-50);
+ * dpred (nullable) receives the unnormalised gradient as above. */
+int cnb_focal_loss_prob_fwd_bwd(const float* pred, const float* gt, float* dpred,
+                                float* loss_out, long long n,
+                                void* workspace, size_t workspace_bytes, cnb_stream_t stream);
+
+/* utils/decode.py:43-45 `sigmoid_clamped` on its own (the drop-in call made by
+ * centernet_detection.py:104): y = clamp(sigmoid(x), lo, hi); x may alias y (in place, like
+ * `x.sigmoid_()`); backward: dx = dy * y(1-y) where the clamp was inactive, else 0. */
+int cnb_sigmoid_clamped_fwd(const float* x, float* y, long long n, float lo, float hi,
+                            cnb_stream_t stream);
+int cnb_sigmoid_clamped_bwd(const float* y, const float* dy, float* dx, long long n, float lo,
+                            float hi, cnb_stream_t stream);
+
+/* Replaces utils/losses.py:53-63 `RegL1Loss` and :81-91 `RegWeightedL1Loss` forward+backward without
+ * the NCHW->NHWC copy of utils/decode.py:59-63.
+ * output [B,C,H,W] fp32; ind [B,M] int64 (each in [0,H*W)); target [B,M,C] fp32;
+ * mask: mask_per_channel==0 -> [B,M] uint8 (bool), expanded over C (denominator counts C*n);
+ *       mask_per_channel==1 -> [B,M,C] fp32 weights (RegWeightedL1Loss).
+ * loss_out: 1 device float.  If doutput != NULL it is zero-filled by this call and receives
+ * (*grad_scale_dev) * dloss/doutput (scatter-add; duplicate indices add); grad_scale_dev is a device
+ * scalar (NULL = 1) so that autograd's upstream gradient never needs a host sync. */
+int cnb_reg_l1_fwd_bwd(const float* output, const void* mask, const long long* ind,
+                       const float* target, float* doutput, float* loss_out,
+                       int B, int C, int H, int W, int M, int mask_per_channel,
+                       const float* grad_scale_dev, cnb_stream_t stream);
+
+/* ---------------------------------------------------------------- convolution engine ------- */
+/* Implicit-GEMM convolution on tcgen05 (bf16 x bf16 -> fp32 in TMEM), NHWC bf16 activations.
+ * Replaces nn.Conv2d + nn.BatchNorm2d(eval) + residual add + nn.ReLU chains of
+ * models/backbones/pose_dla_dcn.py:28-68 (BasicBlock), :165-188 (Root), :351-370, heads.py:4-25.
+ *   x    [B,Hi,Wi,Ci]  bf16 (Ci % 8 == 0), optionally a channel slice of a wider tensor (x_cstride)
+ *   wpk  packed weights from cnb_conv_pack_weights: [Co_pad][Kpad] bf16, K order (kh,kw,ci)
+ *   scale/shift [Co] fp32 applied to the fp32 accumulator (folded BN, or scale=1/shift=bias)
+ *   res  optional residual, same geometry as y (added before ReLU)
+ *   y    [B,Ho,Wo,Co] bf16 NHWC (y_cstride/y_coffset allow writing into a concat buffer), or
+ *        fp32 NCHW (out_nchw_f32 == 1, head maps) or fp32 NHWC (== 2); act: 0 none, 1 relu, 2 sigmoid.
+ * For Ci not a multiple of 8 (the 3-channel stem) pad the activation's channels with
+ * cnb_nchw_f32_to_nhwc_bf16(..., C_pad=8); cnb_conv_pack_weights pads the filter the same way. */
+typedef struct cnb_conv_desc {
+  int B, Hi, Wi, Ci;      /* input geometry */
+  int Co, KH, KW;         /* filter */
+  int stride, pad, dil;
+  int Ho, Wo;
+  int x_cstride;          /* channel stride (elements) between pixels of x; >= Ci */
+  int x_coffset;
+  int y_cstride;          /* channel stride of y / res (NHWC mode) */
+  int y_coffset;
+  int res_cstride;
+  int res_coffset;
+  int act;                /* 0 none, 1 relu, 2 sigmoid */
+  int out_nchw_f32;       /* output format: 0 NHWC bf16, 1 NCHW fp32 (head maps), 2 NHWC fp32 (DCN offsets) */
+} cnb_conv_desc;
+
+size_t cnb_conv_packed_weight_bytes(int Co, int Ci, int KH, int KW);
+/* w: [Co,Ci,KH,KW] fp32 (PyTorch layout, device) -> wpk bf16 device */
+int cnb_conv_pack_weights(const float* w, void* wpk, int Co, int Ci, int KH, int KW,
+                          cnb_stream_t stream);
+int cnb_conv2d_fprop(const cnb_conv_desc* d, const void* x, const void* wpk, const float* scale,
+                     const float* shift, const void* res, void* y, cnb_stream_t stream);
+
+/* Modulated deformable convolution v2 (DCN.dcn_v2.DCN forward; call sites pose_dla_dcn.py:441-449,
+ * resnet_dcn.py:202-210): 3x3, stride 1, pad 1, dil 1, deformable_groups 1.
+ *   om [B,H,W,om_cstride] fp32 NHWC holds the 27 raw channels of the conv_offset_mask conv (run it
+ *   through cnb_conv2d_fprop with out_nchw_f32 == 2).  DCNv2 does o1,o2,mask = chunk(om,3);
+ *   offset = cat(o1,o2) = channels 0..17, so tap k samples at (dy,dx) = (ch 2k, ch 2k+1) and is
+ *   modulated by sigmoid(ch 18+k); samples outside (-1,H)x(-1,W) are 0.
+ * The bilinear sampler writes the A operand tile directly into shared memory; same epilogue as conv. */
+int cnb_dcnv2_fprop(const cnb_conv_desc* d, const void* x, const float* om, int om_cstride,
+                    const void* wpk, const float* scale, const float* shift, void* y,
+                    cnb_stream_t stream);
+
+/* ---------------------------------------------------------------- memory-bound layer ops --- */
+/* MaxPool2d(k, stride=k) NHWC bf16 (pose_dla_dcn.py:243); channel-slice addressing on both sides so that
+ * the pooled map can be written straight into a Root concat buffer (pose_dla_dcn.py:182). */
+int cnb_maxpool2d(const void* x, void* y, int B, int H, int W, int C, int x_cstride, int x_coffset,
+                  int y_cstride, int y_coffset, int k, cnb_stream_t stream);
+/* depthwise ConvTranspose2d(C,C,2f,stride=f,padding=f/2,groups=C,bias=False) (pose_dla_dcn.py:466-475).
+ * w [C,1,2f,2f] fp32 is first re-laid-out to wt [(2f)^2][C] fp32; then y = up(x) (+ add if add != NULL:
+ * fuses `layers[i] + layers[i-1]`, pose_dla_dcn.py:488).  x [B,H,W,C], y/add [B,H*f,W*f,C] NHWC bf16. */
+int cnb_dw_deconv_relayout_weights(const float* w, float* wt, int C, int f, cnb_stream_t stream);
+int cnb_dw_deconv_up(const void* x, const float* wt, const void* add, void* y, int B, int H, int W,
+                     int C, int f, cnb_stream_t stream);
+/* layout changes at the two ends of the NHWC bf16 engine: network input [B,C,H,W] fp32 -> NHWC bf16 with
+ * channels zero-padded to C_pad (3 -> 8 for the 7x7 stem, pose_dla_dcn.py:281-285); a channel slice of an
+ * NHWC bf16 map -> NCHW fp32 (the backbone output contract). */
+int cnb_nchw_f32_to_nhwc_bf16(const float* x, void* y, int B, int C, int H, int W, int C_pad,
+                              cnb_stream_t stream);
+int cnb_nhwc_bf16_to_nchw_f32(const void* x, float* y, int B, int C, int H, int W, int x_cstride,
+                              int x_coffset, cnb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CENTERNET_B200_H_ */
