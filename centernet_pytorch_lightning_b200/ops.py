@@ -1,0 +1,190 @@
+"""Thin torch-tensor wrappers over the conv-engine entry points of the C ABI (include/centernet_b200.h).
+
+Activations are NHWC bf16 torch tensors; a `View` names a channel slice of a (possibly wider) NHWC
+buffer so that `torch.cat` along channels (Root, pose_dla_dcn.py:182) never has to be materialised.
+Everything is asynchronous on the current CUDA stream; torch owns all memory.
+"""
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc
+
+
+@dataclass
+class View:
+    """Channels [coffset, coffset + C) of an NHWC bf16 buffer [B,H,W,cstride]."""
+    buf: torch.Tensor
+    C: int
+    coffset: int = 0
+
+    @property
+    def B(self):
+        return self.buf.shape[0]
+
+    @property
+    def H(self):
+        return self.buf.shape[1]
+
+    @property
+    def W(self):
+        return self.buf.shape[2]
+
+    @property
+    def cstride(self):
+        return self.buf.shape[3]
+
+    def tensor(self):
+        return self.buf[..., self.coffset:self.coffset + self.C]
+
+
+def as_view(x) -> View:
+    if isinstance(x, View):
+        return x
+    assert x.dim() == 4 and x.dtype == torch.bfloat16 and x.is_contiguous()
+    return View(x, x.shape[3], 0)
+
+
+def _stream(t):
+    return _lib.stream_ptr(t.device)
+
+
+def to_nhwc_bf16(x, c_pad: Optional[int] = None):
+    """[B,C,H,W] fp32 -> [B,H,W,c_pad] bf16 (channels zero-padded to a multiple of 8)."""
+    _lib.require_cuda(x)
+    x = x.float().contiguous()
+    B, C, H, W = x.shape
+    c_pad = c_pad or (C + 7) // 8 * 8
+    y = torch.empty((B, H, W, c_pad), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().cnb_nchw_f32_to_nhwc_bf16(_lib.ptr(x), _lib.ptr(y), B, C, H, W, c_pad, _stream(x)),
+                   "cnb_nchw_f32_to_nhwc_bf16")
+    return y
+
+
+def to_nchw_f32(v):
+    v = as_view(v)
+    y = torch.empty((v.B, v.C, v.H, v.W), dtype=torch.float32, device=v.buf.device)
+    with torch.cuda.device(v.buf.device):
+        _lib.check(_lib.lib().cnb_nhwc_bf16_to_nchw_f32(_lib.ptr(v.buf), _lib.ptr(y), v.B, v.C, v.H, v.W,
+                                                         v.cstride, v.coffset, _stream(y)),
+                   "cnb_nhwc_bf16_to_nchw_f32")
+    return y
+
+
+def pack_conv_weights(w):
+    """[Co,Ci,KH,KW] fp32 -> packed bf16 [Co_pad][Kpad] (K order kh,kw,ci; Ci padded to 8)."""
+    _lib.require_cuda(w)
+    w = w.detach().float().contiguous()
+    Co, Ci, KH, KW = w.shape
+    L = _lib.lib()
+    nbytes = L.cnb_conv_packed_weight_bytes(Co, Ci, KH, KW)
+    out = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
+    with torch.cuda.device(w.device):
+        _lib.check(L.cnb_conv_pack_weights(_lib.ptr(w), _lib.ptr(out), Co, Ci, KH, KW, _stream(w)),
+                   "cnb_conv_pack_weights")
+    return out
+
+
+def _out_geometry(H, W, k, stride, pad, dil=1):
+    return (H + 2 * pad - dil * (k - 1) - 1) // stride + 1, (W + 2 * pad - dil * (k - 1) - 1) // stride + 1
+
+
+def _make_desc(x: View, Co, k, stride, pad, dil, Ho, Wo, out_mode, act, y_cstride, y_coffset, res: Optional[View]):
+    d = ConvDesc()
+    d.B, d.Hi, d.Wi, d.Ci = x.B, x.H, x.W, x.C
+    d.Co, d.KH, d.KW = Co, k, k
+    d.stride, d.pad, d.dil = stride, pad, dil
+    d.Ho, d.Wo = Ho, Wo
+    d.x_cstride, d.x_coffset = x.cstride, x.coffset
+    d.y_cstride, d.y_coffset = y_cstride, y_coffset
+    d.res_cstride, d.res_coffset = (res.cstride, res.coffset) if res is not None else (0, 0)
+    d.act, d.out_nchw_f32 = act, out_mode
+    return d
+
+
+def _alloc_out(x: View, Co, Ho, Wo, out_mode, out):
+    dev = x.buf.device
+    if out is not None:
+        out = as_view(out) if out_mode == 0 else out
+        return out
+    if out_mode == 0:
+        return View(torch.empty((x.B, Ho, Wo, Co), dtype=torch.bfloat16, device=dev), Co, 0)
+    if out_mode == 1:
+        return torch.empty((x.B, Co, Ho, Wo), dtype=torch.float32, device=dev)
+    cs = (Co + 15) // 16 * 16
+    return torch.empty((x.B, Ho, Wo, cs), dtype=torch.float32, device=dev)
+
+
+def conv2d(x, wpk, Co, k, stride, pad, scale, shift, res=None, act=0, out_mode=0, out=None, dil=1):
+    """y = act(conv(x, w) * scale + shift (+ res)).  out_mode 0: NHWC bf16 (returns the tensor, or writes the
+    `out` View), 1: NCHW fp32, 2: NHWC fp32 (channel stride rounded up to 16)."""
+    x = as_view(x)
+    res = as_view(res) if res is not None else None
+    Ho, Wo = _out_geometry(x.H, x.W, k, stride, pad, dil)
+    o = _alloc_out(x, Co, Ho, Wo, out_mode, out)
+    if out_mode == 0:
+        y_cs, y_co, y_ptr = o.cstride, o.coffset, _lib.ptr(o.buf)
+    elif out_mode == 1:
+        y_cs, y_co, y_ptr = 0, 0, _lib.ptr(o)
+    else:
+        y_cs, y_co, y_ptr = o.shape[3], 0, _lib.ptr(o)
+    d = _make_desc(x, Co, k, stride, pad, dil, Ho, Wo, out_mode, act, y_cs, y_co, res)
+    with torch.cuda.device(x.buf.device):
+        _lib.check(_lib.lib().cnb_conv2d_fprop(d, _lib.ptr(x.buf), _lib.ptr(wpk), _lib.ptr(scale), _lib.ptr(shift),
+                                                _lib.ptr(res.buf) if res is not None else None, y_ptr,
+                                                _stream(x.buf)), "cnb_conv2d_fprop")
+    if out_mode == 0:
+        return o.buf if (out is None) else o
+    return o
+
+
+def dcnv2(x, om, wpk, Co, scale, shift, act=0, out=None):
+    """Modulated deformable 3x3 conv: x NHWC bf16, om [B,H,W,>=27] fp32 NHWC raw offset/mask channels."""
+    x = as_view(x)
+    assert om.dtype == torch.float32 and om.is_contiguous() and om.shape[:3] == (x.B, x.H, x.W)
+    o = _alloc_out(x, Co, x.H, x.W, 0, out)
+    d = _make_desc(x, Co, 3, 1, 1, 1, x.H, x.W, 0, act, o.cstride, o.coffset, None)
+    with torch.cuda.device(x.buf.device):
+        _lib.check(_lib.lib().cnb_dcnv2_fprop(d, _lib.ptr(x.buf), _lib.ptr(om), om.shape[3], _lib.ptr(wpk),
+                                               _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(o.buf), _stream(x.buf)),
+                   "cnb_dcnv2_fprop")
+    return o.buf if out is None else o
+
+
+def maxpool2d(x, k, out=None):
+    x = as_view(x)
+    Ho, Wo = x.H // k, x.W // k
+    o = as_view(out) if out is not None else View(
+        torch.empty((x.B, Ho, Wo, x.C), dtype=torch.bfloat16, device=x.buf.device), x.C, 0)
+    with torch.cuda.device(x.buf.device):
+        _lib.check(_lib.lib().cnb_maxpool2d(_lib.ptr(x.buf), _lib.ptr(o.buf), x.B, x.H, x.W, x.C, x.cstride,
+                                             x.coffset, o.cstride, o.coffset, k, _stream(x.buf)), "cnb_maxpool2d")
+    return o.buf if out is None else o
+
+
+def relayout_dw_weights(w, f):
+    """[C,1,2f,2f] fp32 -> [(2f)^2, C] fp32 for `dw_deconv_up`."""
+    w = w.detach().float().contiguous()
+    C = w.shape[0]
+    wt = torch.empty((4 * f * f, C), dtype=torch.float32, device=w.device)
+    with torch.cuda.device(w.device):
+        _lib.check(_lib.lib().cnb_dw_deconv_relayout_weights(_lib.ptr(w), _lib.ptr(wt), C, f, _stream(w)),
+                   "cnb_dw_deconv_relayout_weights")
+    return wt
+
+
+def dw_deconv_up(x, wt, f, add=None, out=None):
+    """Depthwise ConvTranspose2d(2f, stride f, pad f/2) (+ add); x / add / out dense NHWC bf16."""
+    x = as_view(x)
+    assert x.coffset == 0 and x.cstride == x.C, "dw_deconv_up needs a dense NHWC input"
+    y = out if out is not None else torch.empty((x.B, x.H * f, x.W * f, x.C), dtype=torch.bfloat16,
+                                                device=x.buf.device)
+    if add is not None:
+        assert add.shape == y.shape and add.is_contiguous()
+    with torch.cuda.device(x.buf.device):
+        _lib.check(_lib.lib().cnb_dw_deconv_up(_lib.ptr(x.buf), _lib.ptr(wt), _lib.ptr(add), _lib.ptr(y), x.B, x.H,
+                                                x.W, x.C, f, _stream(x.buf)), "cnb_dw_deconv_up")
+    return y

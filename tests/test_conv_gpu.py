@@ -1,0 +1,165 @@
+"""-m gpu parity: tcgen05 implicit-GEMM convolution, DCNv2 and the memory-bound layer ops.
+
+Floating point: operands are bf16 (rounded identically for the kernel and the reference), the
+accumulation is fp32 in both; the reference is plain PyTorch fp32 (TF32 disabled in conftest) on
+the bf16-rounded operands.  Tolerance: |err| <= 2e-2 * max|ref| for bf16 outputs (one bf16 rounding
+of the result = 2^-9 relative, plus summation-order noise), 2e-3 for fp32 outputs.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from centernet_pytorch_lightning_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+def _check(got, ref, tol):
+    err = (got.float() - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-6
+    assert err <= tol * scale, f"max err {err} vs scale {scale}"
+
+
+CONV_CASES = [
+    # B, Ci, Co, H, W, k, stride, relu, residual
+    (2, 64, 64, 32, 32, 3, 1, True, False),
+    (2, 64, 64, 32, 32, 3, 1, True, True),
+    (1, 16, 16, 64, 64, 3, 1, True, False),      # Ci=16: 4 taps per 64-wide K block
+    (2, 16, 32, 64, 64, 3, 2, True, False),      # stride 2
+    (2, 128, 128, 16, 16, 3, 1, True, True),
+    (1, 512, 512, 16, 16, 3, 1, False, False),   # 4 N tiles, 72 K blocks
+    (2, 256, 128, 16, 16, 1, 1, True, False),    # 1x1 (Root)
+    (1, 448, 128, 8, 8, 1, 1, True, True),       # Root with odd concat width
+    (3, 64, 80, 20, 28, 3, 1, False, False),     # ragged M (tail tile) and Co=80
+    (1, 8, 16, 40, 40, 7, 1, True, False),       # stem geometry: 7x7 on a channel-padded input
+    (1, 32, 27, 24, 24, 3, 1, False, False),     # Co=27 (offset/mask conv) -> NHWC fp32
+]
+
+
+@pytest.mark.parametrize("B,Ci,Co,H,W,k,stride,relu,residual", CONV_CASES)
+def test_conv_matches_torch(cuda_dev, B, Ci, Co, H, W, k, stride, relu, residual):
+    g = torch.Generator(device="cpu").manual_seed(Ci * 1000 + Co + k)
+    x = _bf(torch.randn(B, Ci, H, W, generator=g)).to(cuda_dev)
+    w = _bf(torch.randn(Co, Ci, k, k, generator=g) / (Ci * k * k) ** 0.5).to(cuda_dev)
+    scale = (0.5 + torch.rand(Co, generator=g)).to(cuda_dev)
+    shift = torch.randn(Co, generator=g).to(cuda_dev)
+    pad = k // 2
+    ref = F.conv2d(x, w, stride=stride, padding=pad) * scale[None, :, None, None] + shift[None, :, None, None]
+    Ho, Wo = ref.shape[2:]
+    res = None
+    if residual:
+        res = _bf(torch.randn(B, Co, Ho, Wo, generator=g)).to(cuda_dev)
+        ref = ref + res
+    if relu:
+        ref = ref.relu()
+    xn = ops.to_nhwc_bf16(x)
+    wpk = ops.pack_conv_weights(w)
+    fp32_out = Co % 8 != 0
+    y = ops.conv2d(xn, wpk, Co, k, stride, pad, scale, shift,
+                   res=ops.to_nhwc_bf16(res) if residual else None, act=1 if relu else 0,
+                   out_mode=2 if fp32_out else 0)
+    torch.cuda.synchronize()
+    got = y[..., :Co].permute(0, 3, 1, 2)
+    _check(got, ref, 2e-3 if fp32_out else 2e-2)
+
+
+def test_conv_concat_slices(cuda_dev):
+    """Reading / writing channel slices of wider NHWC buffers (Root's torch.cat without the copy)."""
+    g = torch.Generator().manual_seed(7)
+    B, H, W = 2, 16, 16
+    xa = _bf(torch.randn(B, 64, H, W, generator=g)).to(cuda_dev)
+    w = _bf(torch.randn(32, 64, 3, 3, generator=g) / 24).to(cuda_dev)
+    wide_in = torch.zeros(B, H, W, 160, dtype=torch.bfloat16, device=cuda_dev)
+    wide_in[..., 96:160] = ops.to_nhwc_bf16(xa)
+    wide_out = torch.full((B, H, W, 96), 7.0, dtype=torch.bfloat16, device=cuda_dev)
+    ops.conv2d(ops.View(wide_in, 64, 96), ops.pack_conv_weights(w), 32, 3, 1, 1, None, None, act=0,
+               out=ops.View(wide_out, 32, 64))
+    torch.cuda.synchronize()
+    ref = F.conv2d(xa, w, padding=1)
+    _check(wide_out[..., 64:96].permute(0, 3, 1, 2), ref, 2e-2)
+    assert torch.all(wide_out[..., :64] == 7.0)      # untouched outside the slice
+
+
+def test_conv_nchw_f32_head_output(cuda_dev):
+    g = torch.Generator().manual_seed(9)
+    B, H, W = 2, 32, 32
+    x = _bf(torch.randn(B, 256, H, W, generator=g)).to(cuda_dev)
+    w = _bf(torch.randn(80, 256, 1, 1, generator=g) / 16).to(cuda_dev)
+    bias = torch.randn(80, generator=g).to(cuda_dev)
+    y = ops.conv2d(ops.to_nhwc_bf16(x), ops.pack_conv_weights(w), 80, 1, 1, 0, None, bias, act=0, out_mode=1)
+    torch.cuda.synchronize()
+    assert y.shape == (B, 80, H, W) and y.dtype == torch.float32
+    _check(y, F.conv2d(x, w, bias), 2e-3)
+    ys = ops.conv2d(ops.to_nhwc_bf16(x), ops.pack_conv_weights(w), 80, 1, 1, 0, None, bias, act=2, out_mode=1)
+    _check(ys, torch.sigmoid(F.conv2d(x, w, bias)), 2e-3)
+
+
+@pytest.mark.parametrize("B,Ci,Co,H,W", [(2, 64, 64, 24, 24), (1, 128, 64, 16, 20), (1, 256, 256, 8, 8)])
+def test_dcnv2_matches_torchvision(cuda_dev, B, Ci, Co, H, W):
+    """DCN numerics are 'parity unpinned' by the reference (external extension); the pin is
+    torchvision.ops.deform_conv2d on CPU fp32 with the same bf16-rounded operands."""
+    from torchvision.ops import deform_conv2d
+    g = torch.Generator().manual_seed(Ci + Co)
+    x = _bf(torch.randn(B, Ci, H, W, generator=g))
+    w = _bf(torch.randn(Co, Ci, 3, 3, generator=g) / (Ci * 9) ** 0.5)
+    bias = torch.randn(Co, generator=g)
+    om = torch.randn(B, 27, H, W, generator=g) * 1.5          # offsets up to a few pixels, some out of range
+    om[:, :18, 0, 0] = 50.0                                     # far outside -> zero contribution
+    o1, o2, m = torch.chunk(om, 3, dim=1)
+    ref = deform_conv2d(x, torch.cat((o1, o2), 1), w, bias, padding=1, mask=torch.sigmoid(m))
+    om_nhwc = torch.zeros(B, H, W, 32)
+    om_nhwc[..., :27] = om.permute(0, 2, 3, 1)
+    y = ops.dcnv2(ops.to_nhwc_bf16(x.to(cuda_dev)), om_nhwc.to(cuda_dev).contiguous(),
+                  ops.pack_conv_weights(w.to(cuda_dev)), Co, None, bias.to(cuda_dev), act=0)
+    torch.cuda.synchronize()
+    _check(y.permute(0, 3, 1, 2).cpu(), ref, 2e-2)
+
+
+def test_dcn_module_matches_torchvision(cuda_dev):
+    """The drop-in `DCN.dcn_v2.DCN` module end to end (offset conv + sampler + GEMM) with non-zero
+    conv_offset_mask weights (zero init would make DCN == 0.5 * conv)."""
+    from torchvision.ops import deform_conv2d
+    from centernet_pytorch_lightning_b200.DCN.dcn_v2 import DCN
+    torch.manual_seed(5)
+    m = DCN(64, 64, kernel_size=(3, 3), stride=1, padding=1, dilation=1, deformable_groups=1)
+    m.conv_offset_mask.weight.data.normal_(0, 0.05)
+    m.conv_offset_mask.bias.data.uniform_(-1, 1)
+    m.bias.data.normal_()
+    x = _bf(torch.randn(2, 64, 20, 20))
+    with torch.no_grad():
+        wq, omq = _bf(m.weight), _bf(m.conv_offset_mask.weight)
+        om = F.conv2d(x, omq, m.conv_offset_mask.bias, padding=1)
+        o1, o2, mk = torch.chunk(om, 3, dim=1)
+        ref = deform_conv2d(x, torch.cat((o1, o2), 1), wq, m.bias, padding=1, mask=torch.sigmoid(mk))
+        got = m.to(cuda_dev).eval()(x.to(cuda_dev))
+    _check(got.cpu(), ref, 3e-2)
+
+
+def test_maxpool_and_upsample(cuda_dev):
+    g = torch.Generator().manual_seed(3)
+    x = _bf(torch.randn(2, 64, 16, 24, generator=g)).to(cuda_dev)
+    xn = ops.to_nhwc_bf16(x)
+    got = ops.maxpool2d(xn, 2)
+    assert torch.equal(got.permute(0, 3, 1, 2).float(), F.max_pool2d(x, 2, 2))
+    for f in (2, 4):
+        w = torch.randn(64, 1, 2 * f, 2 * f, generator=g).to(cuda_dev)
+        add = _bf(torch.randn(2, 64, 16 * f, 24 * f, generator=g)).to(cuda_dev)
+        ref = F.conv_transpose2d(x, w, stride=f, padding=f // 2, groups=64) + add
+        got = ops.dw_deconv_up(xn, ops.relayout_dw_weights(w, f), f, add=ops.to_nhwc_bf16(add))
+        _check(got.permute(0, 3, 1, 2), ref, 1e-2)
+        got = ops.dw_deconv_up(xn, ops.relayout_dw_weights(w, f), f)
+        _check(got.permute(0, 3, 1, 2), ref - add, 1e-2)
+
+
+def test_layout_roundtrip(cuda_dev):
+    x = _bf(torch.randn(2, 3, 10, 12)).to(cuda_dev)
+    xn = ops.to_nhwc_bf16(x, c_pad=8)
+    assert xn.shape == (2, 10, 12, 8)
+    assert torch.equal(xn[..., :3].permute(0, 3, 1, 2).float(), x) and torch.all(xn[..., 3:] == 0)
+    back = ops.to_nchw_f32(ops.View(xn, 3, 0))
+    assert torch.equal(back, x)
