@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of the hot path on synthetic 512x512 COCO-shaped batches (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+
+One step = one pass of the hot path over one batch: DLA-34 backbone (+16 DCNv2) -> ctdet heads (sigmoid
+fused into the heat-map head epilogue) -> fused ctdet_decode, batch 32 per GPU, 512x512 (configs[1]).
+Weak scaling: every rank processes its own 32-image batch, no data-path collective.
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput (CUDA events, max over ranks);
+`e2e` = the same through the public API with pinned-host inputs copied H2D every step and the
+detections read back D2H every step; `roofline` = the tcgen05 conv/DCN kernel family (tensor bound)
+with per-launch CUDA-event timing; `roofline_decode` = the fused decode kernel (HBM bound);
+`cpu_baseline` = the CPU oracle (a port of the reference's PyTorch path) on this box's host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 32
+RES = 512
+HEADS = {"heatmap": 80, "width_height": 2, "regression": 2}
+METRIC = "images/sec @512x512 DLA-34 ctdet (fwd + fused decode)"
+WORKLOAD = "DLA-34 ctdet inference, batch=32/GPU, 512x512 synthetic, fwd+sigmoid+ctdet_decode (configs[1])"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            p = json.load(fh)
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sust=p["bf16_tflops_sustained"], src="measured")
+    except Exception:
+        return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_step(sd, hd, x):
+    """The reference's CPU path for this workload (oracle port): forward, sigmoid_, ctdet_decode."""
+    import torch
+    from oracle import decode_np, net_torch
+    with torch.no_grad():
+        o = net_torch.center_head_forward(hd, net_torch.dla34_seg_forward(sd, x), HEADS)
+        heat = o["heatmap"].sigmoid_()
+    return decode_np.ctdet_decode(heat.numpy(), o["width_height"].numpy(), o["regression"].numpy())
+
+
+def seeded_weights(seed=1234):
+    import torch
+    from centernet_pytorch_lightning_b200.models import create_model
+    from centernet_pytorch_lightning_b200.models.heads import CenterHead
+    from centernet_pytorch_lightning_b200.utils.synthetic import randomize_
+    torch.manual_seed(seed)
+    model, head = create_model("dla_34"), CenterHead(HEADS, 64, 256)
+    randomize_(model.state_dict(), seed)
+    randomize_(head.state_dict(), seed + 1)
+    return model.eval(), head.eval()
+
+
+def time_cpu(sample_batch, reps, warmup):
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    model, head = seeded_weights()
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    hd = {k: v.clone() for k, v in head.state_dict().items()}
+    x = torch.rand(sample_batch, 3, RES, RES, generator=torch.Generator().manual_seed(1))
+    for _ in range(warmup):
+        cpu_reference_step(sd, hd, x)
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        cpu_reference_step(sd, hd, x)
+        ts.append(time.perf_counter() - t0)
+    return ts, torch.get_num_threads()
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    sample = 2
+    ts, threads = time_cpu(sample, max(args.steps, 1), args.warmup)
+    mean_t = sum(ts) / len(ts)
+    value = sample / mean_t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": args.gpus,
+        "steps": len(ts), "warmup": args.warmup, "ms_per_step": mean_t * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": f"{sample} images per step on host cores (CPU path does not batch-scale)"},
+        "cpu_baseline": {"value": value, "unit": "images/sec", "cores": threads, "kind": "port",
+                         "sample": f"oracle port of the reference CPU path (PyTorch fp32 + torchvision deform_conv2d + numpy decode), "
+                                   f"{sample} images/step, {len(ts)} steps"},
+        "e2e": {"value": value, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_b200(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+
+    from centernet_pytorch_lightning_b200 import _lib, build, ops
+    from centernet_pytorch_lightning_b200.decode import ctdet_decode
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback in the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        build.build()
+    if world > 1:
+        dist.barrier()
+    _lib.lib()
+
+    model, head = seeded_weights()
+    model, head = model.to(dev), head.to(dev)
+    g = torch.Generator().manual_seed(100 + rank)
+    x_host = [torch.rand(BATCH, 3, RES, RES, generator=g).pin_memory() for _ in range(2)]
+    x_dev = [t.to(dev) for t in x_host]
+    det_host = torch.empty(BATCH, 100, 6).pin_memory()
+
+    def step(x):
+        with torch.no_grad():
+            feat = model(x)
+            o = head(feat[-1], sigmoid=("heatmap",))
+            return ctdet_decode(o["heatmap"], o["width_height"], reg=o["regression"]), o
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident throughput ------------------------------------------------------------------
+    for i in range(args.warmup):
+        step(x_dev[i % 2])
+    sync_all()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = _lib.launch_count()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        det, _ = step(x_dev[i % 2])
+    e1.record()
+    sync_all()
+    launches = _lib.launch_count() - launches0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = ms.item()
+    clocks = sampler.stop() if sampler else None
+    value = world * BATCH * args.steps / (ms_total / 1e3)
+
+    # ---- end to end: pinned host input H2D every step (prefetched on a copy stream), detections D2H -------
+    copy_stream = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+    copied = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[i % 2])
+            x_dev[i % 2].copy_(x_host[i % 2], non_blocking=True)
+            copied[i % 2].record(copy_stream)
+
+    for ev in consumed:
+        ev.record(main)
+    n_e2e = args.steps
+    prefetch(0)
+    sync_all()
+    t0 = time.perf_counter()
+    for i in range(n_e2e):
+        prefetch(i + 1)
+        main.wait_event(copied[i % 2])
+        det, _ = step(x_dev[i % 2])
+        consumed[i % 2].record(main)
+        det_host.copy_(det, non_blocking=True)
+        main.synchronize()                      # the caller reads this step's detections
+    sync_all()
+    t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = world * BATCH * n_e2e / t_e2e.item()
+    h2d = BATCH * 3 * RES * RES * 4
+    d2h = BATCH * 100 * 6 * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel family (rank 0): per-launch CUDA events, live -------------------
+    pk = peaks()
+    with ops.LaunchProfiler() as prof:
+        for i in range(2):
+            step(x_dev[i % 2])
+    conv_ms, conv_fl, n_conv = prof.summary()
+    conv_ms, conv_fl, n_conv = conv_ms / 2, conv_fl / 2, n_conv // 2
+    tf = conv_fl / (conv_ms * 1e-3) / 1e12
+    dcn_ms, dcn_fl, n_dcn = prof.summary("dcn")
+    roofline = {"bound": "tensor", "kernel": "conv_umma_kernel (tcgen05 implicit GEMM, conv + DCNv2 modes)",
+                "achieved": tf, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": tf / pk["tf_sust"],
+                "traffic": None, "peak_source": pk["src"] + " (sustained bf16, kernel timed inside a long step)",
+                "launches_per_step": n_conv, "kernel_ms_per_step": conv_ms, "flops_per_step": conv_fl,
+                "share_of_step": conv_ms / (ms_total / args.steps),
+                "dcn_ms_per_step": dcn_ms / 2, "dcn_tflops": (dcn_fl / 2) / (dcn_ms / 2 * 1e-3) / 1e12 if dcn_ms else None}
+    # decode alone on resident head maps
+    _, o = step(x_dev[0])
+    hm, wh, rg = o["heatmap"], o["width_height"], o["regression"]
+    for _ in range(3):
+        ctdet_decode(hm, wh, reg=rg)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    dts = []
+    for _ in range(10):
+        flush.fill_(1)                                 # evict L2 (256 MB > 126 MB)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ctdet_decode(hm, wh, reg=rg)
+        b.record()
+        torch.cuda.synchronize()
+        dts.append(a.elapsed_time(b))
+    dec_ms = statistics.median(dts)
+    dec_bytes = BATCH * (80 * 128 * 128 * 4 + 100 * 16 + 100 * 24)
+    dec_gbs = dec_bytes / (dec_ms * 1e-3) / 1e9
+    roofline_decode = {"bound": "hbm", "kernel": "plane_scan_kernel<4,true> (fused nms+topk+gather)",
+                       "achieved": dec_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": dec_gbs / pk["hbm"],
+                       "traffic": None, "ms": dec_ms, "bytes_per_launch": dec_bytes, "peak_source": pk["src"],
+                       "l2": "flushed (256 MB write) before every timed launch"}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        ts, threads = time_cpu(2, 2, 1)
+        cpu = {"value": 2 / min(ts), "unit": "images/sec", "cores": threads, "kind": "port",
+               "sample": "2 images 512x512, fwd+sigmoid+decode on host cores, best of 2 after 1 warm-up "
+                         "(oracle port of the reference CPU path)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "parallelism": f"dp{world} (independent images, no collective)",
+                   "l2": "inputs rotate over 2 buffers (201 MB > 126 MB L2); ~9 GB of activations per step",
+                   "weights": "seeded random init (He-normal convs, perturbed BN stats, non-zero DCN offsets)",
+                   "accumulate": "fp32 (TMEM)"},
+        "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "how": "pinned host batch -> H2D on a copy stream (prefetch depth 1) -> model() -> CenterHead -> ctdet_decode -> D2H + sync every step"},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": roofline, "roofline_decode": roofline_decode, "cpu_baseline": cpu,
+        "img_per_s_ceiling_conv_roofline": 16288.0 * world,
+        "frac_of_conv_roofline": value / (16288.0 * world),
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run on one node
+        port = 29500 + os.getpid() % 2000
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__),
+               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
+        raise SystemExit(subprocess.call(cmd))
+    run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

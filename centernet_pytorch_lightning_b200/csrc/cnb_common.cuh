@@ -80,8 +80,11 @@ __device__ __forceinline__ bool mbar_try_wait(void* bar, u32 parity) {
       : "memory");
   return ok != 0;
 }
+// Bounded spin: a lost arrival traps (-> CUDA error on the host) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(void* bar, u32 parity) {
+  u32 spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 27)) __trap();
   }
 }
 // 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP); bytes % 16 == 0, 16B-aligned.

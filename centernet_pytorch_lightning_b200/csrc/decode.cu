@@ -650,9 +650,9 @@ using namespace cnb;
 extern "C" size_t cnb_ctdet_decode_workspace_bytes(int B, int C, int H, int W, int K) {
   ScanGeom g;
   if (B < 1 || C < 1 || K < 1 || K > MAX_K || !plan_scan(H, W, K, true, &g)) return 0;
-  ScanGeom g1;
-  plan_scan(H, W, K, false, &g1);  // unaligned fallback may band differently; take the larger
-  const size_t a = ws_layout(B, C, g).total, b = ws_layout(B, C, g1).total;
+  ScanGeom g1;   // the unaligned (scalar) fallback may band differently; take the larger of the two
+  const size_t a = ws_layout(B, C, g).total;
+  const size_t b = plan_scan(H, W, K, false, &g1) ? ws_layout(B, C, g1).total : 0;
   return a > b ? a : b;
 }
 
@@ -699,8 +699,8 @@ extern "C" size_t cnb_multi_pose_decode_workspace_bytes(int B, int J, int H, int
   ScanGeom g;
   if (B < 1 || J < 1 || K < 1 || K > MAX_K || !plan_scan(H, W, K, true, &g)) return 0;
   ScanGeom g1;
-  plan_scan(H, W, K, false, &g1);
-  const size_t a = ws_layout(B, 1 + J, g).total, b = ws_layout(B, 1 + J, g1).total;
+  const size_t a = ws_layout(B, 1 + J, g).total;
+  const size_t b = plan_scan(H, W, K, false, &g1) ? ws_layout(B, 1 + J, g1).total : 0;
   return a > b ? a : b;
 }
 

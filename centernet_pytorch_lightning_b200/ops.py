@@ -51,6 +51,37 @@ def _stream(t):
     return _lib.stream_ptr(t.device)
 
 
+class LaunchProfiler:
+    """Optional per-launch CUDA-event timing of the tensor-core kernels (bench.py's roofline leg).
+    `with LaunchProfiler() as p: model(x)` then `p.summary()` -> (total_ms, total_flops, n_launches)."""
+    active = None
+
+    def __init__(self):
+        self.records = []
+
+    def __enter__(self):
+        LaunchProfiler.active = self
+        return self
+
+    def __exit__(self, *exc):
+        LaunchProfiler.active = None
+
+    def begin(self):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def end(self, start, kind, flops):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.records.append((kind, flops, start, e))
+
+    def summary(self, kind=None):
+        torch.cuda.synchronize()
+        rec = [r for r in self.records if kind is None or r[0] == kind]
+        return sum(r[2].elapsed_time(r[3]) for r in rec), sum(r[1] for r in rec), len(rec)
+
+
 def to_nhwc_bf16(x, c_pad: Optional[int] = None):
     """[B,C,H,W] fp32 -> [B,H,W,c_pad] bf16 (channels zero-padded to a multiple of 8)."""
     _lib.require_cuda(x)
@@ -132,10 +163,15 @@ def conv2d(x, wpk, Co, k, stride, pad, scale, shift, res=None, act=0, out_mode=0
     else:
         y_cs, y_co, y_ptr = o.shape[3], 0, _lib.ptr(o)
     d = _make_desc(x, Co, k, stride, pad, dil, Ho, Wo, out_mode, act, y_cs, y_co, res)
+    prof = LaunchProfiler.active
     with torch.cuda.device(x.buf.device):
+        t0 = prof.begin() if prof else None
         _lib.check(_lib.lib().cnb_conv2d_fprop(d, _lib.ptr(x.buf), _lib.ptr(wpk), _lib.ptr(scale), _lib.ptr(shift),
                                                 _lib.ptr(res.buf) if res is not None else None, y_ptr,
                                                 _stream(x.buf)), "cnb_conv2d_fprop")
+        if prof:   # algorithmic FLOPs: 2*MACs with the true input channels (the 7x7 stem pads 3 -> 8)
+            ci = 3 if (k == 7 and x.C == 8) else x.C
+            prof.end(t0, "conv", 2.0 * x.B * Ho * Wo * Co * k * k * ci)
     if out_mode == 0:
         return o.buf if (out is None) else o
     return o
@@ -147,10 +183,14 @@ def dcnv2(x, om, wpk, Co, scale, shift, act=0, out=None):
     assert om.dtype == torch.float32 and om.is_contiguous() and om.shape[:3] == (x.B, x.H, x.W)
     o = _alloc_out(x, Co, x.H, x.W, 0, out)
     d = _make_desc(x, Co, 3, 1, 1, 1, x.H, x.W, 0, act, o.cstride, o.coffset, None)
+    prof = LaunchProfiler.active
     with torch.cuda.device(x.buf.device):
+        t0 = prof.begin() if prof else None
         _lib.check(_lib.lib().cnb_dcnv2_fprop(d, _lib.ptr(x.buf), _lib.ptr(om), om.shape[3], _lib.ptr(wpk),
                                                _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(o.buf), _stream(x.buf)),
                    "cnb_dcnv2_fprop")
+        if prof:
+            prof.end(t0, "dcn", 2.0 * x.B * x.H * x.W * Co * 9 * x.C)
     return o.buf if out is None else o
 
 

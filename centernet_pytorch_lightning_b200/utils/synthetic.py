@@ -4,6 +4,8 @@ Heat maps are *tie-free by construction* (a per-image random permutation of dist
 because ``torch.topk`` leaves the order of equal scores unspecified (SURVEY.md section 7,
 hard part 3) and bit-exact index parity is only defined on distinct scores.
 """
+import math
+
 import numpy as np
 
 
@@ -58,3 +60,34 @@ def multi_pose_maps(B, J=17, H=128, W=128, seed=1234):
     reg = rng.random((B, 2, H, W)).astype(np.float32)
     hp_offset = rng.random((B, 2, H, W)).astype(np.float32)
     return heat, wh, kps, reg, hm_hp, hp_offset
+
+
+def randomize_(sd, seed=0, offset_std=0.02):
+    """Seeded 'trained-looking' parameters in place: He-normal convs (variance preserving through the
+    34 layers), non-trivial BN statistics (so folding is exercised) and non-zero DCN offset/mask weights
+    (zero init would reduce DCN to 0.5 * conv).  Deterministic on CPU."""
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    for k in sorted(sd.keys()):
+        v = sd[k]
+        if k.endswith("num_batches_tracked"):
+            continue
+        if ".up_" in k:
+            continue                                             # bilinear up-sampling kernels stay as initialised
+        if k.endswith("running_mean"):
+            v.copy_(torch.randn(v.shape, generator=g) * 0.1)
+        elif k.endswith("running_var"):
+            v.copy_(0.5 + torch.rand(v.shape, generator=g))
+        elif "conv_offset_mask.weight" in k:
+            v.copy_(torch.randn(v.shape, generator=g) * offset_std)
+        elif "conv_offset_mask.bias" in k:
+            v.copy_(torch.rand(v.shape, generator=g) * 2 - 1)
+        elif v.dim() == 4:
+            fan_in = v.shape[1] * v.shape[2] * v.shape[3]
+            v.copy_(torch.randn(v.shape, generator=g) * math.sqrt(2.0 / fan_in))
+        elif k.endswith(".weight"):                              # BN gamma
+            v.copy_(0.7 + 0.6 * torch.rand(v.shape, generator=g))
+        elif k.endswith(".bias"):
+            v.copy_(torch.randn(v.shape, generator=g) * 0.1)
+    return sd

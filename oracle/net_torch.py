@@ -1,0 +1,111 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU fp32 oracle for the network half of the hot path.
+
+A *functional* PyTorch restatement (state-dict driven, no nn.Module classes) of the reference's
+DLA-34 + DLAUp/IDAUp + CenterHead forward in eval mode:
+  CenterNet/models/backbones/pose_dla_dcn.py:28-68 (BasicBlock), :165-188 (Root), :191-265 (Tree),
+  :268-378 (DLA), :435-454 (DeformConv), :457-488 (IDAUp), :491-516 (DLAUp), :532-570 (DLASeg),
+  CenterNet/models/heads.py:4-50, and the external DCN.dcn_v2.DCN (tteepe/DCNv2, unpinned,
+  requirements.txt:1; restated on torchvision.ops.deform_conv2d -- "parity unpinned" by the reference).
+It is the floating-point reference the tier allows ("keep a torch fp32 reference only for a
+floating-point kernel") and the CPU baseline bench.py times.  Pinned bit-for-bit against the unmodified
+reference modules by tests/test_oracle_net.py (runs where /root/reference exists).
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+from torchvision.ops import deform_conv2d
+
+
+def _bn(sd, p, x):
+    return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],
+                        False, 0.1, 1e-5)
+
+
+def _conv(sd, p, x, stride=1):
+    w = sd[p + ".weight"]
+    return F.conv2d(x, w, sd.get(p + ".bias"), stride=stride, padding=w.shape[2] // 2)
+
+
+def _block(sd, p, x, residual, stride):
+    out = F.relu(_bn(sd, p + ".bn1", _conv(sd, p + ".conv1", x, stride)))
+    out = _bn(sd, p + ".bn2", _conv(sd, p + ".conv2", out))
+    return F.relu(out + residual)
+
+
+def _tree(sd, p, levels, x, stride, level_root, children=None):
+    children = [] if children is None else children
+    bottom = F.max_pool2d(x, stride, stride) if stride > 1 else x
+    residual = bottom
+    if (p + ".project.0.weight") in sd:
+        residual = _bn(sd, p + ".project.1", _conv(sd, p + ".project.0", bottom))
+    if level_root:
+        children.append(bottom)
+    if levels == 1:
+        x1 = _block(sd, p + ".tree1", x, residual, stride)
+        x2 = _block(sd, p + ".tree2", x1, x1, 1)
+        cat = torch.cat([x2, x1] + children, 1)
+        return F.relu(_bn(sd, p + ".root.bn", _conv(sd, p + ".root.conv", cat)))
+    x1 = _tree(sd, p + ".tree1", levels - 1, x, stride, False)
+    children.append(x1)
+    return _tree(sd, p + ".tree2", levels - 1, x1, 1, False, children)
+
+
+def dcn(sd, p, x):
+    """DCNv2 forward: om = conv(x); o1,o2,m = chunk(om,3); offset = cat(o1,o2); mask = sigmoid(m)."""
+    om = F.conv2d(x, sd[p + ".conv_offset_mask.weight"], sd[p + ".conv_offset_mask.bias"], padding=1)
+    o1, o2, m = torch.chunk(om, 3, dim=1)
+    return deform_conv2d(x, torch.cat((o1, o2), 1), sd[p + ".weight"], sd[p + ".bias"], padding=1,
+                         mask=torch.sigmoid(m))
+
+
+def _deform(sd, p, x):
+    return F.relu(_bn(sd, p + ".actf.0", dcn(sd, p + ".conv", x)))
+
+
+def _ida(sd, p, layers, startp, endp):
+    for i in range(startp + 1, endp):
+        j = i - startp
+        w = sd[f"{p}.up_{j}.weight"]
+        f = w.shape[2] // 2
+        up = F.conv_transpose2d(_deform(sd, f"{p}.proj_{j}", layers[i]), w, stride=f, padding=f // 2,
+                                groups=w.shape[0])
+        layers[i] = _deform(sd, f"{p}.node_{j}", up + layers[i - 1])
+
+
+DLA34_LEVELS = [1, 1, 1, 2, 2, 1]
+
+
+def dla34_seg_forward(sd, x, first_level=2, last_level=5):
+    """DLASeg('dla34', down_ratio=4, last_level=5).forward -> [B,64,H/4,W/4]."""
+    h = F.relu(_bn(sd, "base.base_layer.1", _conv(sd, "base.base_layer.0", x)))
+    feats = []
+    h = F.relu(_bn(sd, "base.level0.1", _conv(sd, "base.level0.0", h)))
+    feats.append(h)
+    h = F.relu(_bn(sd, "base.level1.1", _conv(sd, "base.level1.0", h, 2)))
+    feats.append(h)
+    for lvl in range(2, 6):
+        h = _tree(sd, f"base.level{lvl}", DLA34_LEVELS[lvl], h, 2, lvl > 2)
+        feats.append(h)
+    layers = list(feats)
+    outs = [layers[-1]]
+    n = len(layers)
+    for i in range(n - first_level - 1):
+        _ida(sd, f"dla_up.ida_{i}", layers, n - i - 2, n)
+        outs.insert(0, layers[-1])
+    y = [outs[i].clone() for i in range(last_level - first_level)]
+    _ida(sd, "ida_up", y, 0, len(y))
+    return y[-1]
+
+
+def center_head_forward(sd, x, names, prefix=""):
+    """CenterHead.forward (heads.py:38-43): name -> conv1x1(relu(conv3x3(x)))."""
+    out = {}
+    for n in names:
+        p = f"{prefix}{n}.fc"
+        h = F.relu(F.conv2d(x, sd[p + ".0.weight"], sd[p + ".0.bias"], padding=1))
+        out[n] = F.conv2d(h, sd[p + ".2.weight"], sd[p + ".2.bias"])
+    return out
+
+
+from centernet_pytorch_lightning_b200.utils.synthetic import randomize_  # noqa: E402,F401 (seeded weights shared with bench.py)

@@ -1,0 +1,63 @@
+"""CPU: the functional network oracle (oracle/net_torch.py) against the unmodified reference modules
+(only where /root/reference exists), and against a committed fixture of its own output (everywhere)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import net_torch, ref_shim
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+HEADS = {"heatmap": 80, "width_height": 2, "regression": 2}
+
+
+def _seeded_state(seed=0):
+    from centernet_pytorch_lightning_b200.models import create_model
+    from centernet_pytorch_lightning_b200.models.heads import CenterHead
+    torch.manual_seed(seed)
+    sd = {k: v.clone() for k, v in create_model("dla_34").state_dict().items()}
+    hd = {k: v.clone() for k, v in CenterHead(HEADS, 64, 256).state_dict().items()}
+    net_torch.randomize_(sd, seed)
+    net_torch.randomize_(hd, seed + 1)
+    return sd, hd
+
+
+def test_state_dict_schema_matches_reference():
+    if not ref_shim.available():
+        pytest.skip("reference sources not present on this machine")
+    from centernet_pytorch_lightning_b200.models import create_model
+    a, b = create_model("dla_34").state_dict(), ref_shim.ref_dlaseg().state_dict()
+    assert list(a.keys()) == list(b.keys()) and len(a) == 386
+    assert all(a[k].shape == b[k].shape for k in a)
+    assert all(torch.equal(a[k], b[k]) for k in a if ".up_" in k)     # bilinear init (fill_up_weights)
+
+
+def test_net_oracle_matches_reference_modules():
+    if not ref_shim.available():
+        pytest.skip("reference sources not present on this machine")
+    ref_shim.install()
+    from CenterNet.models.heads import CenterHead as RefHead
+    sd, hd = _seeded_state(3)
+    ref = ref_shim.ref_dlaseg().eval()
+    ref.load_state_dict(sd)
+    rh = RefHead(HEADS, 64, 256).eval()
+    rh.load_state_dict(hd)
+    x = torch.rand(1, 3, 96, 128, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        want = ref(x)[-1]
+        got = net_torch.dla34_seg_forward(sd, x)
+        assert torch.equal(got, want)
+        wh, gh = rh(want), net_torch.center_head_forward(hd, got, HEADS)
+        assert all(torch.equal(wh[k], gh[k]) for k in HEADS)
+
+
+def test_net_oracle_fixture():
+    """Seeded weights are reproducible (CPU generator), so a digest of the oracle output pins it here and
+    on the GPU box (same torch build)."""
+    sd, hd = _seeded_state(3)
+    x = torch.rand(1, 3, 64, 64, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        y = net_torch.dla34_seg_forward(sd, x)
+    g = np.load(os.path.join(GOLD, "dla34_oracle.npz"))
+    np.testing.assert_allclose(y.numpy(), g["feat"], rtol=1e-4, atol=1e-5)
