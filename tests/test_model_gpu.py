@@ -1,9 +1,12 @@
 """-m gpu parity: the DLA-34 + ctdet-head engine (NHWC bf16, tcgen05) vs the CPU fp32 oracle on the
 same seeded weights and inputs.
 
-Floating point through ~45 bf16 layers: the bound is a relative L2 error <= 3e-2 and a max error <=
-8e-2 of the map's max (bf16 has 8 mantissa bits; errors random-walk with depth).  The *decode* stage is
-held to bit-exactness separately (tests/test_decode_gpu.py) -- SURVEY.md section 7, hard part 2.
+Floating point through ~60 bf16 layers (fp32 accumulation).  A CPU emulation of per-layer bf16 rounding of
+the oracle itself (tests below re-run it) differs from the fp32 oracle by 0.4 % relative L2 when the DCN
+offset convs have zero weights and ~1 % at the trained-like offset gain used here (the sampling position
+is a very sensitive function of the features).  Bounds: rel-L2 <= 1.5e-2 / max <= 4e-2 (offset gain 0),
+rel-L2 <= 3e-2 / max <= 8e-2 (default gain).  The *decode* stage is held to bit-exactness separately
+(tests/test_decode_gpu.py) -- SURVEY.md section 7, hard part 2.
 """
 import numpy as np
 import pytest
@@ -19,10 +22,10 @@ pytestmark = pytest.mark.gpu
 HEADS = {"heatmap": 80, "width_height": 2, "regression": 2}
 
 
-def _models(seed):
+def _models(seed, offset_gain=0.05):
     torch.manual_seed(seed)
     m, h = create_model("dla_34"), CenterHead(HEADS, 64, 256)
-    randomize_(m.state_dict(), seed)
+    randomize_(m.state_dict(), seed, offset_gain=offset_gain)
     randomize_(h.state_dict(), seed + 1)
     return m.eval(), h.eval()
 
@@ -32,9 +35,11 @@ def _rel(got, ref):
     return ((got - ref).norm() / (ref.norm() + 1e-12)).item(), ((got - ref).abs().max() / (ref.abs().max() + 1e-12)).item()
 
 
-@pytest.mark.parametrize("B,H,W", [(1, 128, 128), (2, 192, 256)])
-def test_dla34_backbone_and_heads_match_oracle(cuda_dev, B, H, W):
-    m, h = _models(3)
+@pytest.mark.parametrize("B,H,W,gain,tol_l2,tol_max", [(1, 128, 128, 0.0, 1.5e-2, 4e-2),
+                                                        (1, 128, 128, 0.05, 3e-2, 8e-2),
+                                                        (2, 192, 256, 0.05, 3e-2, 8e-2)])
+def test_dla34_backbone_and_heads_match_oracle(cuda_dev, B, H, W, gain, tol_l2, tol_max):
+    m, h = _models(3, gain)
     x = torch.rand(B, 3, H, W, generator=torch.Generator().manual_seed(1))
     sd = {k: v.clone() for k, v in m.state_dict().items()}
     hd = {k: v.clone() for k, v in h.state_dict().items()}
@@ -48,12 +53,12 @@ def test_dla34_backbone_and_heads_match_oracle(cuda_dev, B, H, W):
     torch.cuda.synchronize()
     l2, mx = _rel(out[0], ref_feat)
     print(f"backbone rel-L2 {l2:.4f} max-rel {mx:.4f}")
-    assert l2 <= 3e-2 and mx <= 8e-2
+    assert l2 <= tol_l2 and mx <= tol_max
     for k, c in HEADS.items():
         assert heads[k].shape == (B, c, H // 4, W // 4) and heads[k].dtype == torch.float32
         l2, mx = _rel(heads[k], ref_heads[k])
         print(f"head {k} rel-L2 {l2:.4f} max-rel {mx:.4f}")
-        assert l2 <= 3e-2 and mx <= 8e-2
+        assert l2 <= tol_l2 and mx <= tol_max
     # head input given as a plain NCHW fp32 tensor (no NHWC twin attached) takes the conversion path
     heads2 = h(out[-1].clone())
     assert all(torch.allclose(heads2[k], heads[k], rtol=2e-2, atol=2e-2) for k in HEADS)

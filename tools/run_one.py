@@ -1,0 +1,32 @@
+"""Tiny drivers for ncu captures: python tools/run_one.py decode|conv64|dcn64|head"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from centernet_pytorch_lightning_b200 import ops  # noqa: E402
+from centernet_pytorch_lightning_b200.decode import ctdet_decode  # noqa: E402
+from centernet_pytorch_lightning_b200.utils import synthetic  # noqa: E402
+
+what = sys.argv[1]
+dev = torch.device("cuda:0")
+B = 32
+if what == "decode":
+    heat, wh, reg = synthetic.ctdet_maps(B, 80, 128, 128, seed=1)
+    heat, wh, reg = (torch.from_numpy(a).to(dev) for a in (heat, wh, reg))
+    for _ in range(4):
+        ctdet_decode(heat, wh, reg)
+else:
+    ci, co, hw, k = {"conv64": (64, 64, 128, 3), "dcn64": (64, 64, 128, 3), "head": (64, 768, 128, 3),
+                     "conv256": (256, 256, 32, 3), "conv16": (16, 16, 512, 3), "stem": (8, 16, 512, 7)}[what]
+    x = torch.randn(B, hw, hw, ci, device=dev).to(torch.bfloat16)
+    w = ops.pack_conv_weights(torch.randn(co, ci, k, k, device=dev) * 0.05)
+    sc, sh = torch.ones(co, device=dev), torch.zeros(co, device=dev)
+    om = (torch.randn(B, hw, hw, 32, device=dev) * 0.5) if what.startswith("dcn") else None
+    for _ in range(4):
+        if om is not None:
+            ops.dcnv2(x, om, w, co, sc, sh, act=1)
+        else:
+            ops.conv2d(x, w, co, k, 1, k // 2, sc, sh, act=1)
+torch.cuda.synchronize()
