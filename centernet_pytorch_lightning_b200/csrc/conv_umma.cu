@@ -18,6 +18,8 @@
 #include "cnb_common.cuh"
 
 namespace cnb {
+int conv_tma_run(const cnb_conv_desc* d, const void* x, const void* wpk, const float* scale, const float* shift,
+                 const void* res, void* y, cudaStream_t st);   // conv_tma.cu
 namespace {
 
 constexpr int CT = 256;   // threads per CTA (8 warps)
@@ -425,6 +427,14 @@ static int run_conv(const cnb_conv_desc* d, const void* x, const float* om, int 
                       d->Ho == d->Hi && d->Wo == d->Wi,
                   "dcnv2: only 3x3 / stride 1 / pad 1 / dil 1 (the reference's configuration)");
     CNB_CHECK_ARG(d->Ci % 8 == 0, "dcnv2: Ci must be a multiple of 8");
+  }
+  if (!dcn) {
+    // plain convolutions: TMA-im2col warp-specialised kernel (conv_tma.cu); CNB_CONV_IMPL=v1 keeps the
+    // cp.async gather kernel below for A/B comparisons
+    static const bool use_v1 = [] { const char* e = getenv("CNB_CONV_IMPL"); return e && e[0] == 'v' && e[1] == '1'; }();
+    // thin inputs (Ci < 32: 16/32-byte im2col rows) are far below the TMA engine's efficient row size; they
+    // stay on the cp.async gather until the shared-memory patch kernel covers them
+    if (!use_v1 && (d->Ci >= 32)) return conv_tma_run(d, x, wpk, scale, shift, res, y, st);
   }
   const Plan p = make_plan(*d);
   ConvArgs a;

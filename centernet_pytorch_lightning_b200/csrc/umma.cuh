@@ -1,0 +1,94 @@
+// tcgen05 / TMEM / TMA PTX wrappers shared by the tensor-core kernels (sm_100a only).
+#pragma once
+#include "cnb_common.cuh"
+
+namespace cnb {
+
+// ---- TMEM allocation (one full warp) ------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(u32* smem_dst, u32 ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(u32 taddr, u32 ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, single CTA, issued by ONE thread.
+__device__ __forceinline__ void umma_bf16(u32 tmem_d, u64 desc_a, u64 desc_b, u32 idesc, u32 accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrive once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(void* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread (lane = TMEM lane = tile row)
+__device__ __forceinline__ void tmem_ld16_nowait(u32 taddr, u32 (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- shared-memory matrix descriptors (K-major operands) ----------------------------------------------
+// layout_type: 2 = SWIZZLE_128B (rows of 128 B, 8-row groups 1024 B apart), 4 = SWIZZLE_64B (64 B rows, 512 B
+// groups), 6 = SWIZZLE_32B (32 B rows, 256 B groups), 0 = no swizzle (core matrix = 8 rows x 16 B contiguous;
+// SBO between 8-row groups, LBO between the two 8-element K halves of one K=16 instruction).
+__device__ __forceinline__ u64 make_sdesc(u32 smem_addr, u32 lbo_bytes, u32 sbo_bytes, u32 layout_type) {
+  return (u64)((smem_addr >> 4) & 0x3FFF) | ((u64)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((u64)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((u64)layout_type << 61);
+}
+// instruction descriptor, kind::f16: D = f32, A = B = bf16, both K-major, M x N tile
+__host__ __device__ __forceinline__ u32 make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((u32)(N >> 3) << 17) | ((u32)(M >> 4) << 24);
+}
+
+// ---- TMA (tensor maps) ----------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<u64>(tmap)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(u32 dst_smem, const void* tmap, int c0, int c1, void* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+          "r"(dst_smem),
+      "l"(reinterpret_cast<u64>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// im2col mode over an NHWC tensor {C, W, H, N}: (c, w, h, n) = first channel and the base pixel of the first
+// row of the column tile (already shifted by the lower corner), (off_w, off_h) = filter tap offset.
+__device__ __forceinline__ void tma_load_im2col_4d(u32 dst_smem, const void* tmap, int c, int w, int h, int n,
+                                                   unsigned short off_w, unsigned short off_h, void* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(dst_smem),
+      "l"(reinterpret_cast<u64>(tmap)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w),
+      "h"(off_h)
+      : "memory");
+}
+
+__device__ __forceinline__ u32 pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<u32*>(&h);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(u32 v) {
+  __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&v);
+  return __bfloat1622float2(h);
+}
+
+}  // namespace cnb
