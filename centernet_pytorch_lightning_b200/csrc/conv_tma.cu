@@ -17,7 +17,7 @@
 //   * Epilogue: tcgen05.ld (lane = output pixel) -> scale/shift (folded BN or bias) -> (+residual) ->
 //     ReLU/sigmoid -> NHWC bf16 (optionally a channel slice of a concat buffer) | NCHW fp32 | NHWC fp32.
 #include "umma.cuh"
-#include <cuda.h>
+#include "tma_host.h"
 #include <mutex>
 
 namespace cnb {
@@ -49,60 +49,6 @@ struct TArgs {
   u32 idesc;
   int nscale;      // n_tiles * BN
 };
-
-__device__ __forceinline__ void epilogue_store(const TArgs& a, const float* s_scale, const float* s_shift,
-                                               u32 (&v)[16], int m, int cg0, int co0, int HoWo, int on,
-                                               int opix) {
-  const cnb_conv_desc& d = a.d;
-  float f[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) f[j] = fmaf(__uint_as_float(v[j]), s_scale[cg0 + j], s_shift[cg0 + j]);
-  if (a.res) {
-    const uint4* rp = reinterpret_cast<const uint4*>(a.res + (size_t)m * d.res_cstride + d.res_coffset + co0);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      if (co0 + 8 * h < d.Co) {
-        const uint4 r = __ldg(rp + h);
-        const float2 p0 = unpack_bf16x2(r.x), p1 = unpack_bf16x2(r.y), p2 = unpack_bf16x2(r.z),
-                     p3 = unpack_bf16x2(r.w);
-        f[8 * h + 0] += p0.x; f[8 * h + 1] += p0.y; f[8 * h + 2] += p1.x; f[8 * h + 3] += p1.y;
-        f[8 * h + 4] += p2.x; f[8 * h + 5] += p2.y; f[8 * h + 6] += p3.x; f[8 * h + 7] += p3.y;
-      }
-    }
-  }
-  if (d.act == 1) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-  } else if (d.act == 2) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) f[j] = 1.f / (1.f + __expf(-f[j]));
-  }
-  if (d.out_nchw_f32 == 0) {          // NHWC bf16 (optionally a channel slice of a concat buffer)
-    __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(a.y) + (size_t)m * d.y_cstride + d.y_coffset + co0;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      if (co0 + 8 * h < d.Co) {
-        uint4 o;
-        o.x = pack_bf16x2(f[8 * h + 0], f[8 * h + 1]);
-        o.y = pack_bf16x2(f[8 * h + 2], f[8 * h + 3]);
-        o.z = pack_bf16x2(f[8 * h + 4], f[8 * h + 5]);
-        o.w = pack_bf16x2(f[8 * h + 6], f[8 * h + 7]);
-        *reinterpret_cast<uint4*>(yp + 8 * h) = o;
-      }
-    }
-  } else if (d.out_nchw_f32 == 1) {   // NCHW fp32 (head maps for decode / losses): lanes = consecutive pixels
-    float* yp = reinterpret_cast<float*>(a.y) + ((size_t)on * d.Co + co0) * HoWo + opix;
-#pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (co0 + j < d.Co) yp[(size_t)j * HoWo] = f[j];
-  } else {                            // NHWC fp32 (offset/mask maps feeding the DCN sampler)
-    float* yp = reinterpret_cast<float*>(a.y) + (size_t)m * d.y_cstride + d.y_coffset + co0;
-#pragma unroll
-    for (int h = 0; h < 4; ++h)
-      if (co0 + 4 * h < d.y_cstride)
-        *reinterpret_cast<float4*>(yp + 4 * h) = make_float4(f[4 * h], f[4 * h + 1], f[4 * h + 2], f[4 * h + 3]);
-  }
-}
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TArgs a) {
@@ -256,25 +202,13 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
 }
 
-// ---- host side ---------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
-                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// ---- host side (tensor-map encode entry points: tma_host.h) ------------------------------------------------
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
-struct Driver {
-  EncodeTiledFn tiled = nullptr;
-  EncodeIm2colFn im2col = nullptr;
-  int driver_version = 0;
-  int num_sms = 0;
-  bool ok = false;
-};
+}  // namespace
 
-static Driver& driver() {
-  static Driver drv;
+TmaDriver& tma_driver() {
+  static TmaDriver drv;
   static std::once_flag once;
   std::call_once(once, [] {
     cudaDriverEntryPointQueryResult q1, q2;
@@ -296,15 +230,11 @@ static Driver& driver() {
   return drv;
 }
 
-inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
-
-}  // namespace
-
 // Returns CNB_OK, or CNB_ERR_INVALID with the reason in cnb_last_error when this geometry is not covered
 // (callers treat that as an error: there is no fallback path for plain convolutions).
 int conv_tma_run(const cnb_conv_desc* d, const void* x, const void* wpk, const float* scale, const float* shift,
                  const void* res, void* y, cudaStream_t st) {
-  Driver& drv = driver();
+  TmaDriver& drv = tma_driver();
   if (!drv.ok) {
     set_error("conv: cuTensorMapEncode{Tiled,Im2col} entry points unavailable (driver too old?)");
     return CNB_ERR_CUDA;

@@ -20,6 +20,9 @@
 namespace cnb {
 int conv_tma_run(const cnb_conv_desc* d, const void* x, const void* wpk, const float* scale, const float* shift,
                  const void* res, void* y, cudaStream_t st);   // conv_tma.cu
+bool dcn_ws_supported(const cnb_conv_desc* d);                  // dcn_ws.cu
+int dcn_ws_run(const cnb_conv_desc* d, const void* x, const float* om, int om_cstride, const void* wpk,
+               const float* scale, const float* shift, void* y, cudaStream_t st);
 namespace {
 
 constexpr int CT = 256;   // threads per CTA (8 warps)
@@ -427,6 +430,9 @@ static int run_conv(const cnb_conv_desc* d, const void* x, const float* om, int 
                       d->Ho == d->Hi && d->Wo == d->Wi,
                   "dcnv2: only 3x3 / stride 1 / pad 1 / dil 1 (the reference's configuration)");
     CNB_CHECK_ARG(d->Ci % 8 == 0, "dcnv2: Ci must be a multiple of 8");
+    CNB_CHECK_ARG(d->out_nchw_f32 == 0 && ((uintptr_t)om & 15) == 0, "dcnv2: NHWC bf16 output, 16-byte aligned om");
+    // warp-specialised sampler kernel (dcn_ws.cu); CNB_DCN_IMPL=v1 keeps the gather kernel below for A/B runs
+    if (dcn_ws_supported(d)) return dcn_ws_run(d, x, om, om_cstride, wpk, scale, shift, y, st);
   }
   if (!dcn) {
     // plain convolutions: TMA-im2col warp-specialised kernel (conv_tma.cu); CNB_CONV_IMPL=v1 keeps the

@@ -1,0 +1,371 @@
+// Modulated deformable convolution v2 (DCNv2), warp-specialised and persistent, on the 5th-gen tensor cores.
+//
+// Replaces DCN.dcn_v2.DCN forward (external tteepe/DCNv2; call sites CenterNet/models/backbones/
+// pose_dla_dcn.py:441-449 and resnet_dcn.py:202-210): 3x3, stride 1, pad 1, dil 1, deformable_groups 1,
+//   y[n,co,p] = b[co] + sum_{ci,k} W[co,ci,k] * sigmoid(m_k(p)) * bilinear(x[n,ci], p + tap_k + offset_k(p))
+// with the (+ BatchNorm(eval) + ReLU) of DeformConv (pose_dla_dcn.py:435-454) folded into the epilogue.
+//
+// GEMM view: D[M = B*H*W pixels, N = Co] = A[M, K = 9*Ci] * W[N, K]^T where A is the *sampled* column matrix.
+// A is never materialised in HBM.  Per 128-pixel tile the CTA's warps play four roles:
+//   setup warps    : read the 27 offset/mask channels of the tile's pixels once, and turn every (pixel, tap)
+//                    into 4 bilinear weights (mask and validity folded in) + a clamped corner address; the table
+//                    lives in shared memory, double buffered, so tile i+1 is prepared while tile i is sampled;
+//   sampler warps  : per (tap, 64-channel slab) K block gather the 4 corners of each pixel as 16-byte channel
+//                    chunks through L1 (neighbouring pixels/taps share corners), blend in fp32, round to bf16 and
+//                    st.shared the chunk straight into the K-major SWIZZLE_128B operand layout;
+//   MMA warp       : one lane issues tcgen05.mma (M=128, N=Co, K=16) from the stage ring; the weight tile of the
+//                    K block arrives by TMA on the same full barrier; tcgen05.commit recycles the stage;
+//   epilogue warps : TMEM -> scale/shift (bias or folded BN) -> ReLU -> NHWC bf16; two TMEM accumulators so the
+//                    epilogue of tile i overlaps the main loop of tile i+1.
+// K blocks run slab-major / tap-minor: the 9 taps of one slab re-touch the same ~(rows+2) x W x 128 B footprint,
+// which stays in L1.  The kernel is bound by the sampler (L1 wavefronts + fp32 blend issue), not by the MMA.
+#include "umma.cuh"
+#include "tma_host.h"
+#include <stdlib.h>
+
+namespace cnb {
+namespace {
+
+constexpr int BM = 128;
+constexpr int NPROD_WARPS = 8;                       // sampler warps: 256 threads, 4 pixel rows x one 8-ch chunk each
+constexpr int NPROD = NPROD_WARPS * 32;
+constexpr int NSETUP_WARPS = 4;
+constexpr int NSETUP = NSETUP_WARPS * 32;
+constexpr int W_SETUP0 = NPROD_WARPS;                // warps 8..11
+constexpr int W_MMA = W_SETUP0 + NSETUP_WARPS;       // warp 12
+constexpr int W_EPI0 = W_MMA + 1;                    // warps 13..16 (TMEM lane quarters 1,2,3,0)
+constexpr int NTHREADS = (W_EPI0 + 4) * 32;          // 544
+constexpr int MAX_STAGES = 6;
+constexpr int NTAB = BM * 9;                         // (pixel, tap) entries per tile
+constexpr u32 A_BYTES = BM * 64 * 2;                 // one K block of the sampled operand: 128 rows x 128 B
+
+struct DArgs {
+  cnb_conv_desc d;
+  const __nv_bfloat16* x;
+  const float* om;
+  int om_cstride;
+  const float* scale;
+  const float* shift;
+  const __nv_bfloat16* res;   // unused (kept for the shared epilogue)
+  void* y;
+  int M, m_tiles;
+  int BN;          // = Co rounded up to 16, <= 256
+  int nkb;         // 9 * Ci/64
+  int stages;
+  u32 b_bytes, stage_bytes, tmem_cols, acc_stride, idesc;
+};
+
+// packed fp32x2 helpers (Blackwell FFMA2): a 64-bit register holds (low, high) floats
+__device__ __forceinline__ u64 dup2(float w) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(w));
+  return r;
+}
+__device__ __forceinline__ u64 pair_from_bf16x2(u32 v) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(v << 16), "r"(v & 0xffff0000u));
+  return r;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+  u64 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
+  extern __shared__ unsigned char smem_dyn[];
+  __shared__ __align__(8) u64 s_full[MAX_STAGES];
+  __shared__ __align__(8) u64 s_empty[MAX_STAGES];
+  __shared__ __align__(8) u64 s_tfull[2];
+  __shared__ __align__(8) u64 s_tempty[2];
+  __shared__ __align__(8) u64 s_tabfull[2];
+  __shared__ __align__(8) u64 s_tabempty[2];
+  __shared__ u32 s_tmem;
+
+  const cnb_conv_desc& d = a.d;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const u32 smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char* smem_al = smem_dyn + (smem_base - smem_u32(smem_dyn));
+  float4* s_tabw = reinterpret_cast<float4*>(smem_al + (size_t)a.stages * a.stage_bytes);   // [2][NTAB]
+  u32* s_tabb = reinterpret_cast<u32*>(s_tabw + 2 * NTAB);                                  // [2][NTAB]
+  float* s_scale = reinterpret_cast<float*>(s_tabb + 2 * NTAB);
+  float* s_shift = s_scale + a.BN;
+
+  if (tid == 0) {
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(&s_full[s], NPROD_WARPS + 1);   // one arrival per sampler warp + the weight tile's expect_tx
+      mbar_init(&s_empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_tfull[i], 1);
+      mbar_init(&s_tempty[i], 4);
+      mbar_init(&s_tabfull[i], NSETUP_WARPS);
+      mbar_init(&s_tabempty[i], NPROD_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmB);
+  if (warp == W_MMA) tmem_alloc(&s_tmem, a.tmem_cols);
+  for (int i = tid; i < a.BN; i += NTHREADS) {
+    s_scale[i] = (i < d.Co && a.scale) ? a.scale[i] : 1.f;
+    s_shift[i] = (i < d.Co && a.shift) ? a.shift[i] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const u32 tmem_base = s_tmem;
+  const int HW = d.Hi * d.Wi;
+
+  if (warp < NPROD_WARPS) {
+    // =============================== samplers ===============================================================
+    const int chunk = tid & 7;          // 16-byte channel chunk inside the 64-channel slab
+    const int r0 = tid >> 3;            // rows r0 + 32*i
+    const u32 cs = (u32)d.x_cstride;
+    const u32 row_step = (u32)d.Wi * cs;
+    u32 it = 0, t = 0;
+    for (int tile = blockIdx.x; tile < a.m_tiles; tile += gridDim.x, ++t) {
+      const u32 tb = t & 1u;
+      mbar_wait(&s_tabfull[tb], (t >> 1) & 1u);
+      const float4* tw = s_tabw + tb * NTAB;
+      const u32* tbs = s_tabb + tb * NTAB;
+      int slab = 0, tap = 0;
+      for (int kb = 0; kb < a.nkb; ++kb, ++it) {
+        const u32 s = it % (u32)a.stages, ph = (it / (u32)a.stages) & 1u;
+        mbar_wait(&s_empty[s], ph ^ 1u);
+        const u32 sa = smem_base + s * a.stage_bytes;
+        if (tid == 0) {
+          mbar_expect_tx(&s_full[s], a.b_bytes);
+          tma_load_2d(sa + A_BYTES, &tmB, tap * d.Ci + slab * 64, 0, &s_full[s]);
+        }
+        const __nv_bfloat16* xs = a.x + d.x_coffset + slab * 64 + chunk * 8;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint4 q[2][4];
+          float4 w[2];
+          u64 ww[2][4];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int item = (r0 + 32 * (2 * h + i)) * 9 + tap;
+            w[i] = tw[item];
+            ww[i][0] = dup2(w[i].x); ww[i][1] = dup2(w[i].y); ww[i][2] = dup2(w[i].z); ww[i][3] = dup2(w[i].w);
+            const u32 b = tbs[item];
+            const u32 o00 = b & 0x3FFFFFFFu;                       // element offset of the clamped (y0, x0) pixel
+            const u32 o01 = o00 + (((b >> 30) & 1u) ? cs : 0u);
+            const u32 ddy = (b >> 31) ? row_step : 0u;
+            q[i][0] = __ldg(reinterpret_cast<const uint4*>(xs + o00));
+            q[i][1] = __ldg(reinterpret_cast<const uint4*>(xs + o01));
+            q[i][2] = __ldg(reinterpret_cast<const uint4*>(xs + (o00 + ddy)));
+            q[i][3] = __ldg(reinterpret_cast<const uint4*>(xs + (o01 + ddy)));
+          }
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int row = r0 + 32 * (2 * h + i);
+            u32 o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const u32 v0 = (&q[i][0].x)[e], v1 = (&q[i][1].x)[e], v2 = (&q[i][2].x)[e], v3 = (&q[i][3].x)[e];
+              // bf16 -> fp32 is a 16-bit shift: low element = v << 16, high element = v & 0xffff0000;
+              // the (low, high) pair is blended with one packed fp32x2 FMA per corner
+              u64 acc = mul2(ww[i][0], pair_from_bf16x2(v0));
+              acc = fma2(ww[i][1], pair_from_bf16x2(v1), acc);
+              acc = fma2(ww[i][2], pair_from_bf16x2(v2), acc);
+              acc = fma2(ww[i][3], pair_from_bf16x2(v3), acc);
+              float lo, hi;
+              asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc));
+              o[e] = pack_bf16x2(lo, hi);
+            }
+            const u32 dst = sa + row * 128 + ((chunk ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(o[0]), "r"(o[1]), "r"(o[2]),
+                         "r"(o[3])
+                         : "memory");
+          }
+        }
+        fence_proxy_async_smem();       // generic-proxy stores -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_full[s]);
+        if (++tap == 9) {
+          tap = 0;
+          ++slab;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_tabempty[tb]);
+    }
+  } else if (warp < W_MMA) {
+    // =============================== setup: (pixel, tap) -> weights + corner address =========================
+    const int stid = tid - W_SETUP0 * 32;
+    u32 t = 0;
+    for (int tile = blockIdx.x; tile < a.m_tiles; tile += gridDim.x, ++t) {
+      const u32 tb = t & 1u;
+      mbar_wait(&s_tabempty[tb], ((t >> 1) & 1u) ^ 1u);
+      const int m0 = tile * BM;
+#pragma unroll 3
+      for (int item = stid; item < NTAB; item += NSETUP) {
+        const int r = item / 9, tap = item - r * 9;
+        const int m = m0 + r;
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        u32 b = 0;
+        if (m < a.M) {
+          const int n = m / HW;
+          const int rem = m - n * HW;
+          const int oy = rem / d.Wi, ox = rem - oy * d.Wi;
+          const int kh = tap / 3, kw = tap - 3 * kh;
+          const float* omp = a.om + (size_t)m * a.om_cstride;
+          const float dy = __ldg(omp + 2 * tap);
+          const float dx = __ldg(omp + 2 * tap + 1);
+          const float mk = 1.f / (1.f + __expf(-__ldg(omp + 18 + tap)));
+          const float py = (float)(oy - 1 + kh) + dy;
+          const float px = (float)(ox - 1 + kw) + dx;
+          if (py > -1.f && px > -1.f && py < (float)d.Hi && px < (float)d.Wi) {
+            const int y0 = (int)floorf(py), x0 = (int)floorf(px);
+            const float ly = py - (float)y0, lx = px - (float)x0;
+            const float hy = 1.f - ly, hx = 1.f - lx;
+            const bool vy0 = y0 >= 0, vy1 = y0 + 1 <= d.Hi - 1, vx0 = x0 >= 0, vx1 = x0 + 1 <= d.Wi - 1;
+            w.x = (vy0 && vx0) ? hy * hx * mk : 0.f;
+            w.y = (vy0 && vx1) ? hy * lx * mk : 0.f;
+            w.z = (vy1 && vx0) ? ly * hx * mk : 0.f;
+            w.w = (vy1 && vx1) ? ly * lx * mk : 0.f;
+            const int y0c = max(y0, 0), y1c = min(y0 + 1, d.Hi - 1);
+            const int x0c = max(x0, 0), x1c = min(x0 + 1, d.Wi - 1);
+            b = (u32)((n * d.Hi + y0c) * d.Wi + x0c) * (u32)d.x_cstride | ((u32)(x1c - x0c) << 30) |
+                ((u32)(y1c - y0c) << 31);
+          }
+        }
+        s_tabw[tb * NTAB + item] = w;
+        s_tabb[tb * NTAB + item] = b;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_tabfull[tb]);
+    }
+  } else if (warp == W_MMA) {
+    // =============================== MMA issuer ==============================================================
+    if (lane == 0) {
+      u32 it = 0, t = 0;
+      for (int tile = blockIdx.x; tile < a.m_tiles; tile += gridDim.x, ++t) {
+        const u32 acc = t & 1u, acc_ph = (t >> 1) & 1u;
+        mbar_wait(&s_tempty[acc], acc_ph ^ 1u);
+        tc_fence_after();
+        const u32 tmem_d = tmem_base + acc * a.acc_stride;
+        u32 accumulate = 0;
+        for (int kb = 0; kb < a.nkb; ++kb, ++it) {
+          const u32 s = it % (u32)a.stages, ph = (it / (u32)a.stages) & 1u;
+          mbar_wait(&s_full[s], ph);
+          tc_fence_after();
+          const u32 sa = smem_base + s * a.stage_bytes;
+          const u64 da = make_sdesc(sa, 16, 1024, 2);
+          const u64 db = make_sdesc(sa + A_BYTES, 16, 1024, 2);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {   // +32 bytes of K inside the swizzle atom
+            umma_bf16(tmem_d, da + (u64)(2 * kk), db + (u64)(2 * kk), a.idesc, accumulate);
+            accumulate = 1;
+          }
+          umma_commit(&s_empty[s]);
+        }
+        umma_commit(&s_tfull[acc]);
+      }
+    }
+  } else {
+    // =============================== epilogue ================================================================
+    const int q = warp & 3;
+    u32 t = 0;
+    for (int tile = blockIdx.x; tile < a.m_tiles; tile += gridDim.x, ++t) {
+      const u32 acc = t & 1u, acc_ph = (t >> 1) & 1u;
+      const int m = tile * BM + 32 * q + lane;
+      mbar_wait(&s_tfull[acc], acc_ph);
+      tc_fence_after();
+      const u32 taddr = tmem_base + acc * a.acc_stride + ((u32)(32 * q) << 16);
+      const int ngroups = a.BN / 16;
+      for (int g = 0; g < ngroups; ++g) {
+        u32 v[16];
+        tmem_ld16_nowait(taddr + (u32)(g * 16), v);
+        tmem_ld_wait();
+        const int co0 = g * 16;
+        if (m < a.M && co0 < d.Co) epilogue_store(a, s_scale, s_shift, v, m, co0, co0, HW, 0, 0);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_tempty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) tmem_dealloc(tmem_base, a.tmem_cols);
+}
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+
+// Geometries this kernel covers (the rest stays on the cp.async gather kernel of conv_umma.cu).
+bool dcn_ws_supported(const cnb_conv_desc* d) {
+  static const bool off = [] { const char* e = getenv("CNB_DCN_IMPL"); return e && e[0] == 'v' && e[1] == '1'; }();
+  return !off && d->Ci % 64 == 0 && d->Co % 8 == 0 && round_up(d->Co, 16) <= 256 &&
+         (long long)d->B * d->Hi * d->Wi * d->x_cstride < (1ll << 30);
+}
+
+int dcn_ws_run(const cnb_conv_desc* d, const void* x, const float* om, int om_cstride, const void* wpk,
+               const float* scale, const float* shift, void* y, cudaStream_t st) {
+  TmaDriver& drv = tma_driver();
+  if (!drv.ok) {
+    set_error("dcnv2: cuTensorMapEncodeTiled entry point unavailable (driver too old?)");
+    return CNB_ERR_CUDA;
+  }
+  DArgs a;
+  a.d = *d;
+  a.x = (const __nv_bfloat16*)x;
+  a.om = om;
+  a.om_cstride = om_cstride;
+  a.scale = scale;
+  a.shift = shift;
+  a.res = nullptr;
+  a.y = y;
+  a.M = d->B * d->Hi * d->Wi;
+  a.m_tiles = (a.M + BM - 1) / BM;
+  a.BN = round_up(d->Co, 16);
+  a.nkb = 9 * (d->Ci / 64);
+  a.b_bytes = (u32)a.BN * 128u;
+  a.stage_bytes = A_BYTES + ((a.b_bytes + 1023u) & ~1023u);
+  const size_t fixed = (size_t)2 * NTAB * (sizeof(float4) + sizeof(u32)) + (size_t)a.BN * 8 + 1024;
+  static const int env_stages = [] { const char* e = getenv("CNB_DCN_STAGES"); return e ? atoi(e) : 0; }();
+  a.stages = env_stages > 0 ? env_stages : (a.BN <= 64 ? 4 : 3);
+  if (a.stages > MAX_STAGES) a.stages = MAX_STAGES;
+  while (a.stages > 2 && (size_t)a.stages * a.stage_bytes + fixed > 220 * 1024) --a.stages;
+  a.acc_stride = (u32)round_up(a.BN, 32);
+  a.tmem_cols = 32;
+  while (a.tmem_cols < 2 * a.acc_stride) a.tmem_cols <<= 1;
+  a.idesc = make_idesc_bf16(BM, a.BN);
+  const size_t smem = (size_t)a.stages * a.stage_bytes + fixed;
+
+  CUtensorMap tmB;
+  {
+    const int Kpad = 9 * d->Ci;   // Ci % 64 == 0: already a multiple of the packing granularity
+    cuuint64_t dims[2] = {(cuuint64_t)Kpad, (cuuint64_t)a.BN};
+    cuuint64_t strides[1] = {(cuuint64_t)Kpad * 2};
+    cuuint32_t box[2] = {64u, (cuuint32_t)a.BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = drv.tiled(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)wpk, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("dcnv2: cuTensorMapEncodeTiled failed (%d) Kpad=%d BN=%d", (int)r, Kpad, a.BN);
+      return CNB_ERR_CUDA;
+    }
+  }
+  static bool configured = false;
+  if (!configured) {
+    CNB_CUDA(cudaFuncSetAttribute(dcn_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    configured = true;
+  }
+  const int grid = a.m_tiles < drv.num_sms ? a.m_tiles : drv.num_sms;
+  dcn_ws_kernel<<<grid, NTHREADS, smem, st>>>(tmB, a);
+  CNB_LAUNCH_CHECK();
+  return CNB_OK;
+}
+
+}  // namespace cnb

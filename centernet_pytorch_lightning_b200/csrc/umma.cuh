@@ -91,4 +91,63 @@ __device__ __forceinline__ float2 unpack_bf16x2(u32 v) {
   return __bfloat1622float2(h);
 }
 
+// ---- shared epilogue of the tensor-core kernels ------------------------------------------------------------
+// 16 consecutive output channels [co0, co0+16) of output pixel m: accumulator -> scale/shift (folded BN or
+// bias) -> (+residual) -> ReLU/sigmoid -> NHWC bf16 (optionally a concat slice) | NCHW fp32 | NHWC fp32.
+// Args needs: cnb_conv_desc d; const __nv_bfloat16* res; void* y.   cg0 indexes s_scale/s_shift.
+template <class Args>
+__device__ __forceinline__ void epilogue_store(const Args& a, const float* s_scale, const float* s_shift,
+                                               u32 (&v)[16], int m, int cg0, int co0, int HoWo, int on,
+                                               int opix) {
+  const cnb_conv_desc& d = a.d;
+  float f[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) f[j] = fmaf(__uint_as_float(v[j]), s_scale[cg0 + j], s_shift[cg0 + j]);
+  if (a.res) {
+    const uint4* rp = reinterpret_cast<const uint4*>(a.res + (size_t)m * d.res_cstride + d.res_coffset + co0);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (co0 + 8 * h < d.Co) {
+        const uint4 r = __ldg(rp + h);
+        const float2 p0 = unpack_bf16x2(r.x), p1 = unpack_bf16x2(r.y), p2 = unpack_bf16x2(r.z),
+                     p3 = unpack_bf16x2(r.w);
+        f[8 * h + 0] += p0.x; f[8 * h + 1] += p0.y; f[8 * h + 2] += p1.x; f[8 * h + 3] += p1.y;
+        f[8 * h + 4] += p2.x; f[8 * h + 5] += p2.y; f[8 * h + 6] += p3.x; f[8 * h + 7] += p3.y;
+      }
+    }
+  }
+  if (d.act == 1) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+  } else if (d.act == 2) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = 1.f / (1.f + __expf(-f[j]));
+  }
+  if (d.out_nchw_f32 == 0) {          // NHWC bf16 (optionally a channel slice of a concat buffer)
+    __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(a.y) + (size_t)m * d.y_cstride + d.y_coffset + co0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (co0 + 8 * h < d.Co) {
+        uint4 o;
+        o.x = pack_bf16x2(f[8 * h + 0], f[8 * h + 1]);
+        o.y = pack_bf16x2(f[8 * h + 2], f[8 * h + 3]);
+        o.z = pack_bf16x2(f[8 * h + 4], f[8 * h + 5]);
+        o.w = pack_bf16x2(f[8 * h + 6], f[8 * h + 7]);
+        *reinterpret_cast<uint4*>(yp + 8 * h) = o;
+      }
+    }
+  } else if (d.out_nchw_f32 == 1) {   // NCHW fp32 (head maps for decode / losses): lanes = consecutive pixels
+    float* yp = reinterpret_cast<float*>(a.y) + ((size_t)on * d.Co + co0) * HoWo + opix;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (co0 + j < d.Co) yp[(size_t)j * HoWo] = f[j];
+  } else {                            // NHWC fp32 (offset/mask maps feeding the DCN sampler)
+    float* yp = reinterpret_cast<float*>(a.y) + (size_t)m * d.y_cstride + d.y_coffset + co0;
+#pragma unroll
+    for (int h = 0; h < 4; ++h)
+      if (co0 + 4 * h < d.y_cstride)
+        *reinterpret_cast<float4*>(yp + 4 * h) = make_float4(f[4 * h], f[4 * h + 1], f[4 * h + 2], f[4 * h + 3]);
+  }
+}
+
 }  // namespace cnb
