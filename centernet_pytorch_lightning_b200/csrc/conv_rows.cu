@@ -1,0 +1,396 @@
+// Row-window convolution for the wide, thin layers (W_out % 128 == 0, Ci in {8,16,32,64}) on tcgen05.
+//
+// Replaces (reference file:line under CenterNet/models/backbones/pose_dla_dcn.py): the stem :281-285 (7x7, 3->16
+// @512^2), the conv levels :351-370 (16->16 @512^2, 16->32 stride 2), the stride-2 / stride-1 3x3 convs of the first
+// Tree (BasicBlock :28-68, 32->64 and 64->64 @128^2) and the 64->27 conv_offset_mask convs of the DCN layers that
+// run at 128^2 (pose_dla_dcn.py:441) -- each with BatchNorm(eval) / bias, residual and ReLU in the epilogue.
+//
+// Why another kernel: with few channels the implicit-GEMM K dimension is short (144..576) and N is tiny
+// (16..64), so a tile's MMA time is a few hundred clocks while an im2col feed re-reads every input pixel KH*KW
+// times from L2.  Here every input pixel is fetched ONCE per 128-pixel column strip and the im2col structure is
+// expressed purely through shared-memory *descriptors*:
+//   * a CTA walks down a strip (image n, 128 output columns) row by row and keeps the last KH input rows in a
+//     ring of shared-memory slots; one slot = one input row, stored as planes [phase][8-channel chunk][pixel] of
+//     16-byte pixels (phase = x mod stride, so a stride-2 conv also reads unit-stride planes);
+//   * in the canonical no-swizzle K-major layout a core matrix is 8 rows x 16 B contiguous, i.e. 8 consecutive
+//     pixels of one plane.  The A operand of filter tap (kh, kw) is therefore just the plane of row slot kh,
+//     started kw pixels later: descriptor start = plane + kw*16 B, SBO = 128 B (next 8 pixels), LBO = the distance
+//     to the second 8-channel half of the K=16 step (the next chunk plane, or -- 8-channel stem -- the next pixel,
+//     which pairs the taps kw, kw+1).  No im2col copy exists anywhere, not even in shared memory;
+//   * the packed weights (all of K x Co) stay resident in shared memory for the CTA's lifetime (TMA, SWIZZLE_128B).
+// Warp roles: 4 producer warps (16-byte cp.async with zero fill at the borders, completion handed to an mbarrier
+// two rows behind), 1 MMA warp (one lane issues tcgen05.mma M=128, N=Co, K=16), 4 epilogue warps; two TMEM
+// accumulators so the epilogue of row i overlaps the MMAs of row i+1.
+#include "umma.cuh"
+#include "tma_host.h"
+#include <stdlib.h>
+
+namespace cnb {
+namespace {
+
+constexpr int BM = 128;
+constexpr int NPW = 4;                       // producer warps
+constexpr int NPT = NPW * 32;
+constexpr int W_MMA = NPW;                   // warp 4
+constexpr int W_EPI0 = NPW + 1;              // warps 5..8 (TMEM lane quarters 1,2,3,0)
+constexpr int NTHREADS = (W_EPI0 + 4) * 32;  // 288
+constexpr int MAX_SLOTS = 12;
+constexpr int DEPTH = 2;                     // input rows a producer thread keeps in flight
+
+struct RArgs {
+  cnb_conv_desc d;
+  const __nv_bfloat16* x;
+  const float* scale;
+  const float* shift;
+  const __nv_bfloat16* res;
+  void* y;
+  int s;             // stride (1 or 2)
+  int nch;           // Ci / 8: chunk planes per phase
+  int KWp;           // KW as packed in the weights (KW rounded up to even when Ci == 8)
+  int PW;            // pixels stored per plane (128 + halo)
+  int q_off;         // plane pixel j holds q = ox0 + q_off + j   (input x = s*q + phase)
+  u32 plane_bytes;
+  u32 slot_bytes;
+  int nslots;
+  int nseg;          // Wo / 128
+  int units;         // B * nseg * Ho  (one unit = one 128-pixel output row segment)
+  int BN;
+  int nslab;         // 64-wide K slabs of the resident weights
+  u32 b_slab_bytes, b_bytes;
+  u32 tmem_cols, acc_stride, idesc;
+};
+
+__device__ __forceinline__ void cp_async16(u32 dst, const void* src, u32 src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Walks the CTA's units in order and tells, for every unit, which input rows are new.  Used identically by the
+// producer and the MMA warp so that both agree on the load index L of every input row (slot = L % nslots).
+struct RowWalk {
+  int Ho, s, pad, KH;
+  int strip, oy;       // current unit
+  int Lbase;           // load index of the unit's first input row (iy0 = oy*s - pad)
+  int Lnext;           // next load index to be assigned
+  bool fresh;          // first unit of a run (strip start): all KH rows are new
+  __device__ void start(int u, int Ho_, int s_, int pad_, int KH_) {
+    Ho = Ho_; s = s_; pad = pad_; KH = KH_;
+    strip = u / Ho;
+    oy = u - strip * Ho;
+    Lbase = 0;
+    Lnext = KH;
+    fresh = true;
+  }
+  __device__ int first_new() const { return fresh ? Lbase : Lbase + KH - s; }   // load indices [first_new, Lnext)
+  __device__ bool last_of_run(int u, int u_end) const { return u + 1 == u_end || oy == Ho - 1; }
+  __device__ void next() {   // advance to the following unit
+    if (oy == Ho - 1) {      // next strip: every row is reloaded
+      ++strip;
+      oy = 0;
+      Lbase = Lnext;
+      Lnext = Lbase + KH;
+      fresh = true;
+    } else {
+      ++oy;
+      Lbase += s;
+      Lnext = Lbase + KH;
+      fresh = false;
+    }
+  }
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
+  extern __shared__ unsigned char smem_dyn[];
+  __shared__ __align__(8) u64 s_full[MAX_SLOTS];
+  __shared__ __align__(8) u64 s_empty[MAX_SLOTS];
+  __shared__ __align__(8) u64 s_tfull[2];
+  __shared__ __align__(8) u64 s_tempty[2];
+  __shared__ __align__(8) u64 s_bfull;
+  __shared__ u32 s_tmem;
+
+  const cnb_conv_desc& d = a.d;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const u32 smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  const u32 ring_base = smem_base + a.b_bytes;
+  float* s_scale = reinterpret_cast<float*>(smem_dyn + (smem_base - smem_u32(smem_dyn)) + a.b_bytes +
+                                            (size_t)a.nslots * a.slot_bytes);
+  float* s_shift = s_scale + a.BN;
+
+  if (tid == 0) {
+    for (int i = 0; i < a.nslots; ++i) {
+      mbar_init(&s_full[i], NPW);
+      mbar_init(&s_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_tfull[i], 1);
+      mbar_init(&s_tempty[i], 4);
+    }
+    mbar_init(&s_bfull, 1);
+    fence_mbar_init();
+  }
+  if (warp == W_MMA) tmem_alloc(&s_tmem, a.tmem_cols);
+  for (int i = tid; i < a.BN; i += NTHREADS) {
+    s_scale[i] = (i < d.Co && a.scale) ? a.scale[i] : 1.f;
+    s_shift[i] = (i < d.Co && a.shift) ? a.shift[i] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const u32 tmem_base = s_tmem;
+
+  const int u_begin = (int)((long long)blockIdx.x * a.units / gridDim.x);
+  const int u_end = (int)((long long)(blockIdx.x + 1) * a.units / gridDim.x);
+  if (u_begin >= u_end) {
+    __syncthreads();
+    if (warp == W_MMA) tmem_dealloc(tmem_base, a.tmem_cols);
+    return;
+  }
+
+  if (warp < NPW) {
+    // =============================== producers: input rows -> ring slots =====================================
+    RowWalk w;
+    w.start(u_begin, d.Ho, a.s, d.pad, d.KH);
+    const int items = a.s * a.nch * a.PW;
+    int pending[DEPTH];   // load indices whose copies are in flight (oldest first)
+    int npend = 0;
+    auto complete_oldest = [&]() {   // the oldest row's copies have landed (caller waited on the group)
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_full[pending[0] % a.nslots]);
+#pragma unroll
+      for (int i = 1; i < DEPTH; ++i) pending[i - 1] = pending[i];
+      --npend;
+    };
+    for (int u = u_begin; u < u_end; ++u) {
+      const int n = w.strip / a.nseg, seg = w.strip - n * a.nseg;
+      const int q0 = seg * BM + a.q_off;            // q of plane pixel 0
+      const int iy0 = w.oy * a.s - d.pad;
+      for (int L = w.first_new(); L < w.Lnext; ++L) {
+        const int iy = iy0 + (L - w.Lbase);
+        const int slot = L % a.nslots;
+        mbar_wait(&s_empty[slot], (((u32)(L / a.nslots)) & 1u) ^ 1u);
+        const u32 dst0 = ring_base + (u32)slot * a.slot_bytes;
+        const bool row_ok = iy >= 0 && iy < d.Hi;
+        const __nv_bfloat16* rowp = a.x + ((size_t)(n * d.Hi + (row_ok ? iy : 0)) * d.Wi) * d.x_cstride + d.x_coffset;
+        for (int it = tid; it < items; it += NPT) {
+          const int c = it % a.nch;
+          const int r = it / a.nch;
+          const int j = r % a.PW, p = r / a.PW;
+          const int xg = a.s * (q0 + j) + p;
+          const bool ok = row_ok && xg >= 0 && xg < d.Wi;
+          const __nv_bfloat16* src = ok ? rowp + (size_t)xg * d.x_cstride + c * 8 : a.x;
+          cp_async16(dst0 + (u32)(p * a.nch + c) * a.plane_bytes + (u32)j * 16u, src, ok ? 16u : 0u);
+        }
+        cp_async_commit();
+        pending[npend++] = L;
+        if (npend == DEPTH) {
+          cp_async_wait<DEPTH - 1>();
+          complete_oldest();
+        }
+      }
+      w.next();
+    }
+    while (npend > 0) {   // drain
+      cp_async_wait<0>();
+      complete_oldest();
+    }
+  } else if (warp == W_MMA) {
+    // =============================== MMA issuer ==============================================================
+    if (lane == 0) {
+      // resident weights
+      mbar_expect_tx(&s_bfull, a.b_bytes);
+      for (int sl = 0; sl < a.nslab; ++sl) tma_load_2d(smem_base + (u32)sl * a.b_slab_bytes, &tmB, sl * 64, 0, &s_bfull);
+      mbar_wait(&s_bfull, 0);
+      RowWalk w;
+      w.start(u_begin, d.Ho, a.s, d.pad, d.KH);
+      const int ncp = a.nch >= 2 ? a.nch / 2 : 0;
+      u32 t = 0;
+      for (int u = u_begin; u < u_end; ++u, ++t) {
+        for (int L = w.first_new(); L < w.Lnext; ++L) mbar_wait(&s_full[L % a.nslots], ((u32)(L / a.nslots)) & 1u);
+        const u32 acc = t & 1u, acc_ph = (t >> 1) & 1u;
+        mbar_wait(&s_tempty[acc], acc_ph ^ 1u);
+        tc_fence_after();
+        const u32 tmem_d = tmem_base + acc * a.acc_stride;
+        u32 accumulate = 0;
+        int ks = 0;
+        for (int kh = 0; kh < d.KH; ++kh) {
+          const u32 slot_addr = ring_base + (u32)((w.Lbase + kh) % a.nslots) * a.slot_bytes;
+          if (ncp) {
+            for (int kw = 0; kw < d.KW; ++kw) {
+              // input x = s*ox + kw - pad = s*(ox + dq) + phase
+              const int off = kw - d.pad;
+              const int dq = off >= 0 ? off / a.s : -((-off + a.s - 1) / a.s);
+              const int p = off - dq * a.s;
+              for (int cp = 0; cp < ncp; ++cp, ++ks) {
+                const u32 astart = slot_addr + (u32)(p * a.nch + 2 * cp) * a.plane_bytes + (u32)(dq - a.q_off) * 16u;
+                const u64 da = make_sdesc(astart, a.plane_bytes, 128, 0);
+                const u64 db = make_sdesc(smem_base + (u32)(ks >> 2) * a.b_slab_bytes, 16, 1024, 2) + (u64)(2 * (ks & 3));
+                umma_bf16(tmem_d, da, db, a.idesc, accumulate);
+                accumulate = 1;
+              }
+            }
+          } else {
+            for (int j = 0; j < a.KWp / 2; ++j, ++ks) {   // 8 channels: one K=16 step = the taps kw = 2j, 2j+1
+              const u32 astart = slot_addr + (u32)(2 * j) * 16u;
+              const u64 da = make_sdesc(astart, 16, 128, 0);
+              const u64 db = make_sdesc(smem_base + (u32)(ks >> 2) * a.b_slab_bytes, 16, 1024, 2) + (u64)(2 * (ks & 3));
+              umma_bf16(tmem_d, da, db, a.idesc, accumulate);
+              accumulate = 1;
+            }
+          }
+        }
+        // release the input rows no later unit needs
+        const int nrel = w.last_of_run(u, u_end) ? d.KH : a.s;
+        for (int i = 0; i < nrel; ++i) umma_commit(&s_empty[(w.Lbase + i) % a.nslots]);
+        umma_commit(&s_tfull[acc]);
+        w.next();
+      }
+    }
+  } else {
+    // =============================== epilogue ================================================================
+    const int q = warp & 3;
+    const int HoWo = d.Ho * d.Wo;
+    int strip = u_begin / d.Ho;
+    int oy = u_begin - strip * d.Ho;
+    u32 t = 0;
+    for (int u = u_begin; u < u_end; ++u, ++t) {
+      const int n = strip / a.nseg, seg = strip - n * a.nseg;
+      const u32 acc = t & 1u, acc_ph = (t >> 1) & 1u;
+      const int opix = oy * d.Wo + seg * BM + 32 * q + lane;
+      const int m = n * HoWo + opix;
+      mbar_wait(&s_tfull[acc], acc_ph);
+      tc_fence_after();
+      const u32 taddr = tmem_base + acc * a.acc_stride + ((u32)(32 * q) << 16);
+      const int ngroups = a.BN / 16;
+      for (int g = 0; g < ngroups; ++g) {
+        u32 v[16];
+        tmem_ld16_nowait(taddr + (u32)(g * 16), v);
+        tmem_ld_wait();
+        const int co0 = g * 16;
+        if (co0 < d.Co) epilogue_store(a, s_scale, s_shift, v, m, co0, co0, HoWo, n, opix);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_tempty[acc]);
+      if (++oy == d.Ho) {
+        oy = 0;
+        ++strip;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) tmem_dealloc(tmem_base, a.tmem_cols);
+}
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+struct RPlan {
+  RArgs a;
+  size_t smem;
+};
+
+// false when this geometry is not covered
+static bool plan_rows(const cnb_conv_desc* d, RPlan* p) {
+  static const bool off = [] { const char* e = getenv("CNB_CONV_ROWS"); return e && e[0] == '0'; }();
+  if (off) return false;
+  const int Ci = d->Ci, s = d->stride;
+  if (!(Ci == 8 || Ci == 16 || Ci == 32 || Ci == 64)) return false;
+  if (!(s == 1 || s == 2) || d->dil != 1 || d->KH != d->KW || d->KH % 2 == 0 || d->pad != d->KH / 2) return false;
+  if (d->KH < 3) return false;                       // 1x1: nothing to reuse, the im2col kernel is fine
+  if (d->Wo % BM != 0 || d->Ho < 1) return false;
+  if (d->Wi != d->Wo * s || d->Hi != d->Ho * s) return false;
+  const int KWp = d->w_kw > 0 ? d->w_kw : d->KW;
+  if (Ci == 8 && (s != 1 || KWp % 2 != 0 || KWp < d->KW)) return false;
+  if (Ci != 8 && KWp != d->KW) return false;
+  RArgs& a = p->a;
+  a.s = s;
+  a.nch = Ci / 8;
+  a.KWp = KWp;
+  // plane pixel range: q in [ox0 + floor(-pad/s), ox0 + 127 + floor((KWp-1-pad)/s)]
+  a.q_off = -((d->pad + s - 1) / s);
+  const int q_hi = (KWp - 1 - d->pad) / s;           // KWp-1-pad >= 0
+  a.PW = BM + q_hi - a.q_off;
+  int pw_alloc = a.PW;
+  if (a.nch > 2)                                     // plane stride == 16 B mod 128 B: the 8 chunk planes of a pixel
+    while ((pw_alloc * 16) % 128 != 16) ++pw_alloc;  // fall into distinct banks for the producers' stores
+  a.plane_bytes = (u32)pw_alloc * 16u;
+  a.slot_bytes = (u32)(s * a.nch) * a.plane_bytes;
+  a.nslots = d->KH + s + DEPTH;
+  if (a.nslots > MAX_SLOTS) return false;
+  a.nseg = d->Wo / BM;
+  const long long units = (long long)d->B * a.nseg * d->Ho;
+  if (units >= (1ll << 31)) return false;
+  a.units = (int)units;
+  a.BN = round_up(d->Co, 16);
+  if (a.BN > 256) return false;
+  const int Ktot = d->KH * KWp * Ci;
+  const int Kpad = round_up(Ktot, 64);
+  if (Ktot % 16 != 0) return false;
+  a.nslab = Kpad / 64;
+  a.b_slab_bytes = (u32)a.BN * 128u;
+  a.b_bytes = (u32)a.nslab * a.b_slab_bytes;
+  a.b_bytes = (a.b_bytes + 1023u) & ~1023u;
+  a.acc_stride = (u32)round_up(a.BN, 32);
+  a.tmem_cols = 32;
+  while (a.tmem_cols < 2 * a.acc_stride) a.tmem_cols <<= 1;
+  a.idesc = make_idesc_bf16(BM, a.BN);
+  p->smem = (size_t)a.b_bytes + (size_t)a.nslots * a.slot_bytes + (size_t)a.BN * 8 + 1024;
+  return p->smem <= 200 * 1024;
+}
+
+}  // namespace
+
+bool conv_rows_supported(const cnb_conv_desc* d) {
+  RPlan p;
+  return plan_rows(d, &p);
+}
+
+int conv_rows_run(const cnb_conv_desc* d, const void* x, const void* wpk, const float* scale, const float* shift,
+                  const void* res, void* y, cudaStream_t st) {
+  TmaDriver& drv = tma_driver();
+  if (!drv.ok) {
+    set_error("conv: cuTensorMapEncodeTiled entry point unavailable (driver too old?)");
+    return CNB_ERR_CUDA;
+  }
+  RPlan p;
+  CNB_CHECK_ARG(plan_rows(d, &p), "conv_rows: unsupported geometry");
+  RArgs& a = p.a;
+  a.d = *d;
+  a.x = (const __nv_bfloat16*)x;
+  a.scale = scale;
+  a.shift = shift;
+  a.res = (const __nv_bfloat16*)res;
+  a.y = y;
+  CUtensorMap tmB;
+  {
+    const int Kpad = a.nslab * 64;
+    cuuint64_t dims[2] = {(cuuint64_t)Kpad, (cuuint64_t)a.BN};
+    cuuint64_t strides[1] = {(cuuint64_t)Kpad * 2};
+    cuuint32_t box[2] = {64u, (cuuint32_t)a.BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = drv.tiled(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)wpk, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("conv_rows: cuTensorMapEncodeTiled failed (%d) Kpad=%d BN=%d", (int)r, Kpad, a.BN);
+      return CNB_ERR_CUDA;
+    }
+  }
+  static bool configured = false;
+  if (!configured) {
+    CNB_CUDA(cudaFuncSetAttribute(conv_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    configured = true;
+  }
+  const int grid = a.units < drv.num_sms ? a.units : drv.num_sms;
+  conv_rows_kernel<<<grid, NTHREADS, p.smem, st>>>(tmB, a);
+  CNB_LAUNCH_CHECK();
+  return CNB_OK;
+}
+
+}  // namespace cnb

@@ -20,7 +20,10 @@
 namespace cnb {
 int conv_tma_run(const cnb_conv_desc* d, const void* x, const void* wpk, const float* scale, const float* shift,
                  const void* res, void* y, cudaStream_t st);   // conv_tma.cu
-bool dcn_ws_supported(const cnb_conv_desc* d);                  // dcn_ws.cu
+bool conv_rows_supported(const cnb_conv_desc* d);                // conv_rows.cu
+int conv_rows_run(const cnb_conv_desc* d, const void* x, const void* wpk, const float* scale, const float* shift,
+                  const void* res, void* y, cudaStream_t st);
+bool dcn_ws_supported(const cnb_conv_desc* d, int om_cstride);                  // dcn_ws.cu
 int dcn_ws_run(const cnb_conv_desc* d, const void* x, const float* om, int om_cstride, const void* wpk,
                const float* scale, const float* shift, void* y, cudaStream_t st);
 namespace {
@@ -94,6 +97,7 @@ struct ConvArgs {
   int om_cstride;
   int M;                     // B*Ho*Wo
   int Ktot, Kpad, nkb;
+  int KWp;                   // filter width of the packed weights (>= KW; extra columns are zero)
   int BN;                    // N tile (multiple of 16, <= 256)
   int Co_pad;
   u32 tmem_cols;
@@ -179,7 +183,7 @@ __global__ void __launch_bounds__(CT) conv_umma_kernel(const ConvArgs a) {
     const int kg = kb * BK + cchunk * 8;   // first K index of this thread's chunk
     const int tap = kg / d.Ci;
     const int ci = kg - tap * d.Ci;
-    const int kh = tap / d.KW, kw = tap - kh * d.KW;
+    const int kh = tap / a.KWp, kw = tap - kh * a.KWp;
     const bool kvalid = kg < a.Ktot;
     if (!DCN) {
 #pragma unroll
@@ -376,7 +380,7 @@ struct Plan {
 static Plan make_plan(const cnb_conv_desc& d) {
   Plan p;
   p.Co_pad = round_up(d.Co, 16);
-  p.Ktot = d.KH * d.KW * d.Ci;
+  p.Ktot = d.KH * (d.w_kw > 0 ? d.w_kw : d.KW) * d.Ci;
   p.Kpad = round_up(p.Ktot, BK);
   p.nkb = p.Kpad / BK;
   p.BN = p.Co_pad <= 128 ? p.Co_pad : 128;
@@ -432,7 +436,7 @@ static int run_conv(const cnb_conv_desc* d, const void* x, const float* om, int 
     CNB_CHECK_ARG(d->Ci % 8 == 0, "dcnv2: Ci must be a multiple of 8");
     CNB_CHECK_ARG(d->out_nchw_f32 == 0 && ((uintptr_t)om & 15) == 0, "dcnv2: NHWC bf16 output, 16-byte aligned om");
     // warp-specialised sampler kernel (dcn_ws.cu); CNB_DCN_IMPL=v1 keeps the gather kernel below for A/B runs
-    if (dcn_ws_supported(d)) return dcn_ws_run(d, x, om, om_cstride, wpk, scale, shift, y, st);
+    if (dcn_ws_supported(d, om_cstride)) return dcn_ws_run(d, x, om, om_cstride, wpk, scale, shift, y, st);
   }
   if (!dcn) {
     // plain convolutions: TMA-im2col warp-specialised kernel (conv_tma.cu); CNB_CONV_IMPL=v1 keeps the
@@ -440,7 +444,11 @@ static int run_conv(const cnb_conv_desc* d, const void* x, const float* om, int 
     static const bool use_v1 = [] { const char* e = getenv("CNB_CONV_IMPL"); return e && e[0] == 'v' && e[1] == '1'; }();
     // thin inputs (Ci < 32: 16/32-byte im2col rows) are far below the TMA engine's efficient row size; they
     // stay on the cp.async gather until the shared-memory patch kernel covers them
-    if (!use_v1 && (d->Ci >= 32)) return conv_tma_run(d, x, wpk, scale, shift, res, y, st);
+    CNB_CHECK_ARG(d->w_kw == 0 || d->w_kw >= d->KW, "conv: w_kw=%d smaller than KW=%d", d->w_kw, d->KW);
+    // wide thin layers (W_out % 128 == 0, Ci <= 64, KxK): row-window kernel, every input pixel fetched once
+    if (!use_v1 && conv_rows_supported(d)) return conv_rows_run(d, x, wpk, scale, shift, res, y, st);
+    if (!use_v1 && (d->Ci >= 32) && (d->w_kw == 0 || d->w_kw == d->KW))
+      return conv_tma_run(d, x, wpk, scale, shift, res, y, st);
   }
   const Plan p = make_plan(*d);
   ConvArgs a;
@@ -455,6 +463,7 @@ static int run_conv(const cnb_conv_desc* d, const void* x, const float* om, int 
   a.om_cstride = om_cstride;
   a.M = (int)M;
   a.Ktot = p.Ktot;
+  a.KWp = d->w_kw > 0 ? d->w_kw : d->KW;
   a.Kpad = p.Kpad;
   a.nkb = p.nkb;
   a.BN = p.BN;

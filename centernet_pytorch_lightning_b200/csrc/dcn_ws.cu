@@ -27,16 +27,18 @@ namespace cnb {
 namespace {
 
 constexpr int BM = 128;
-constexpr int NPROD_WARPS = 8;                       // sampler warps: 256 threads, 4 pixel rows x one 8-ch chunk each
+constexpr int NPROD_WARPS = 16;                      // sampler warps: 512 threads, 2 pixel rows x one 8-ch chunk each
 constexpr int NPROD = NPROD_WARPS * 32;
 constexpr int NSETUP_WARPS = 4;
 constexpr int NSETUP = NSETUP_WARPS * 32;
-constexpr int W_SETUP0 = NPROD_WARPS;                // warps 8..11
-constexpr int W_MMA = W_SETUP0 + NSETUP_WARPS;       // warp 12
-constexpr int W_EPI0 = W_MMA + 1;                    // warps 13..16 (TMEM lane quarters 1,2,3,0)
-constexpr int NTHREADS = (W_EPI0 + 4) * 32;          // 544
+constexpr int W_SETUP0 = NPROD_WARPS;                // warps 16..19
+constexpr int W_MMA = W_SETUP0 + NSETUP_WARPS;       // warp 20
+constexpr int W_EPI0 = W_MMA + 1;                    // warps 21..24 (TMEM lane quarters 1,2,3,0)
+constexpr int NTHREADS = (W_EPI0 + 4) * 32;          // 800
+constexpr int ROWS_PT = BM * 8 / NPROD;              // pixel rows per sampler thread and K block
 constexpr int MAX_STAGES = 6;
 constexpr int NTAB = BM * 9;                         // (pixel, tap) entries per tile
+constexpr int OM_CS = 32;                            // channel stride of the offset/mask map this kernel takes
 constexpr u32 A_BYTES = BM * 64 * 2;                 // one K block of the sampled operand: 128 rows x 128 B
 
 struct DArgs {
@@ -86,6 +88,7 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
   __shared__ __align__(8) u64 s_tempty[2];
   __shared__ __align__(8) u64 s_tabfull[2];
   __shared__ __align__(8) u64 s_tabempty[2];
+  __shared__ __align__(8) u64 s_omfull[2];
   __shared__ u32 s_tmem;
 
   const cnb_conv_desc& d = a.d;
@@ -94,7 +97,8 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
   unsigned char* smem_al = smem_dyn + (smem_base - smem_u32(smem_dyn));
   float4* s_tabw = reinterpret_cast<float4*>(smem_al + (size_t)a.stages * a.stage_bytes);   // [2][NTAB]
   u32* s_tabb = reinterpret_cast<u32*>(s_tabw + 2 * NTAB);                                  // [2][NTAB]
-  float* s_scale = reinterpret_cast<float*>(s_tabb + 2 * NTAB);
+  float* s_om = reinterpret_cast<float*>(s_tabb + 2 * NTAB);                                // [2][BM][OM_CS]
+  float* s_scale = s_om + 2 * BM * OM_CS;
   float* s_shift = s_scale + a.BN;
 
   if (tid == 0) {
@@ -107,8 +111,10 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
       mbar_init(&s_tempty[i], 4);
       mbar_init(&s_tabfull[i], NSETUP_WARPS);
       mbar_init(&s_tabempty[i], NPROD_WARPS);
+      mbar_init(&s_omfull[i], 1);
     }
     fence_mbar_init();
+    fence_proxy_async_smem();
   }
   if (warp == 0 && lane == 0) tma_prefetch_desc(&tmB);
   if (warp == W_MMA) tmem_alloc(&s_tmem, a.tmem_cols);
@@ -121,22 +127,25 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
   tc_fence_after();
   const u32 tmem_base = s_tmem;
   const int HW = d.Hi * d.Wi;
+  // contiguous tile range per CTA: consecutive tiles are neighbouring image rows, whose sampling footprints
+  // overlap in L1 / L2
+  const int tile_begin = (int)((long long)blockIdx.x * a.m_tiles / gridDim.x);
+  const int tile_end = (int)((long long)(blockIdx.x + 1) * a.m_tiles / gridDim.x);
 
   if (warp < NPROD_WARPS) {
     // =============================== samplers ===============================================================
     const int chunk = tid & 7;          // 16-byte channel chunk inside the 64-channel slab
-    const int r0 = tid >> 3;            // rows r0 + 32*i
+    const int r0 = tid >> 3;            // rows r0 + (NPROD/8)*i
     const u32 cs = (u32)d.x_cstride;
     const u32 row_step = (u32)d.Wi * cs;
-    u32 it = 0, t = 0;
-    for (int tile = blockIdx.x; tile < a.m_tiles; tile += gridDim.x, ++t) {
+    u32 s = 0, ph = 0, t = 0;
+    for (int tile = tile_begin; tile < tile_end; ++tile, ++t) {
       const u32 tb = t & 1u;
       mbar_wait(&s_tabfull[tb], (t >> 1) & 1u);
       const float4* tw = s_tabw + tb * NTAB;
       const u32* tbs = s_tabb + tb * NTAB;
       int slab = 0, tap = 0;
-      for (int kb = 0; kb < a.nkb; ++kb, ++it) {
-        const u32 s = it % (u32)a.stages, ph = (it / (u32)a.stages) & 1u;
+      for (int kb = 0; kb < a.nkb; ++kb) {
         mbar_wait(&s_empty[s], ph ^ 1u);
         const u32 sa = smem_base + s * a.stage_bytes;
         if (tid == 0) {
@@ -144,14 +153,13 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
           tma_load_2d(sa + A_BYTES, &tmB, tap * d.Ci + slab * 64, 0, &s_full[s]);
         }
         const __nv_bfloat16* xs = a.x + d.x_coffset + slab * 64 + chunk * 8;
+        {
+          uint4 q[ROWS_PT][4];
+          float4 w[ROWS_PT];
+          u64 ww[ROWS_PT][4];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint4 q[2][4];
-          float4 w[2];
-          u64 ww[2][4];
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const int item = (r0 + 32 * (2 * h + i)) * 9 + tap;
+          for (int i = 0; i < ROWS_PT; ++i) {
+            const int item = (r0 + (NPROD / 8) * i) * 9 + tap;
             w[i] = tw[item];
             ww[i][0] = dup2(w[i].x); ww[i][1] = dup2(w[i].y); ww[i][2] = dup2(w[i].z); ww[i][3] = dup2(w[i].w);
             const u32 b = tbs[item];
@@ -164,8 +172,8 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
             q[i][3] = __ldg(reinterpret_cast<const uint4*>(xs + (o01 + ddy)));
           }
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const int row = r0 + 32 * (2 * h + i);
+          for (int i = 0; i < ROWS_PT; ++i) {
+            const int row = r0 + (NPROD / 8) * i;
             u32 o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -193,17 +201,37 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
           tap = 0;
           ++slab;
         }
+        if (++s == (u32)a.stages) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_tabempty[tb]);
     }
   } else if (warp < W_MMA) {
     // =============================== setup: (pixel, tap) -> weights + corner address =========================
+    // The tile's 128 x 32 offset/mask floats are one contiguous 16 KB run of the NHWC fp32 map: a 1-D bulk copy
+    // (double buffered, issued two tiles ahead) stages them in shared memory, so the table math never waits on
+    // global memory.
     const int stid = tid - W_SETUP0 * 32;
+    auto issue_om = [&](int tile, u32 buf) {
+      const int m0 = tile * BM;
+      const int rows = min(BM, a.M - m0);
+      const u32 bytes = (u32)rows * OM_CS * 4u;
+      mbar_expect_tx(&s_omfull[buf], bytes);
+      bulk_g2s(s_om + buf * (BM * OM_CS), a.om + (size_t)m0 * OM_CS, bytes, &s_omfull[buf]);
+    };
+    if (stid == 0) {
+      if (tile_begin < tile_end) issue_om(tile_begin, 0);
+      if (tile_begin + 1 < tile_end) issue_om(tile_begin + 1, 1);
+    }
     u32 t = 0;
-    for (int tile = blockIdx.x; tile < a.m_tiles; tile += gridDim.x, ++t) {
+    for (int tile = tile_begin; tile < tile_end; ++tile, ++t) {
       const u32 tb = t & 1u;
       mbar_wait(&s_tabempty[tb], ((t >> 1) & 1u) ^ 1u);
+      mbar_wait(&s_omfull[tb], (t >> 1) & 1u);
+      const float* oms = s_om + tb * (BM * OM_CS);
       const int m0 = tile * BM;
 #pragma unroll 3
       for (int item = stid; item < NTAB; item += NSETUP) {
@@ -216,10 +244,10 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
           const int rem = m - n * HW;
           const int oy = rem / d.Wi, ox = rem - oy * d.Wi;
           const int kh = tap / 3, kw = tap - 3 * kh;
-          const float* omp = a.om + (size_t)m * a.om_cstride;
-          const float dy = __ldg(omp + 2 * tap);
-          const float dx = __ldg(omp + 2 * tap + 1);
-          const float mk = 1.f / (1.f + __expf(-__ldg(omp + 18 + tap)));
+          const float* omp = oms + r * OM_CS;
+          const float dy = omp[2 * tap];
+          const float dx = omp[2 * tap + 1];
+          const float mk = 1.f / (1.f + __expf(-omp[18 + tap]));
           const float py = (float)(oy - 1 + kh) + dy;
           const float px = (float)(ox - 1 + kw) + dx;
           if (py > -1.f && px > -1.f && py < (float)d.Hi && px < (float)d.Wi) {
@@ -242,19 +270,21 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_tabfull[tb]);
+      // all setup warps are done with this om buffer: refill it for tile + 2
+      asm volatile("bar.sync 1, %0;" ::"n"(NSETUP) : "memory");
+      if (stid == 0 && tile + 2 < tile_end) issue_om(tile + 2, tb);
     }
   } else if (warp == W_MMA) {
     // =============================== MMA issuer ==============================================================
     if (lane == 0) {
-      u32 it = 0, t = 0;
-      for (int tile = blockIdx.x; tile < a.m_tiles; tile += gridDim.x, ++t) {
+      u32 s = 0, ph = 0, t = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile, ++t) {
         const u32 acc = t & 1u, acc_ph = (t >> 1) & 1u;
         mbar_wait(&s_tempty[acc], acc_ph ^ 1u);
         tc_fence_after();
         const u32 tmem_d = tmem_base + acc * a.acc_stride;
         u32 accumulate = 0;
-        for (int kb = 0; kb < a.nkb; ++kb, ++it) {
-          const u32 s = it % (u32)a.stages, ph = (it / (u32)a.stages) & 1u;
+        for (int kb = 0; kb < a.nkb; ++kb) {
           mbar_wait(&s_full[s], ph);
           tc_fence_after();
           const u32 sa = smem_base + s * a.stage_bytes;
@@ -266,6 +296,10 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
             accumulate = 1;
           }
           umma_commit(&s_empty[s]);
+          if (++s == (u32)a.stages) {
+            s = 0;
+            ph ^= 1u;
+          }
         }
         umma_commit(&s_tfull[acc]);
       }
@@ -274,7 +308,7 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
     // =============================== epilogue ================================================================
     const int q = warp & 3;
     u32 t = 0;
-    for (int tile = blockIdx.x; tile < a.m_tiles; tile += gridDim.x, ++t) {
+    for (int tile = tile_begin; tile < tile_end; ++tile, ++t) {
       const u32 acc = t & 1u, acc_ph = (t >> 1) & 1u;
       const int m = tile * BM + 32 * q + lane;
       mbar_wait(&s_tfull[acc], acc_ph);
@@ -303,9 +337,9 @@ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 }  // namespace
 
 // Geometries this kernel covers (the rest stays on the cp.async gather kernel of conv_umma.cu).
-bool dcn_ws_supported(const cnb_conv_desc* d) {
+bool dcn_ws_supported(const cnb_conv_desc* d, int om_cstride) {
   static const bool off = [] { const char* e = getenv("CNB_DCN_IMPL"); return e && e[0] == 'v' && e[1] == '1'; }();
-  return !off && d->Ci % 64 == 0 && d->Co % 8 == 0 && round_up(d->Co, 16) <= 256 &&
+  return !off && om_cstride == OM_CS && d->Ci % 64 == 0 && d->Co % 8 == 0 && round_up(d->Co, 16) <= 256 &&
          (long long)d->B * d->Hi * d->Wi * d->x_cstride < (1ll << 30);
 }
 
@@ -331,9 +365,10 @@ int dcn_ws_run(const cnb_conv_desc* d, const void* x, const float* om, int om_cs
   a.nkb = 9 * (d->Ci / 64);
   a.b_bytes = (u32)a.BN * 128u;
   a.stage_bytes = A_BYTES + ((a.b_bytes + 1023u) & ~1023u);
-  const size_t fixed = (size_t)2 * NTAB * (sizeof(float4) + sizeof(u32)) + (size_t)a.BN * 8 + 1024;
+  const size_t fixed = (size_t)2 * NTAB * (sizeof(float4) + sizeof(u32)) + (size_t)2 * BM * OM_CS * 4 +
+                       (size_t)a.BN * 8 + 1024;
   static const int env_stages = [] { const char* e = getenv("CNB_DCN_STAGES"); return e ? atoi(e) : 0; }();
-  a.stages = env_stages > 0 ? env_stages : (a.BN <= 64 ? 4 : 3);
+  a.stages = env_stages > 0 ? env_stages : 3;
   if (a.stages > MAX_STAGES) a.stages = MAX_STAGES;
   while (a.stages > 2 && (size_t)a.stages * a.stage_bytes + fixed > 220 * 1024) --a.stages;
   a.acc_stride = (u32)round_up(a.BN, 32);

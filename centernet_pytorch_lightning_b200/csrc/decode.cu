@@ -1,56 +1,82 @@
 // Fused decode for CenterNet heads: 3x3 max-pool NMS + top-K peak extraction + offset gather.
 //
 // Replaces (reference file:line, all under CenterNet/):
-//   utils/decode.py:5-10   _nms                 -> plane_scan_kernel (sliding 3x3 max in smem)
-//   utils/decode.py:13-28  _topk                -> per-plane candidate lists + per-image merge
-//   utils/decode.py:31-40  _topk_channel        -> exact per-plane lists
+//   utils/decode.py:5-10   _nms                 -> decode_scan_kernel (3x3 test in the smem tile, only where needed)
+//   utils/decode.py:13-28  _topk                -> streaming selection with a per-image running threshold
+//   utils/decode.py:31-40  _topk_channel        -> the same with one group per plane
 //   utils/decode.py:59-63  _transpose_and_gather_feat -> direct NCHW gathers at the K winners
-//   decode/ctdet.py:6-38   ctdet_decode         -> plane_scan_kernel<.., FUSE_CTDET> (one launch;
-//                                                  the last CTA of an image merges and writes [K,6])
-//   decode/multi_pose.py:7-96 multi_pose_decode -> plane_scan_kernel + multi_pose_assoc_kernel
+//   decode/ctdet.py:6-38   ctdet_decode         -> decode_scan_kernel (one launch; the CTA that completes an
+//                                                  image merges its candidates and writes [K,6])
+//   decode/multi_pose.py:7-96 multi_pose_decode -> decode_scan_kernel + multi_pose_assoc_kernel
 //
-// Data layout in HBM: heat maps NCHW fp32 exactly as the heads emit them.  Every (image, class)
-// plane (or a band of rows of it) is streamed ONCE from HBM into shared memory with a 1-D TMA bulk
-// copy; algorithmic traffic = C*H*W*4 B per image (+ a few KB of candidates), see DESIGN.md.
+// Data layout in HBM: heat maps NCHW fp32 exactly as the heads emit them.  They are streamed ONCE:
+// persistent CTAs (2 per SM) each own a contiguous range of (group, plane, band-of-rows) chunks and pull them
+// through a 4-stage ring of 1-D TMA bulk copies; algorithmic traffic = C*H*W*4 B per image (+ a few KB of
+// candidates), see DESIGN.md.
 //
-// Ordering: all selections use 64-bit keys  (score_bits << 32) | (0xFFFFFFFF - flat_index)  so that
-// "larger key" == (higher score, then lower flat index); keys are distinct, which makes every
-// selection deterministic.  Scores must be >= 0 (sigmoid outputs, as at every reference call site).
+// Selection.  A *group* is the set of planes that compete in one top-K (ctdet: the C class planes of an image;
+// multi_pose: every plane on its own).  All selections order 64-bit keys
+//     (score_bits << 32) | (0xFFFFFFFF - flat_index)        "larger key" == (higher score, then lower index)
+// which are distinct, so every result is deterministic (the reference leaves ties to torch.topk).  Scores must
+// be >= 0 (sigmoid outputs, as at every reference call site).  Per group the kernel keeps in global memory
+//   thr   : a monotone lower bound of the group's K-th largest key (atomicMax),
+//   hist  : counts of NMS survivors per score bin (7 mantissa bits, scores in [2^-8, 1]); whenever the counts
+//           of the bins >= t reach K, (edge(t) << 32) is a sound new bound,
+//   list  : appended candidate keys (only those >= thr at the time).
+// A tile element is looked at closely only if its value reaches the bound (`max4 >= thr`): in steady state the
+// scan is one LDS.128 + 3 FMNMX + 1 compare per 4 elements, so the kernel is HBM bound.  Chunks that hold more
+// than ACAP live survivors (the first chunks of a group, plateaus of equal scores) take an exact radix select
+// over the 64-bit keys, which also publishes an exact bound -- ties are then pruned by index.
 #include "cnb_common.cuh"
+#include <stdlib.h>
 
 namespace cnb {
 namespace {
 
 constexpr int NT = 256;          // threads per CTA
 constexpr int NW = NT / 32;
-constexpr int SURV_CAP = 1024;   // survivors kept in smem during a merge
 constexpr int MAX_K = 512;
+constexpr int NST = 4;           // tile stages in flight per CTA
+constexpr int NB = 1026;         // score histogram bins
+constexpr int BIN_BASE = 0x3B7F; // (bits >> 16) of 2^-8, minus 1: bin 0 = everything below 2^-8
+constexpr int FB0 = 513;         // first coarse bin (score 2^-4) that has fine sub-bins
+constexpr int FSUB = 32;         // fine sub-bins per coarse bin (5 more mantissa bits)
+constexpr int NBF = (NB - FB0) * FSUB;
+constexpr int MCAP = 2048;       // merge candidates staged in shared memory
+constexpr int RANK_DIRECT = 384; // up to this many candidates are ranked by direct counting
+constexpr int HCAP = 512;        // hit positions recorded per chunk before the dense path takes over
+constexpr int FLUSH_AT = 64;     // live survivors a CTA carries across chunks before it talks to global memory
 
 struct ScanArgs {
   const float* t0;   // [B, C0, H, W]
   const float* t1;   // [B, C1, H, W] or nullptr
   int C0, C1;
+  int PG;            // planes per group
+  int G;             // groups
   int B, H, W, K;
-  int R;        // rows per band
+  int R;             // rows per chunk
   int nbands;
-  int rpt;      // rows per thread segment
-  int cap;      // list capacity (keys)
-  int exact0, exact1;   // emit exact sorted top-K lists for planes of t0 / t1
-  u64* lists;   // per-list mode: [B*P*nbands][cap]; fused ctdet: [B][P*nbands*cap] append arrays
-  int* counts;  // per-list mode: [B*P*nbands];      fused ctdet: [B] append cursors (zeroed)
-  // fused ctdet epilogue
-  int* done;    // [B] arrival counters (zeroed by the host wrapper)
-  const float* wh;
+  int rpt;           // rows per thread segment
+  int acap;          // live survivors a chunk may append (>= K)
+  int cpg;           // chunks per group
+  int total_chunks;
+  int gcap;          // candidate list capacity per group
+  int tile_bytes;
+  // per-group state (zeroed by the host wrapper before the launch)
+  u64* thr;          // [G]
+  int* gcount;       // [G]
+  int* gdone;        // [G]
+  int* gtop;         // [G]
+  int* ghist;        // [G][NB]
+  int* gfine;        // [G][NBF] or nullptr: sub-bins of the coarse bins >= FB0 (large groups only)
+  u64* lists;        // [G][gcap]
+  // results
+  u64* topk;         // multi_pose: [G][K] sorted keys
+  int* have;         // multi_pose: [G]
+  const float* wh;   // fused ctdet epilogue
   const float* reg;
-  float* out;   // [B,K,6]
-};
-
-struct SelSmem {
-  u64* list;     // [SURV_CAP]
-  u64* out;      // [MAX_K]
-  u32* vals;     // [NT]
-  int* red;      // [NW]
-  int* misc;     // [4]  (0: n, 1: flag, 2..3: bound lo/hi)
+  float* out;        // [B,K,6]
+  int fuse_ctdet;
 };
 
 __device__ __forceinline__ u64 make_key(float score, u32 flat) {
@@ -59,62 +85,31 @@ __device__ __forceinline__ u64 make_key(float score, u32 flat) {
 __device__ __forceinline__ u32 key_hi(u64 k) { return (u32)(k >> 32); }
 __device__ __forceinline__ u32 key_idx(u64 k) { return 0xFFFFFFFFu - (u32)(k & 0xFFFFFFFFull); }
 
-__device__ __forceinline__ int block_sum(int v, int* red) {
-  v = warp_sum(v);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  int t = 0;
-#pragma unroll
-  for (int i = 0; i < NW; ++i) t += red[i];
-  __syncthreads();
-  return t;
+__device__ __forceinline__ int score_bin(u32 bits) {
+  const int b = (int)(bits >> 16) - BIN_BASE;
+  return min(max(b, 0), NB - 1);
+}
+__device__ __forceinline__ u32 bin_edge_bits(int bin) { return (u32)(bin + BIN_BASE) << 16; }   // bin >= 1
+
+__device__ __forceinline__ u64 ldcg_u64(const u64* p) {
+  return __ldcg(reinterpret_cast<const unsigned long long*>(p));
 }
 
-// K-th largest (1-based) of the NT per-thread values; 0 when fewer than K values are non-zero or
-// K > NT.  A sound lower bound for the K-th largest candidate of the block: the thread maxima are
-// K distinct candidates >= the returned value.
-__device__ __forceinline__ u32 block_kth_of_thread_max(u32 tmax, int K, const SelSmem& sm) {
-  sm.vals[threadIdx.x] = tmax;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    u32 v[NW];
-#pragma unroll
-    for (int i = 0; i < NW; ++i) v[i] = sm.vals[threadIdx.x + 32 * i];
-    u32 t = 0;
-    for (int bit = 31; bit >= 0; --bit) {
-      const u32 c = t | (1u << bit);
-      int n = 0;
-#pragma unroll
-      for (int i = 0; i < NW; ++i) n += (v[i] >= c);
-      n = warp_sum(n);
-      if (n >= K) t = c;
-    }
-    if (threadIdx.x == 0) sm.misc[2] = (int)t;
-  }
-  __syncthreads();
-  const u32 b = (u32)sm.misc[2];
-  __syncthreads();
-  return b;
-}
+// ---- shared-memory scratch shared by the selection routines -----------------------------------------------
+struct Scratch {
+  u32* hist;     // [256]
+  int* red;      // [NW]
+  int* misc;     // [8]
+  u64* keyred;   // [2*NW]
+};
 
-// Exact ranking of the n (<= SURV_CAP) distinct keys in sm.list: key with rank r < K goes to sm.out[r].
-__device__ __forceinline__ void block_rank_to_out(int n, int K, const SelSmem& sm) {
-  for (int i = threadIdx.x; i < n; i += NT) {
-    const u64 k = sm.list[i];
-    int r = 0;
-    for (int j = 0; j < n; ++j) r += (sm.list[j] > k);
-    if (r < K) sm.out[r] = k;
-  }
-  __syncthreads();
-}
-
-// ---- candidate iteration over a scanned band (flags -> scores in the smem tile) ------------------
+// ---- candidate enumerators --------------------------------------------------------------------------------
 template <int VEC>
-struct BandCands {
-  const float* tile;   // tile row 0 == global row r0-1
+struct FlagCands {       // survivors of the scanned chunk, kept as a per-thread bit mask
+  const float* tile;     // tile row 0 == global row r0-1
   u64 flags;
   int rs, cg, W, r0;
-  u32 flat_base;       // plane_in_tensor*H*W
+  u32 flat_base;
   template <class F>
   __device__ __forceinline__ void for_each(F f) const {
     u64 fl = flags;
@@ -128,83 +123,103 @@ struct BandCands {
     }
   }
 };
-
-// ---- candidate iteration over global lists (merge) -----------------------------------------------
-struct ListCands {
-  const u64* lists;
-  const int* counts;
-  int nlists, cap;
+struct SmemCands {
+  const u64* list;
+  int n;
   template <class F>
   __device__ __forceinline__ void for_each(F f) const {
-    for (int l = 0; l < nlists; ++l) {
-      const int n = __ldcg(counts + l);
-      for (int s = threadIdx.x; s < n; s += NT) f(__ldcg(lists + (size_t)l * cap + s));
+    for (int i = threadIdx.x; i < n; i += NT) f(list[i]);
+  }
+};
+struct GlobalCands {
+  const u64* list;
+  int n;
+  u64 floor;
+  template <class F>
+  __device__ __forceinline__ void for_each(F f) const {
+    for (int i = threadIdx.x; i < n; i += NT) {
+      const u64 k = ldcg_u64(list + i);
+      if (k >= floor) f(k);
     }
   }
 };
 
-// Exact K-th largest 64-bit key over all candidates of the block (slow path; keys distinct).
+// Exact K-th largest of the CTA's (distinct) candidate keys; the caller guarantees at least K candidates.
+// MSD radix select, 8-bit digits; digits on which all candidates agree are skipped (one AND/OR reduction).
 template <class Cands>
-__device__ u64 block_exact_kth(const Cands& c, int K, const SelSmem& sm) {
-  u64 t = 0;
-  for (int bit = 63; bit >= 0; --bit) {
-    const u64 cand = t | (1ull << bit);
-    int n = 0;
-    c.for_each([&](u64 k) { n += (k >= cand); });
-    n = block_sum(n, sm.red);
-    if (n >= K) t = cand;
-  }
-  return t;
-}
-
-// Put a superset (<= limit keys) of the block's top-K candidates into sm.list; returns its size.
-// `total` = number of candidates of the whole block, tmax = this thread's best score bits.
-template <class Cands>
-__device__ int block_collect(const Cands& c, int total, u32 tmax, int K, int limit, const SelSmem& sm) {
-  u32 bound = 0;
-  if (total > limit) bound = block_kth_of_thread_max(tmax, K, sm);
-  if (threadIdx.x == 0) sm.misc[0] = 0;
-  __syncthreads();
-  if (tmax >= bound && tmax != 0) {
-    c.for_each([&](u64 k) {
-      if (key_hi(k) >= bound) {
-        const int slot = atomicAdd(&sm.misc[0], 1);
-        if (slot < limit) sm.list[slot] = k;
-      }
-    });
-  }
-  __syncthreads();
-  int n = sm.misc[0];
-  __syncthreads();
-  if (n > limit) {  // adversarial distribution: fall back to an exact bitwise search
-    const u64 t = block_exact_kth(c, K, sm);
-    if (threadIdx.x == 0) sm.misc[0] = 0;
-    __syncthreads();
-    c.for_each([&](u64 k) {
-      if (k >= t) {
-        const int slot = atomicAdd(&sm.misc[0], 1);
-        if (slot < limit) sm.list[slot] = k;
-      }
-    });
-    __syncthreads();
-    n = sm.misc[0];
-    __syncthreads();
-  }
-  return n;
-}
-
-// Exact sorted top-K of several global candidate lists -> sm.out[0..ret)
-__device__ int block_select_from_lists(const ListCands& c, int K, const SelSmem& sm) {
-  u32 tmax = 0;
-  int cnt = 0;
+__device__ u64 block_kth_key(const Cands& c, int K, const Scratch& sc) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  u64 kand = ~0ull, kor = 0ull;
   c.for_each([&](u64 k) {
-    tmax = max(tmax, key_hi(k));
-    ++cnt;
+    kand &= k;
+    kor |= k;
   });
-  const int total = block_sum(cnt, sm.red);
-  const int n = block_collect(c, total, tmax, K, SURV_CAP, sm);
-  block_rank_to_out(n, K, sm);
-  return min(n, K);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    kand &= __shfl_xor_sync(0xffffffffu, kand, o);
+    kor |= __shfl_xor_sync(0xffffffffu, kor, o);
+  }
+  if (lane == 0) {
+    sc.keyred[warp] = kand;
+    sc.keyred[NW + warp] = kor;
+  }
+  __syncthreads();
+  kand = ~0ull;
+  kor = 0ull;
+#pragma unroll
+  for (int i = 0; i < NW; ++i) {
+    kand &= sc.keyred[i];
+    kor |= sc.keyred[NW + i];
+  }
+  const u64 varying = kand ^ kor;
+  u64 prefix = 0;
+  int rem = K;
+  for (int shift = 56; shift >= 0; shift -= 8) {
+    if (((varying >> shift) & 0xFFull) == 0) {   // block-uniform: every candidate has this digit
+      prefix |= kand & (0xFFull << shift);
+      continue;
+    }
+    sc.hist[tid] = 0;   // NT == 256 bins
+    __syncthreads();
+    const u64 himask = shift == 56 ? 0ull : (~0ull << (shift + 8));
+    c.for_each([&](u64 k) {
+      if ((k & himask) == prefix) atomicAdd(&sc.hist[(u32)(k >> shift) & 0xFFu], 1u);
+    });
+    __syncthreads();
+    if (warp == 0) {
+      u32 cnt[8];
+      u32 s = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {   // lane 0 owns the 8 largest digits
+        cnt[j] = sc.hist[255 - 8 * lane - j];
+        s += cnt[j];
+      }
+      u32 incl = s;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+      }
+      const u32 excl = incl - s;
+      if (excl < (u32)rem && (u32)rem <= incl) {
+        u32 r = (u32)rem - excl;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (r <= cnt[j]) {
+            sc.misc[0] = 255 - 8 * lane - j;
+            sc.misc[1] = (int)r;
+            break;
+          }
+          r -= cnt[j];
+        }
+      }
+    }
+    __syncthreads();
+    prefix |= (u64)(u32)sc.misc[0] << shift;
+    rem = sc.misc[1];
+  }
+  __syncthreads();
+  return prefix;
 }
 
 // Is flat element `idx` of image-tensor `img` ([C,H,W]) a strictly positive NMS survivor?
@@ -227,27 +242,27 @@ __device__ __forceinline__ bool is_positive_peak(const float* img, int idx, int 
   return true;
 }
 
-// Reference semantics when an image has fewer than K positive peaks: torch.topk then returns
-// zero-valued entries of heat*keep; we define their order as flat index ascending.
-__device__ void block_zero_fill(const float* img, int n_elems, int H, int W, int have, int K,
-                                const SelSmem& sm) {
+// Reference semantics when a group has fewer than K positive peaks: torch.topk then returns zero-valued
+// entries of heat*keep; we define their order as flat index ascending.
+__device__ void block_zero_fill(const float* img, int n_elems, int H, int W, int have, int K, u64* out,
+                                int* red) {
   int filled = have;
   for (int base = 0; base < n_elems && filled < K; base += NT) {
     const int idx = base + threadIdx.x;
     const bool z = idx < n_elems && !is_positive_peak(img, idx, H, W);
     const u32 bal = __ballot_sync(0xffffffffu, z);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0) sm.red[w] = __popc(bal);
+    if (lane == 0) red[w] = __popc(bal);
     __syncthreads();
     int before = 0, tot = 0;
 #pragma unroll
     for (int i = 0; i < NW; ++i) {
-      const int c = sm.red[i];
+      const int c = red[i];
       if (i < w) before += c;
       tot += c;
     }
     const int slot = filled + before + __popc(bal & ((1u << lane) - 1u));
-    if (z && slot < K) sm.out[slot] = make_key(0.f, (u32)idx);
+    if (z && slot < K) out[slot] = make_key(0.f, (u32)idx);
     filled += tot;
     __syncthreads();
   }
@@ -281,169 +296,524 @@ __device__ void ctdet_write_rows(const ScanArgs& a, int b, const u64* keys) {
   }
 }
 
-// =================================================================================================
-// plane_scan_kernel: one CTA per (image, plane, band of rows).
-// =================================================================================================
-template <int VEC, bool FUSE_CTDET>
-__global__ void __launch_bounds__(NT) plane_scan_kernel(const ScanArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) u64 s_mbar;
-  __shared__ u32 s_vals[NT];
-  __shared__ int s_red[NW];
-  __shared__ int s_misc[4];
-
-  const int P = a.C0 + a.C1;
-  const int band = blockIdx.x % a.nbands;
-  const int bp = blockIdx.x / a.nbands;
-  const int p = bp % P;
-  const int b = bp / P;
+// plane pointer of plane `pg` of group `g`
+__device__ __forceinline__ const float* plane_ptr(const ScanArgs& a, int g, int pg, u32* flat_base) {
   const int HW = a.H * a.W;
-  const bool second = p >= a.C0;
-  const int pl = second ? p - a.C0 : p;
-  const float* plane = second ? a.t1 + ((size_t)b * a.C1 + pl) * HW : a.t0 + ((size_t)b * a.C0 + pl) * HW;
-  const bool exact = second ? (a.exact1 != 0) : (a.exact0 != 0);
+  const int ppi = a.C0 + a.C1;
+  const int P = g * a.PG + pg;
+  const int b = P / ppi, p = P - b * ppi;
+  *flat_base = (u32)(pg * HW);
+  return p < a.C0 ? a.t0 + ((size_t)b * a.C0 + p) * HW : a.t1 + ((size_t)b * a.C1 + (p - a.C0)) * HW;
+}
 
-  const int r0 = band * a.R;
-  const int r1 = min(r0 + a.R, a.H);
-  const int g0 = max(r0 - 1, 0);
-  const int g1 = min(r1 + 1, a.H);
-  const int tile_rows = a.R + 2;
-  float* tile = reinterpret_cast<float*>(smem_raw);
-  const size_t tile_bytes = (((size_t)tile_rows * a.W * sizeof(float)) + 127) & ~(size_t)127;
-  // band phase: list[cap] + out[K] live behind the tile; the merge phase (tile dead) re-carves from 0
-  SelSmem sm;
-  sm.list = reinterpret_cast<u64*>(smem_raw + tile_bytes);
-  sm.out = sm.list + a.cap;
-  sm.vals = s_vals;
-  sm.red = s_red;
-  sm.misc = s_misc;
+// =================================================================================================
+// decode_scan_kernel: persistent CTAs over contiguous ranges of (group, plane, band) chunks.
+// =================================================================================================
+template <int VEC>
+__global__ void __launch_bounds__(NT, 2) decode_scan_kernel(const ScanArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) u64 s_full[NST];
+  __shared__ __align__(8) u64 s_keyred[2 * NW];
+  __shared__ __align__(8) u64 s_thr;
+  __shared__ u32 s_hist[256];
+  __shared__ int s_red[NW];
+  __shared__ int s_misc[8];
+  __shared__ int s_cnt;        // live survivors carried in s_list
+  __shared__ int s_nhit[3];    // hits of chunk k in s_hits[k % 3]
+  __shared__ __align__(8) u64 s_thrq[3];   // the group's bound for chunk k, fetched by thread 0 one chunk ahead
 
-  // ---- stage the band (+ halo rows) in shared memory -------------------------------------------
-  const int tid = threadIdx.x;
-  if (VEC == 4) {
-    if (tid == 0) {
-      mbar_init(&s_mbar, 1);
-      fence_mbar_init();
-      fence_proxy_async_smem();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int NSTAGE = VEC == 4 ? NST : 1;
+  u64* s_mlist = reinterpret_cast<u64*>(smem_raw + (size_t)NSTAGE * a.tile_bytes);   // [MCAP]
+  const int LC = HCAP + FLUSH_AT;
+  u64* s_list = s_mlist + MCAP;                                                      // [LC]
+  u64* s_out = s_list + LC;                                                          // [MAX_K]
+  u32* s_hits = reinterpret_cast<u32*>(s_out + MAX_K);                               // [3][HCAP]
+  const Scratch sc{s_hist, s_red, s_misc, s_keyred};
+
+  const int c_begin = (int)((long long)blockIdx.x * a.total_chunks / gridDim.x);
+  const int c_end = (int)((long long)(blockIdx.x + 1) * a.total_chunks / gridDim.x);
+  const int HW = a.H * a.W;
+
+  auto issue_load = [&](int g, int pg, int band, int stage) {   // thread 0 only (VEC == 4)
+    u32 fb;
+    const float* plane = plane_ptr(a, g, pg, &fb);
+    const int r0 = band * a.R, r1 = min(r0 + a.R, a.H);
+    const int g0 = max(r0 - 1, 0), g1 = min(r1 + 1, a.H);
+    const u32 bytes = (u32)((g1 - g0) * a.W * sizeof(float));
+    float* tile = reinterpret_cast<float*>(smem_raw + (size_t)stage * a.tile_bytes);
+    mbar_expect_tx(&s_full[stage], bytes);
+    bulk_g2s(tile + (size_t)(g0 - (r0 - 1)) * a.W, plane + (size_t)g0 * a.W, bytes, &s_full[stage]);
+  };
+  auto advance = [&](int& g, int& pg, int& band) {
+    if (++band == a.nbands) {
+      band = 0;
+      if (++pg == a.PG) {
+        pg = 0;
+        ++g;
+      }
     }
-    __syncthreads();
-    if (tid == 0) {
-      const u32 bytes = (u32)((g1 - g0) * a.W * sizeof(float));
-      mbar_expect_tx(&s_mbar, bytes);
-      bulk_g2s(tile + (size_t)(g0 - (r0 - 1)) * a.W, plane + (size_t)g0 * a.W, bytes, &s_mbar);
+  };
+  // group of the chunk `d` (<= 3) positions after chunk (g, pg, band)
+  auto group_after = [&](int g, int pg, int band, int d) {
+    int rem = pg * a.nbands + band + d;
+    while (rem >= a.cpg) {
+      rem -= a.cpg;
+      ++g;
     }
-    mbar_wait(&s_mbar, 0);
-  } else {
-    const int n = (g1 - g0) * a.W;
-    float* dst = tile + (size_t)(g0 - (r0 - 1)) * a.W;
-    const float* src = plane + (size_t)g0 * a.W;
-    for (int i = tid; i < n; i += NT) dst[i] = __ldg(src + i);
-    __syncthreads();
+    return g;
+  };
+
+  if (tid == 0) {
+    for (int s = 0; s < NST; ++s) mbar_init(&s_full[s], 1);
+    fence_mbar_init();
+    fence_proxy_async_smem();
+    s_cnt = 0;
+    s_nhit[0] = s_nhit[1] = s_nhit[2] = 0;
   }
-
-  // ---- sliding-window 3x3 max: thread = (column group cg, row segment seg) ----------------------
+  __syncthreads();
   const int W4 = a.W / VEC;
   const int cg = tid % W4;
   const int seg = tid / W4;
-  const int rs = r0 + seg * a.rpt;
-  const int re = min(rs + a.rpt, r1);
-  u64 flags = 0;
-  u32 tmax = 0;
-  const float NEG = -INFINITY;
-  if (rs < re) {
-    float hp2[VEC], hp1[VEC], cp1[VEC];
+  int done_in_group = 0;
+  int carry = 0;           // live survivors carried in s_list across chunks (block-uniform)
+  // chunk coordinates advance incrementally (no per-chunk integer divisions)
+  int g = c_begin < c_end ? c_begin / a.cpg : 0;
+  int pg, band;
+  {
+    const int rem = c_begin - g * a.cpg;
+    pg = rem / a.nbands;
+    band = rem - pg * a.nbands;
+  }
+  int lg = g, lpg = pg, lband = band;   // load cursor: the chunk NST ahead
+  for (int s = 0; s < NST; ++s) {
+    if (VEC == 4 && tid == 0 && c_begin + s < c_end) issue_load(lg, lpg, lband, s);
+    advance(lg, lpg, lband);
+  }
+  // The group's bound for chunk k is fetched by thread 0 three chunks ahead (register) and handed over through
+  // s_thrq two chunks ahead, so its L2 latency never sits on a barrier.
+  u64 tq = 0ull;           // thread 0: bound fetched for chunk k + 2
+  u64 learned = 0ull;      // the best bound this CTA computed itself for group `learned_g`
+  int learned_g = -1;
+  if (tid == 0 && c_begin < c_end) {
+    s_thrq[0] = ldcg_u64(a.thr + g);
+    if (c_begin + 1 < c_end) s_thrq[1] = ldcg_u64(a.thr + group_after(g, pg, band, 1));
+    if (c_begin + 2 < c_end) tq = ldcg_u64(a.thr + group_after(g, pg, band, 2));
+  }
+  __syncthreads();
+
+  for (int c = c_begin; c < c_end; ++c) {
+    const int k = c - c_begin;
+    const int stage = VEC == 4 ? (k & (NST - 1)) : 0;
+    u32 flat_base;
+    const float* plane = plane_ptr(a, g, pg, &flat_base);
+    const int r0 = band * a.R, r1 = min(r0 + a.R, a.H);
+    float* tile = reinterpret_cast<float*>(smem_raw + (size_t)stage * a.tile_bytes);
+    const bool group_ends = (c + 1 == c_end) || (pg == a.PG - 1 && band == a.nbands - 1);
+    int* nhit = &s_nhit[k % 3];
+    u32* hits = s_hits + (k % 3) * HCAP;
+    if (tid == 0) s_nhit[(k + 1) % 3] = 0;
+
+    u64 thr = s_thrq[k % 3];                      // a (slightly stale, hence sound) bound of the group
+    if (learned_g == g && learned > thr) thr = learned;
+    if (VEC == 4) {
+      mbar_wait(&s_full[stage], (u32)(k / NST) & 1u);
+    } else {   // unaligned / odd widths: plain cooperative loads, no pipelining
+      const int g0 = max(r0 - 1, 0), g1 = min(r1 + 1, a.H);
+      const int n = (g1 - g0) * a.W;
+      float* dst = tile + (size_t)(g0 - (r0 - 1)) * a.W;
+      const float* src = plane + (size_t)g0 * a.W;
+      for (int i = tid; i < n; i += NT) dst[i] = __ldg(src + i);
+      __syncthreads();
+    }
+
+    // ---- scan: thread = (column group cg, row segment seg) --------------------------------------------
+    // Elements that reach the bound are only *recorded* here (position in the tile); the 3x3 test runs
+    // afterwards over the hit list with all threads busy.  With no bound yet (first chunk of a group) every
+    // element would be a hit: that case goes straight to the dense path below.
+    const float ts = __uint_as_float(key_hi(thr));
+    const int rs = r0 + seg * a.rpt;
+    const int re = min(rs + a.rpt, r1);
+    const bool dense0 = thr == 0ull;              // block-uniform
+    bool any_hit = false;
+    if (!dense0) {
+      // one look at the whole chunk first: the largest value of the thread's rows against the bound, one vote
+      float mt = 0.f;
+      if constexpr (VEC == 4) {
+        float4 qq[4];
+        for (int rb = 0; rb < a.rpt; rb += 4) {
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) hp2[i] = hp1[i] = cp1[i] = NEG;
-    for (int g = rs - 1; g <= re; ++g) {
-      float c[VEC], hm[VEC];
-      if (g >= 0 && g < a.H) {
-        const float* rowp = tile + (size_t)(g - (r0 - 1)) * a.W + cg * VEC;
-        if constexpr (VEC == 4) {
-          const float4 q = *reinterpret_cast<const float4*>(rowp);
-          c[0] = q.x; c[1 % VEC] = q.y; c[2 % VEC] = q.z; c[3 % VEC] = q.w;
-        } else {
-          c[0] = rowp[0];
-        }
-        const float l = cg > 0 ? rowp[-1] : NEG;
-        const float r = cg < W4 - 1 ? rowp[VEC] : NEG;
+          for (int u = 0; u < 4; ++u) {
+            const int row = min(rs + rb + u, max(re - 1, r0));
+            qq[u] = *reinterpret_cast<const float4*>(tile + (size_t)(row - (r0 - 1)) * a.W + cg * VEC);
+          }
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-          const float lft = i == 0 ? l : c[(i - 1 + VEC) % VEC];
-          const float rgt = i == VEC - 1 ? r : c[(i + 1) % VEC];
-          hm[i] = max3f(lft, c[i], rgt);
+          for (int u = 0; u < 4; ++u)
+            mt = fmaxf(mt, fmaxf(fmaxf(qq[u].x, qq[u].y), fmaxf(qq[u].z, qq[u].w)));
         }
       } else {
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) c[i] = hm[i] = NEG;
+        for (int row = rs; row < re; ++row) mt = fmaxf(mt, tile[(size_t)(row - (r0 - 1)) * a.W + cg]);
       }
-      if (g >= rs + 1) {
-        const int rrel = g - 1 - rs;
+      any_hit = __any_sync(0xffffffffu, rs < re && mt >= ts && mt > 0.f);
+    }
+    if (any_hit) {
+      for (int rr = 0; rr < a.rpt; ++rr) {        // same trip count in every lane (votes inside)
+        const int row = rs + rr;
+        const bool live = row < re;
+        const float* rowp = tile + (size_t)((live ? row : r0) - (r0 - 1)) * a.W + cg * VEC;
+        float v[VEC];
+        float m4;
+        if constexpr (VEC == 4) {
+          const float4 q = *reinterpret_cast<const float4*>(rowp);
+          v[0] = q.x; v[1 % VEC] = q.y; v[2 % VEC] = q.z; v[3 % VEC] = q.w;
+          m4 = fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w));
+        } else {
+          v[0] = rowp[0];
+          m4 = v[0];
+        }
+        const bool maybe = live && m4 >= ts && m4 > 0.f;
+        if (!__any_sync(0xffffffffu, maybe)) continue;   // the common case once the bound has tightened
+        u32 hm = 0;
+        if (maybe) {
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-          const float m = max3f(hp2[i], hp1[i], hm[i]);
-          const float v = cp1[i];
-          if (v == m && v > 0.f) {
-            flags |= 1ull << (rrel * VEC + i);
-            tmax = max(tmax, __float_as_uint(v));
+          for (int i = 0; i < VEC; ++i) {
+            const float x = v[i];
+            if (x >= ts && x > 0.f &&
+                make_key(x, flat_base + (u32)(row * a.W + cg * VEC + i)) >= thr)
+              hm |= 1u << i;
+          }
+        }
+        // warp-aggregated append of the hit positions: one shared-memory atomic per warp and row
+        const int mine = __popc(hm);
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int up = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += up;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total) {
+          int base = 0;
+          if (lane == 31) base = atomicAdd(nhit, total);
+          base = __shfl_sync(0xffffffffu, base, 31);
+          int pos = base + incl - mine;
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) {
+            if (hm & (1u << i)) {
+              if (pos < HCAP) hits[pos] = ((u32)(row - (r0 - 1)) << 16) | (u32)(cg * VEC + i);
+              ++pos;
+            }
           }
         }
       }
+    }
+    if (tid == 0) {
+      if (c + 2 < c_end) s_thrq[(k + 2) % 3] = tq;
+      if (c + 3 < c_end) tq = ldcg_u64(a.thr + group_after(g, pg, band, 3));
+    }
+    __syncthreads();
+    const int nh = dense0 ? HCAP + 1 : *nhit;
+    u64 flags = 0;
+    if (nh > 0) {
+      if (nh <= HCAP) {
+        // ---- 3x3 max-pool NMS on the recorded hits (utils/decode.py:5-10: keep iff no neighbour is larger)
+        for (int i = tid; i < nh; i += NT) {
+          const u32 h = hits[i];
+          const int trow = (int)(h >> 16), col = (int)(h & 0xFFFFu);
+          const int row = trow + (r0 - 1);
+          const float x = tile[(size_t)trow * a.W + col];
+          bool peak = true;
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        hp2[i] = hp1[i];
-        hp1[i] = hm[i];
-        cp1[i] = c[i];
+          for (int dy = -1; dy <= 1; ++dy) {
+            const int gy = row + dy;
+            if (gy < 0 || gy >= a.H) continue;
+            const float* np = tile + (size_t)(trow + dy) * a.W;
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+              const int gx = col + dx;
+              if (gx < 0 || gx >= a.W) continue;
+              if (np[gx] > x) peak = false;
+            }
+          }
+          if (peak) s_list[atomicAdd(&s_cnt, 1)] = make_key(x, flat_base + (u32)(row * a.W + col));
+        }
+      } else {
+        // ---- dense path: separable sliding-window 3x3 max over the thread's rows -----------------------
+        if (rs < re) {
+          const float NEG = -INFINITY;
+          float hp2[VEC], hp1[VEC], cp1[VEC];
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) hp2[i] = hp1[i] = cp1[i] = NEG;
+          for (int gy = rs - 1; gy <= re; ++gy) {
+            float cv[VEC], hmx[VEC];
+            if (gy >= 0 && gy < a.H) {
+              const float* rowp = tile + (size_t)(gy - (r0 - 1)) * a.W + cg * VEC;
+              if constexpr (VEC == 4) {
+                const float4 q = *reinterpret_cast<const float4*>(rowp);
+                cv[0] = q.x; cv[1 % VEC] = q.y; cv[2 % VEC] = q.z; cv[3 % VEC] = q.w;
+              } else {
+                cv[0] = rowp[0];
+              }
+              const float l = cg > 0 ? rowp[-1] : NEG;
+              const float r = cg < W4 - 1 ? rowp[VEC] : NEG;
+#pragma unroll
+              for (int i = 0; i < VEC; ++i) {
+                const float lft = i == 0 ? l : cv[(i - 1 + VEC) % VEC];
+                const float rgt = i == VEC - 1 ? r : cv[(i + 1) % VEC];
+                hmx[i] = max3f(lft, cv[i], rgt);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < VEC; ++i) cv[i] = hmx[i] = NEG;
+            }
+            if (gy >= rs + 1) {
+              const int row = gy - 1;
+#pragma unroll
+              for (int i = 0; i < VEC; ++i) {
+                const float m = max3f(hp2[i], hp1[i], hmx[i]);
+                const float x = cp1[i];
+                if (x == m && x > 0.f) {
+                  const u64 key = make_key(x, flat_base + (u32)(row * a.W + cg * VEC + i));
+                  if (key >= thr) {
+                    flags |= 1ull << ((row - rs) * VEC + i);
+                    const int slot = atomicAdd(&s_cnt, 1);
+                    if (slot < LC) s_list[slot] = key;
+                  }
+                }
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+              hp2[i] = hp1[i];
+              hp1[i] = hmx[i];
+              cp1[i] = cv[i];
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+    int n = (nh > 0) ? s_cnt : carry;
+
+    if (n > LC) {   // (dense path only) more live survivors than the list holds: exact local top-K
+      const FlagCands<VEC> fc{tile, flags, rs, cg, a.W, r0, flat_base};
+      const u64 kth = block_kth_key(fc, a.K, sc);
+      if (tid == 0) s_misc[2] = carry;
+      __syncthreads();
+      fc.for_each([&](u64 key) {
+        if (key >= kth) s_list[atomicAdd(&s_misc[2], 1)] = key;   // exactly K more entries
+      });
+      __syncthreads();
+      n = s_misc[2];
+      if (tid == 0) {
+        s_cnt = n;
+        atomicMax(reinterpret_cast<unsigned long long*>(a.thr + g), (unsigned long long)kth);
+      }
+      if (kth > thr) thr = kth;
+      __syncthreads();
+    }
+    carry = n;
+
+    // ---- flush: tighten the group's bound, append what can still matter --------------------------------
+    if (carry > 0 && (group_ends || carry >= FLUSH_AT)) {   // block-uniform
+      if (carry > a.acap) {   // never hand more than acap (>= K) keys per flush to the group's list
+        const SmemCands smc{s_list, carry};
+        const u64 kth = block_kth_key(smc, a.K, sc);
+        u64 mine[(HCAP + FLUSH_AT + NT - 1) / NT];
+        int nm = 0;
+        for (int i = tid; i < carry; i += NT) mine[nm++] = s_list[i];
+        if (tid == 0) s_cnt = 0;
+        __syncthreads();
+        for (int j = 0; j < nm; ++j)
+          if (mine[j] >= kth) s_list[atomicAdd(&s_cnt, 1)] = mine[j];
+        if (tid == 0) atomicMax(reinterpret_cast<unsigned long long*>(a.thr + g), (unsigned long long)kth);
+        if (kth > thr) thr = kth;
+        __syncthreads();
+        carry = s_cnt;   // == K
+        __syncthreads();
+      }
+      const int nf = carry;
+      for (int i = tid; i < nf; i += NT) {
+        const u64 key = s_list[i];
+        if (key >= thr) {
+          const u32 bits = key_hi(key);
+          const int bin = score_bin(bits);
+          if (bin >= 1) atomicAdd(a.ghist + (size_t)g * NB + bin, 1);
+          if (a.gfine && bin >= FB0)
+            atomicAdd(a.gfine + (size_t)g * NBF + (bin - FB0) * FSUB + (int)((bits >> 11) & (FSUB - 1)), 1);
+        }
+      }
+      // No fence: the histogram is read right away, possibly without this CTA's own increments -- counts only
+      // grow, so a stale read gives a weaker but still sound bound; the next flush catches up.
+      if (warp == 0) {
+        // largest bin t such that count(bins >= t) >= K  ->  (edge(t) << 32) bounds the K-th key from below
+        int hi = NB - 1;
+        int acc = 0, found = 0, above = 0;
+        const int* hist = a.ghist + (size_t)g * NB;
+        while (hi >= 1 && !found) {
+          int cb[8], sum = 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int bin = hi - (lane * 8 + j);
+            cb[j] = bin >= 1 ? __ldcg(hist + bin) : 0;
+            sum += cb[j];
+          }
+          int incl = sum;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+          }
+          const int total = __shfl_sync(0xffffffffu, incl, 31);
+          if (acc + total >= a.K) {
+            const int excl = acc + incl - sum;
+            int mybin = 0, myabove = 0;
+            if (excl < a.K && acc + incl >= a.K) {
+              int r = excl;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (r + cb[j] >= a.K && !mybin) {
+                  mybin = hi - (lane * 8 + j);
+                  myabove = r;               // survivors counted in the bins above the crossing bin
+                }
+                r += cb[j];
+              }
+            }
+            found = __reduce_max_sync(0xffffffffu, mybin);
+            above = __reduce_max_sync(0xffffffffu, myabove);
+          } else {
+            acc += total;
+            hi -= 256;
+          }
+        }
+        u32 sub_bits = 0;
+        if (found >= FB0 && a.gfine) {   // refine inside the crossing bin with its 32 sub-bins
+          const int f = __ldcg(a.gfine + (size_t)g * NBF + (found - FB0) * FSUB + (FSUB - 1 - lane));
+          int incl = f;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+          }
+          const u32 ok = __ballot_sync(0xffffffffu, above + incl >= a.K);
+          if (ok) sub_bits = (u32)(FSUB - 1 - (__ffs(ok) - 1)) << 11;
+        }
+        if (lane == 0) {
+          u64 t = thr;
+          if (found >= 1) {
+            const u64 nt = (u64)(bin_edge_bits(found) | sub_bits) << 32;
+            atomicMax(reinterpret_cast<unsigned long long*>(a.thr + g), (unsigned long long)nt);
+            if (nt > t) t = nt;
+          }
+          s_thr = t;
+          s_cnt = 0;
+        }
+      }
+      __syncthreads();
+      thr = s_thr;
+      for (int i0 = 0; i0 < nf; i0 += NT) {   // warp-aggregated append to the group's candidate list
+        const int i = i0 + tid;
+        const u64 key = i < nf ? s_list[i] : 0ull;
+        const bool keep = i < nf && key >= thr;
+        const u32 bal = __ballot_sync(0xffffffffu, keep);
+        if (bal) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(a.gcount + g, __popc(bal));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          const int pos = base + __popc(bal & ((1u << lane) - 1u));
+          if (keep && pos < a.gcap) a.lists[(size_t)g * a.gcap + pos] = key;
+        }
+      }
+      carry = 0;
+      learned = thr;   // what this CTA just learnt applies to its next chunks of the group
+      learned_g = g;
+      __syncthreads();
+    }
+
+    if (VEC == 4 && tid == 0 && c + NST < c_end) issue_load(lg, lpg, lband, stage);
+    advance(lg, lpg, lband);
+    ++done_in_group;
+
+    // ---- group boundary: account for the chunks done; the CTA that completes the group merges it -------
+    if (group_ends) {
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) {
+        const int prev = atomicAdd(a.gdone + g, done_in_group);
+        s_misc[3] = (prev + done_in_group == a.cpg);
+      }
+      __syncthreads();
+      done_in_group = 0;
+      if (s_misc[3]) {
+        __threadfence();
+        const int n_all = min(__ldcg(a.gcount + g), a.gcap);
+        const u64 floor = ldcg_u64(a.thr + g);
+        const u64* gl = a.lists + (size_t)g * a.gcap;
+        if (tid == 0) s_misc[4] = 0;
+        __syncthreads();
+        for (int i = tid; i < n_all; i += NT) {
+          const u64 key = ldcg_u64(gl + i);
+          if (key >= floor) {
+            const int slot = atomicAdd(&s_misc[4], 1);
+            if (slot < MCAP) s_mlist[slot] = key;
+          }
+        }
+        __syncthreads();
+        int m = s_misc[4];
+        __syncthreads();
+        const u64* L = s_mlist;
+        if (m > MCAP) {   // more candidates than the staging area holds: exact K-th straight from global memory
+          const GlobalCands gc{gl, n_all, floor};
+          const u64 kth = block_kth_key(gc, a.K, sc);
+          if (tid == 0) s_misc[4] = 0;
+          __syncthreads();
+          gc.for_each([&](u64 key) {
+            if (key >= kth) s_mlist[atomicAdd(&s_misc[4], 1)] = key;
+          });
+          __syncthreads();
+          m = s_misc[4];
+        } else if (m > RANK_DIRECT && m > a.K) {
+          const SmemCands smc{s_mlist, m};
+          const u64 kth = block_kth_key(smc, a.K, sc);
+          if (tid == 0) s_misc[4] = 0;
+          __syncthreads();
+          smc.for_each([&](u64 key) {
+            if (key >= kth) s_list[atomicAdd(&s_misc[4], 1)] = key;   // exactly K <= acap entries
+          });
+          __syncthreads();
+          m = s_misc[4];
+          L = s_list;
+        }
+        for (int i = tid; i < m; i += NT) {   // exact rank by counting (keys distinct)
+          const u64 key = L[i];
+          int r = 0;
+          for (int j = 0; j < m; ++j) r += (L[j] > key);
+          if (r < a.K) s_out[r] = key;
+        }
+        __syncthreads();
+        int have = min(m, a.K);
+        if (a.fuse_ctdet) {
+          if (have < a.K) {
+            block_zero_fill(a.t0 + (size_t)g * a.C0 * HW, a.C0 * HW, a.H, a.W, have, a.K, s_out, s_red);
+            __syncthreads();
+          }
+          ctdet_write_rows(a, g, s_out);
+        } else {
+          const int ppi = a.C0 + a.C1;
+          const int b = g / ppi, p = g - b * ppi;
+          if (p < a.C0 && have < a.K) {   // detection heat map: zero-filled like torch.topk
+            block_zero_fill(a.t0 + ((size_t)b * a.C0 + p) * HW, HW, a.H, a.W, have, a.K, s_out, s_red);
+            __syncthreads();
+            have = a.K;
+          }
+          for (int i = tid; i < have; i += NT) a.topk[(size_t)g * a.K + i] = s_out[i];
+          if (tid == 0) a.have[g] = have;
+        }
+        __syncthreads();
       }
     }
+    advance(g, pg, band);
   }
-
-  // ---- candidate selection for this band ---------------------------------------------------------
-  BandCands<VEC> cands{tile, flags, rs, cg, a.W, r0, (u32)(pl * HW)};
-  const int total = block_sum(__popcll(flags), sm.red);
-  int n = block_collect(cands, total, tmax, a.K, a.cap, sm);
-  if (!FUSE_CTDET) {
-    const int li = blockIdx.x;  // list index == (b*P + p)*nbands + band
-    u64* gl = a.lists + (size_t)li * a.cap;
-    if (exact) {
-      block_rank_to_out(n, a.K, sm);
-      n = min(n, a.K);
-      for (int i = tid; i < n; i += NT) gl[i] = sm.out[i];
-    } else {
-      for (int i = tid; i < n; i += NT) gl[i] = sm.list[i];
-    }
-    if (tid == 0) a.counts[li] = n;
-    return;
-  }
-
-  // ---- fused ctdet: append this band's survivors to the image's candidate array ------------------
-  const size_t img_cap = (size_t)P * a.nbands * a.cap;
-  if (tid == 0) s_misc[3] = n ? atomicAdd(a.counts + b, n) : 0;
-  __syncthreads();
-  {
-    u64* gl = a.lists + (size_t)b * img_cap + s_misc[3];
-    for (int i = tid; i < n; i += NT) gl[i] = sm.list[i];
-  }
-
-  // ---- last CTA of the image merges all lists and writes the detections -------------------------
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const int prev = atomicAdd(a.done + b, 1);
-    s_misc[1] = (prev == P * a.nbands - 1);
-  }
-  __syncthreads();
-  if (!s_misc[1]) return;
-  __threadfence();
-  SelSmem msm = sm;   // tile is dead: SURV_CAP survivors + MAX_K outputs from the start of smem
-  msm.list = reinterpret_cast<u64*>(smem_raw);
-  msm.out = msm.list + SURV_CAP;
-  ListCands lc{a.lists + (size_t)b * img_cap, a.counts + b, 1, 0};
-  const int have = block_select_from_lists(lc, a.K, msm);
-  if (have < a.K) {
-    block_zero_fill(a.t0 + (size_t)b * a.C0 * HW, a.C0 * HW, a.H, a.W, have, a.K, msm);
-    __syncthreads();
-  }
-  ctdet_write_rows(a, b, msm.out);
 }
 
 // =================================================================================================
@@ -453,46 +823,28 @@ struct PoseArgs {
   const float *heat, *wh, *kps, *reg, *hm_hp, *hp_offset;
   float* out;
   int B, J, H, W, K;
-  int nbands, cap;
-  const u64* lists;
-  const int* counts;
+  const u64* topk;   // [B*(1+J)][K] sorted keys per plane (plane 0 = detections, 1+j = joint j)
+  const int* have;   // [B*(1+J)]
 };
 
 __global__ void __launch_bounds__(NT) multi_pose_assoc_kernel(const PoseArgs a) {
-  __shared__ __align__(8) u64 s_list[SURV_CAP];
-  __shared__ __align__(8) u64 s_out[MAX_K];
   __shared__ __align__(8) u64 s_det[MAX_K];
   __shared__ float s_hx[MAX_K], s_hy[MAX_K], s_hs[MAX_K];
-  __shared__ u32 s_vals[NT];
-  __shared__ int s_red[NW];
-  __shared__ int s_misc[4];
-  SelSmem sm{s_list, s_out, s_vals, s_red, s_misc};
 
   const int j = blockIdx.x, b = blockIdx.y;
   const int P = 1 + a.J, HW = a.H * a.W, K = a.K;
   const int tid = threadIdx.x;
 
   // (1) detections: exact top-K of the (single-class) heat plane, zero-filled like torch.topk
-  {
-    ListCands lc{a.lists + (size_t)(b * P) * a.nbands * a.cap, a.counts + (size_t)(b * P) * a.nbands,
-                 a.nbands, a.cap};
-    const int have = block_select_from_lists(lc, K, sm);
-    if (have < K) {
-      block_zero_fill(a.heat + (size_t)b * HW, HW, a.H, a.W, have, K, sm);
-      __syncthreads();
-    }
-    for (int i = tid; i < K; i += NT) s_det[i] = s_out[i];
-    __syncthreads();
-  }
+  for (int i = tid; i < K; i += NT) s_det[i] = a.topk[(size_t)(b * P) * K + i];
   // (2) joint candidates: exact top-K of hm_hp plane j (utils/decode.py:31-40) + offsets + threshold
   {
-    ListCands lc{a.lists + (size_t)(b * P + 1 + j) * a.nbands * a.cap,
-                 a.counts + (size_t)(b * P + 1 + j) * a.nbands, a.nbands, a.cap};
-    const int have = block_select_from_lists(lc, K, sm);
+    const int gj = b * P + 1 + j;
+    const int have = a.have[gj];
     for (int m = tid; m < K; m += NT) {
       float sc = 0.f, hx = 0.f, hy = 0.f;
       if (m < have) {
-        const u64 key = s_out[m];
+        const u64 key = a.topk[(size_t)gj * K + m];
         sc = __uint_as_float(key_hi(key));
         const int pix = (int)key_idx(key) % HW;
         hx = (float)(pix % a.W);
@@ -569,7 +921,7 @@ __global__ void __launch_bounds__(NT) multi_pose_assoc_kernel(const PoseArgs a) 
 // host side
 // =================================================================================================
 struct ScanGeom {
-  int vec, R, nbands, rpt, cap;
+  int vec, R, nbands, rpt, acap, tile_bytes;
   size_t smem;
 };
 
@@ -582,65 +934,111 @@ static bool plan_scan(int H, int W, int K, bool aligned, ScanGeom* g) {
   const int vec = (aligned && W % 4 == 0) ? 4 : 1;
   const int W4 = W / vec;
   if (W4 > NT || W4 < 1) return false;
-  const int S = NT / W4;
-  const int max_rpt = 64 / vec;
-  int rpt = env_int("CNB_DECODE_RPT", 8);
-  if (rpt < 1) rpt = 1;
+  const int S = NT / W4;                       // row segments scanned in parallel
+  const int max_rpt = 64 / vec;                // survivor flags are one 64-bit mask per thread
+  int rpt = env_int("CNB_DECODE_RPT", 0);
+  if (rpt < 1) {                               // ~16 KB of rows per chunk
+    rpt = (4096 / W + S / 2) / S;
+    if (rpt < 1) rpt = 1;
+  }
   if (rpt > max_rpt) rpt = max_rpt;
-  int R;
+  int acap = K > 256 ? K : 256;
+  const int nstage = vec == 4 ? NST : 1;
+  const size_t fixed = (size_t)(MCAP + (HCAP + FLUSH_AT) + MAX_K) * sizeof(u64) + 3 * HCAP * sizeof(u32);
+  int R, tile_bytes;
   size_t smem;
-  int cap = 2 * K;
-  if (cap < 64) cap = 64;
-  cap = (cap + 31) & ~31;
-  const size_t band_extra = (size_t)(cap + K) * sizeof(u64);
-  const size_t merge_bytes = (size_t)(SURV_CAP + MAX_K) * sizeof(u64);
   for (;;) {
     R = S * rpt;
     if (R > H) R = H;
-    smem = ((((size_t)(R + 2) * W * sizeof(float)) + 127) & ~(size_t)127) + band_extra;
-    if (smem <= 100 * 1024 || rpt == 1) break;
+    tile_bytes = (int)((((size_t)(R + 2) * W * sizeof(float)) + 127) & ~(size_t)127);
+    smem = (size_t)nstage * tile_bytes + fixed;
+    if (smem <= 110 * 1024 || rpt == 1) break;
     rpt /= 2;
   }
-  if (smem > 200 * 1024) return false;
-  if (smem < merge_bytes) smem = merge_bytes;
+  if (smem > 110 * 1024) return false;
   g->vec = vec;
   g->R = R;
   g->nbands = (H + R - 1) / R;
   g->rpt = (R + S - 1) / S;
-  g->cap = cap;
+  g->acap = acap;
+  g->tile_bytes = tile_bytes;
   g->smem = smem;
   return true;
 }
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// workspace: [thr G*8 | gcount G*4 | gdone G*4 | gtop G*4 | ghist G*NB*4] (zeroed per call) | lists | topk | have
 struct WsLayout {
-  size_t lists_off, counts_off, done_off, total;
+  size_t thr_off, gcount_off, gdone_off, gtop_off, ghist_off, gfine_off, zero_bytes, lists_off, topk_off, have_off, total;
+  bool fine;
+  int gcap;
 };
-static WsLayout ws_layout(int B, int P, const ScanGeom& g) {
+// Fine sub-bins pay off when one coarse bin near the top can hold many more than K survivors: large groups
+// (ctdet: C planes per image); single-plane groups (multi_pose) resolve well enough with the coarse bins.
+static bool fine_for(int PG) { return PG >= 8; }
+
+static WsLayout ws_layout(int G, int PG, int K, const ScanGeom& g, bool want_topk) {
   WsLayout w;
-  const size_t nl = (size_t)B * P * g.nbands;
-  w.lists_off = 0;
-  w.counts_off = align_up(nl * g.cap * sizeof(u64), 256);
-  w.done_off = w.counts_off + align_up((nl > (size_t)B ? nl : (size_t)B) * sizeof(int), 256);
-  w.total = w.done_off + align_up((size_t)B * sizeof(int), 256);
+  w.gcap = PG * g.nbands * g.acap;
+  w.thr_off = 0;
+  w.gcount_off = align_up((size_t)G * sizeof(u64), 256);
+  w.gdone_off = w.gcount_off + align_up((size_t)G * sizeof(int), 256);
+  w.gtop_off = w.gdone_off + align_up((size_t)G * sizeof(int), 256);
+  w.ghist_off = w.gtop_off + align_up((size_t)G * sizeof(int), 256);
+  w.fine = fine_for(PG);
+  w.gfine_off = w.ghist_off + align_up((size_t)G * NB * sizeof(int), 256);
+  w.zero_bytes = w.gfine_off + (w.fine ? align_up((size_t)G * NBF * sizeof(int), 256) : 0);
+  w.lists_off = w.zero_bytes;
+  w.topk_off = w.lists_off + align_up((size_t)G * w.gcap * sizeof(u64), 256);
+  w.have_off = w.topk_off + (want_topk ? align_up((size_t)G * K * sizeof(u64), 256) : 0);
+  w.total = w.have_off + (want_topk ? align_up((size_t)G * sizeof(int), 256) : 0);
   return w;
 }
 
-template <int VEC, bool FUSE>
-static cudaError_t launch_scan(const ScanArgs& a, size_t smem, int grid, cudaStream_t st) {
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n < 1) n = 1;
+  }
+  return n;
+}
+
+template <int VEC>
+static cudaError_t launch_scan(const ScanArgs& a, size_t smem, cudaStream_t st) {
   static bool configured = false;  // per template instantiation
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(plane_scan_kernel<VEC, FUSE>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(decode_scan_kernel<VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         112 * 1024);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  plane_scan_kernel<VEC, FUSE><<<grid, NT, smem, st>>>(a);
+  int grid = env_int("CNB_DECODE_CTAS", 2 * num_sms());
+  if (grid > a.total_chunks) grid = a.total_chunks;
+  if (grid < 1) grid = 1;
+  decode_scan_kernel<VEC><<<grid, NT, smem, st>>>(a);
   return cudaGetLastError();
 }
 
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+static void fill_scan_args(ScanArgs& a, const ScanGeom& g, const WsLayout& w, unsigned char* ws) {
+  a.R = g.R; a.nbands = g.nbands; a.rpt = g.rpt; a.acap = g.acap;
+  a.cpg = a.PG * g.nbands;
+  a.total_chunks = a.G * a.cpg;
+  a.gcap = w.gcap;
+  a.tile_bytes = g.tile_bytes;
+  a.thr = (u64*)(ws + w.thr_off);
+  a.gcount = (int*)(ws + w.gcount_off);
+  a.gdone = (int*)(ws + w.gdone_off);
+  a.gtop = (int*)(ws + w.gtop_off);
+  a.ghist = (int*)(ws + w.ghist_off);
+  a.gfine = w.fine ? (int*)(ws + w.gfine_off) : nullptr;
+  a.lists = (u64*)(ws + w.lists_off);
+}
 
 }  // namespace
 }  // namespace cnb
@@ -651,8 +1049,8 @@ extern "C" size_t cnb_ctdet_decode_workspace_bytes(int B, int C, int H, int W, i
   ScanGeom g;
   if (B < 1 || C < 1 || K < 1 || K > MAX_K || !plan_scan(H, W, K, true, &g)) return 0;
   ScanGeom g1;   // the unaligned (scalar) fallback may band differently; take the larger of the two
-  const size_t a = ws_layout(B, C, g).total;
-  const size_t b = plan_scan(H, W, K, false, &g1) ? ws_layout(B, C, g1).total : 0;
+  const size_t a = ws_layout(B, C, K, g, false).total;
+  const size_t b = plan_scan(H, W, K, false, &g1) ? ws_layout(B, C, K, g1, false).total : 0;
   return a > b ? a : b;
 }
 
@@ -666,7 +1064,8 @@ extern "C" int cnb_ctdet_decode(const float* heat, const float* wh, const float*
   CNB_CHECK_ARG((long long)C * H * W < (1ll << 31), "ctdet_decode: C*H*W too large");
   ScanGeom g;
   CNB_CHECK_ARG(plan_scan(H, W, K, aligned16(heat), &g), "ctdet_decode: unsupported map size %dx%d", H, W);
-  const WsLayout w = ws_layout(B, C, g);
+  CNB_CHECK_ARG((long long)B * C * g.nbands < (1ll << 31), "ctdet_decode: too many chunks");
+  const WsLayout w = ws_layout(B, C, K, g, false);
   if (workspace_bytes < w.total) {
     set_error("ctdet_decode: workspace %zu < %zu bytes", workspace_bytes, w.total);
     return CNB_ERR_WORKSPACE;
@@ -675,18 +1074,14 @@ extern "C" int cnb_ctdet_decode(const float* heat, const float* wh, const float*
   unsigned char* ws = (unsigned char*)workspace;
   ScanArgs a{};
   a.t0 = heat; a.t1 = nullptr; a.C0 = C; a.C1 = 0;
+  a.PG = C; a.G = B;
   a.B = B; a.H = H; a.W = W; a.K = K;
-  a.R = g.R; a.nbands = g.nbands; a.rpt = g.rpt; a.cap = g.cap;
-  a.exact0 = 0; a.exact1 = 0;
-  a.lists = (u64*)(ws + w.lists_off);
-  a.counts = (int*)(ws + w.counts_off);
-  a.done = (int*)(ws + w.done_off);
+  fill_scan_args(a, g, w, ws);
+  a.topk = nullptr; a.have = nullptr;
   a.wh = wh; a.reg = reg; a.out = out;
-  // zero the per-image append cursors and arrival counters (contiguous: counts .. done)
-  CNB_CUDA(cudaMemsetAsync(a.counts, 0, (w.done_off - w.counts_off) + (size_t)B * sizeof(int), st));
-  const int grid = B * C * g.nbands;
-  cudaError_t e = g.vec == 4 ? launch_scan<4, true>(a, g.smem, grid, st)
-                             : launch_scan<1, true>(a, g.smem, grid, st);
+  a.fuse_ctdet = 1;
+  CNB_CUDA(cudaMemsetAsync(ws, 0, w.zero_bytes, st));
+  cudaError_t e = g.vec == 4 ? launch_scan<4>(a, g.smem, st) : launch_scan<1>(a, g.smem, st);
   if (e != cudaSuccess) {
     set_error("ctdet_decode launch failed: %s", cudaGetErrorString(e));
     return CNB_ERR_CUDA;
@@ -699,8 +1094,8 @@ extern "C" size_t cnb_multi_pose_decode_workspace_bytes(int B, int J, int H, int
   ScanGeom g;
   if (B < 1 || J < 1 || K < 1 || K > MAX_K || !plan_scan(H, W, K, true, &g)) return 0;
   ScanGeom g1;
-  const size_t a = ws_layout(B, 1 + J, g).total;
-  const size_t b = plan_scan(H, W, K, false, &g1) ? ws_layout(B, 1 + J, g1).total : 0;
+  const size_t a = ws_layout(B * (1 + J), 1, K, g, true).total;
+  const size_t b = plan_scan(H, W, K, false, &g1) ? ws_layout(B * (1 + J), 1, K, g1, true).total : 0;
   return a > b ? a : b;
 }
 
@@ -719,7 +1114,8 @@ extern "C" int cnb_multi_pose_decode(const float* heat, const float* wh, const f
   CNB_CHECK_ARG(plan_scan(H, W, K, aligned16(heat) && aligned16(hm_hp), &g),
                 "multi_pose_decode: unsupported map size %dx%d", H, W);
   const int P = 1 + J;
-  const WsLayout w = ws_layout(B, P, g);
+  CNB_CHECK_ARG((long long)B * P * g.nbands < (1ll << 31), "multi_pose_decode: too many chunks");
+  const WsLayout w = ws_layout(B * P, 1, K, g, true);
   if (workspace_bytes < w.total) {
     set_error("multi_pose_decode: workspace %zu < %zu bytes", workspace_bytes, w.total);
     return CNB_ERR_WORKSPACE;
@@ -728,21 +1124,21 @@ extern "C" int cnb_multi_pose_decode(const float* heat, const float* wh, const f
   unsigned char* ws = (unsigned char*)workspace;
   ScanArgs a{};
   a.t0 = heat; a.t1 = hm_hp; a.C0 = 1; a.C1 = J;
+  a.PG = 1; a.G = B * P;
   a.B = B; a.H = H; a.W = W; a.K = K;
-  a.R = g.R; a.nbands = g.nbands; a.rpt = g.rpt; a.cap = g.cap;
-  a.exact0 = 1; a.exact1 = 1;
-  a.lists = (u64*)(ws + w.lists_off);
-  a.counts = (int*)(ws + w.counts_off);
-  a.done = nullptr; a.wh = nullptr; a.reg = nullptr; a.out = nullptr;
-  const int grid = B * P * g.nbands;
-  cudaError_t e = g.vec == 4 ? launch_scan<4, false>(a, g.smem, grid, st)
-                             : launch_scan<1, false>(a, g.smem, grid, st);
+  fill_scan_args(a, g, w, ws);
+  a.topk = (u64*)(ws + w.topk_off);
+  a.have = (int*)(ws + w.have_off);
+  a.wh = nullptr; a.reg = nullptr; a.out = nullptr;
+  a.fuse_ctdet = 0;
+  CNB_CUDA(cudaMemsetAsync(ws, 0, w.zero_bytes, st));
+  cudaError_t e = g.vec == 4 ? launch_scan<4>(a, g.smem, st) : launch_scan<1>(a, g.smem, st);
   if (e != cudaSuccess) {
     set_error("multi_pose_decode scan launch failed: %s", cudaGetErrorString(e));
     return CNB_ERR_CUDA;
   }
   count_launch();
-  PoseArgs pa{heat, wh, kps, reg, hm_hp, hp_offset, out, B, J, H, W, K, g.nbands, g.cap, a.lists, a.counts};
+  PoseArgs pa{heat, wh, kps, reg, hm_hp, hp_offset, out, B, J, H, W, K, a.topk, a.have};
   multi_pose_assoc_kernel<<<dim3(J, B), NT, 0, st>>>(pa);
   CNB_LAUNCH_CHECK();
   return CNB_OK;

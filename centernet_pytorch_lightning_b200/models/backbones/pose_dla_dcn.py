@@ -150,12 +150,16 @@ class _Compiled:
     def conv(self, conv, bn=None):
         key = id(conv)
         if key not in self.cache:
-            wpk = ops.pack_conv_weights(conv.weight)
+            # the 3-channel 7x7 stem runs on an 8-channel padded input: packed 7x8 (zero column) so that the taps
+            # (kw, kw+1) of one row form one K=16 tensor-core step (cnb_conv_desc.w_kw)
+            w_kw = conv.kernel_size[1] + 1 if (conv.in_channels <= 8 and conv.kernel_size[1] % 2 == 1
+                                               and conv.kernel_size[1] > 1) else 0
+            wpk = ops.pack_conv_weights(conv.weight, kw_pad=w_kw or None)
             if bn is not None:
                 scale, shift = fold_bn(bn, conv.bias)
             else:
                 scale, shift = None, (conv.bias.detach().float().contiguous() if conv.bias is not None else None)
-            self.cache[key] = (wpk, scale, shift)
+            self.cache[key] = (wpk, scale, shift, w_kw)
         return self.cache[key]
 
     def deform(self, dc):
@@ -177,9 +181,9 @@ def _new(x, H, W, C):
 
 
 def _conv_bn_act(cc, x, conv, bn, act=1, res=None, out=None):
-    wpk, scale, shift = cc.conv(conv, bn)
+    wpk, scale, shift, w_kw = cc.conv(conv, bn)
     k, s = conv.kernel_size[0], conv.stride[0]
-    y = ops.conv2d(x, wpk, conv.out_channels, k, s, k // 2, scale, shift, res=res, act=act, out=out)
+    y = ops.conv2d(x, wpk, conv.out_channels, k, s, k // 2, scale, shift, res=res, act=act, out=out, w_kw=w_kw)
     return y if isinstance(y, View) else View(y, conv.out_channels, 0)
 
 

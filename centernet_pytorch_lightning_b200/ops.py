@@ -105,10 +105,14 @@ def to_nchw_f32(v):
     return y
 
 
-def pack_conv_weights(w):
-    """[Co,Ci,KH,KW] fp32 -> packed bf16 [Co_pad][Kpad] (K order kh,kw,ci; Ci padded to 8)."""
+def pack_conv_weights(w, kw_pad=None):
+    """[Co,Ci,KH,KW] fp32 -> packed bf16 [Co_pad][Kpad] (K order kh,kw,ci; Ci padded to 8).
+    `kw_pad` > KW appends zero filter columns first (pass the same value as `w_kw` to conv2d)."""
     _lib.require_cuda(w)
-    w = w.detach().float().contiguous()
+    w = w.detach().float()
+    if kw_pad is not None and kw_pad > w.shape[3]:
+        w = torch.nn.functional.pad(w, (0, kw_pad - w.shape[3]))
+    w = w.contiguous()
     Co, Ci, KH, KW = w.shape
     L = _lib.lib()
     nbytes = L.cnb_conv_packed_weight_bytes(Co, Ci, KH, KW)
@@ -123,7 +127,8 @@ def _out_geometry(H, W, k, stride, pad, dil=1):
     return (H + 2 * pad - dil * (k - 1) - 1) // stride + 1, (W + 2 * pad - dil * (k - 1) - 1) // stride + 1
 
 
-def _make_desc(x: View, Co, k, stride, pad, dil, Ho, Wo, out_mode, act, y_cstride, y_coffset, res: Optional[View]):
+def _make_desc(x: View, Co, k, stride, pad, dil, Ho, Wo, out_mode, act, y_cstride, y_coffset, res: Optional[View],
+               w_kw=0):
     d = ConvDesc()
     d.B, d.Hi, d.Wi, d.Ci = x.B, x.H, x.W, x.C
     d.Co, d.KH, d.KW = Co, k, k
@@ -133,6 +138,7 @@ def _make_desc(x: View, Co, k, stride, pad, dil, Ho, Wo, out_mode, act, y_cstrid
     d.y_cstride, d.y_coffset = y_cstride, y_coffset
     d.res_cstride, d.res_coffset = (res.cstride, res.coffset) if res is not None else (0, 0)
     d.act, d.out_nchw_f32 = act, out_mode
+    d.w_kw = w_kw
     return d
 
 
@@ -149,7 +155,7 @@ def _alloc_out(x: View, Co, Ho, Wo, out_mode, out):
     return torch.empty((x.B, Ho, Wo, cs), dtype=torch.float32, device=dev)
 
 
-def conv2d(x, wpk, Co, k, stride, pad, scale, shift, res=None, act=0, out_mode=0, out=None, dil=1):
+def conv2d(x, wpk, Co, k, stride, pad, scale, shift, res=None, act=0, out_mode=0, out=None, dil=1, w_kw=0):
     """y = act(conv(x, w) * scale + shift (+ res)).  out_mode 0: NHWC bf16 (returns the tensor, or writes the
     `out` View), 1: NCHW fp32, 2: NHWC fp32 (channel stride rounded up to 16)."""
     x = as_view(x)
@@ -162,7 +168,7 @@ def conv2d(x, wpk, Co, k, stride, pad, scale, shift, res=None, act=0, out_mode=0
         y_cs, y_co, y_ptr = 0, 0, _lib.ptr(o)
     else:
         y_cs, y_co, y_ptr = o.shape[3], 0, _lib.ptr(o)
-    d = _make_desc(x, Co, k, stride, pad, dil, Ho, Wo, out_mode, act, y_cs, y_co, res)
+    d = _make_desc(x, Co, k, stride, pad, dil, Ho, Wo, out_mode, act, y_cs, y_co, res, w_kw)
     prof = LaunchProfiler.active
     with torch.cuda.device(x.buf.device):
         t0 = prof.begin() if prof else None

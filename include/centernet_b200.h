@@ -130,6 +130,8 @@ typedef struct cnb_conv_desc {
   int res_coffset;
   int act;                /* 0 none, 1 relu, 2 sigmoid */
   int out_nchw_f32;       /* output format: 0 NHWC bf16, 1 NCHW fp32 (head maps), 2 NHWC fp32 (DCN offsets) */
+  int w_kw;               /* filter width the weights were PACKED with (0 = KW).  The 8-channel stem packs its 7x7
+                             filter as 7x8 (zero column) so that pairs of taps form one K=16 tensor-core step. */
 } cnb_conv_desc;
 
 size_t cnb_conv_packed_weight_bytes(int Co, int Ci, int KH, int KW);

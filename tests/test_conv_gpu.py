@@ -38,6 +38,15 @@ CONV_CASES = [
     (3, 64, 80, 20, 28, 3, 1, False, False),     # ragged M (tail tile) and Co=80
     (1, 8, 16, 40, 40, 7, 1, True, False),       # stem geometry: 7x7 on a channel-padded input
     (1, 32, 27, 24, 24, 3, 1, False, False),     # Co=27 (offset/mask conv) -> NHWC fp32
+    # row-window kernel (conv_rows.cu): W_out % 128 == 0, Ci <= 64
+    (1, 16, 16, 8, 128, 3, 1, True, False),      # one strip, H < ring depth
+    (4, 16, 16, 128, 128, 3, 1, True, False),    # several rows per CTA: ring reuse, strips end mid-range
+    (2, 16, 32, 16, 256, 3, 2, True, False),     # stride 2: phase planes
+    (1, 32, 64, 24, 256, 3, 2, True, False),
+    (2, 64, 64, 10, 128, 3, 1, True, True),      # 8 chunk planes, residual
+    (1, 64, 27, 6, 256, 3, 1, False, False),     # offset/mask conv geometry, two strips per row, fp32 out
+    (1, 8, 16, 12, 128, 7, 1, True, False),      # stem: taps paired along kw (weights packed 7x8)
+    (2, 8, 16, 40, 256, 7, 1, True, False),
 ]
 
 
@@ -58,11 +67,12 @@ def test_conv_matches_torch(cuda_dev, B, Ci, Co, H, W, k, stride, relu, residual
     if relu:
         ref = ref.relu()
     xn = ops.to_nhwc_bf16(x)
-    wpk = ops.pack_conv_weights(w)
+    w_kw = 8 if (Ci == 8 and k == 7) else 0      # the stem packs its filter 7x8 (see cnb_conv_desc.w_kw)
+    wpk = ops.pack_conv_weights(w, kw_pad=w_kw or None)
     fp32_out = Co % 8 != 0
     y = ops.conv2d(xn, wpk, Co, k, stride, pad, scale, shift,
                    res=ops.to_nhwc_bf16(res) if residual else None, act=1 if relu else 0,
-                   out_mode=2 if fp32_out else 0)
+                   out_mode=2 if fp32_out else 0, w_kw=w_kw)
     torch.cuda.synchronize()
     got = y[..., :Co].permute(0, 3, 1, 2)
     _check(got, ref, 2e-3 if fp32_out else 2e-2)

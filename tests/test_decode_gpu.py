@@ -137,6 +137,39 @@ def test_ctdet_full_size_properties(cuda_dev):
     assert np.isfinite(cx).all() and np.isfinite(cy).all() and (cls >= 0).all() and (cls < 80).all()
 
 
+def test_ctdet_saturated_network_like_maps(cuda_dev):
+    """Heat maps as a random-weight network emits them: sigmoid of large logits -> big plateaus of exactly
+    1.0 (every plateau pixel survives the NMS) next to exact zeros; the top-K is then decided by flat index."""
+    rng = np.random.default_rng(7)
+    B, C, H, W = 3, 80, 128, 128
+    logits = rng.standard_normal((B, C, H // 8, W // 8)).astype(np.float32) * 30.0
+    logits = np.kron(logits, np.ones((8, 8), np.float32)) + rng.standard_normal((B, C, H, W)).astype(np.float32)
+    heat = (1.0 / (1.0 + np.exp(-logits.astype(np.float64)))).astype(np.float32)
+    assert (heat == 1.0).sum() > 10000
+    wh = rng.random((B, 2, H, W)).astype(np.float32) * 30
+    reg = rng.random((B, 2, H, W)).astype(np.float32)
+    ref = decode_np.ctdet_decode(heat, wh, reg)
+    got = _run_ctdet(cuda_dev, heat, wh, reg, 100)
+    assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("ctas", ["1", "3", "7"])
+def test_ctdet_cta_ranges_span_images(cuda_dev, monkeypatch, ctas):
+    """Few persistent CTAs: every CTA's chunk range crosses image (group) boundaries."""
+    monkeypatch.setenv("CNB_DECODE_CTAS", ctas)
+    for kind in ("uniform", "bumps"):
+        heat, wh, reg = synthetic.ctdet_maps(5, 6, 64, 64, seed=17, kind=kind)
+        ref = decode_np.ctdet_decode(heat, wh, reg)
+        assert np.array_equal(_run_ctdet(cuda_dev, heat, wh, reg, 100), ref)
+
+
+def test_ctdet_large_k(cuda_dev):
+    heat, wh, reg = synthetic.ctdet_maps(2, 4, 64, 64, seed=23)
+    for K in (1, 257, 512):
+        ref = decode_np.ctdet_decode(heat, wh, reg, K=K)
+        assert np.array_equal(_run_ctdet(cuda_dev, heat, wh, reg, K), ref)
+
+
 MP_SHAPES = [(2, 17, 128, 128, 100), (3, 17, 64, 96, 100), (1, 5, 30, 41, 40), (2, 17, 136, 136, 100)]
 
 
