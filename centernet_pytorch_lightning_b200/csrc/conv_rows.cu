@@ -34,8 +34,8 @@ constexpr int NPT = NPW * 32;
 constexpr int W_MMA = NPW;                   // warp 4
 constexpr int W_EPI0 = NPW + 1;              // warps 5..8 (TMEM lane quarters 1,2,3,0)
 constexpr int NTHREADS = (W_EPI0 + 4) * 32;  // 288
-constexpr int MAX_SLOTS = 12;
-constexpr int DEPTH = 2;                     // input rows a producer thread keeps in flight
+constexpr int MAX_SLOTS = 20;
+constexpr int MAX_DEPTH = 8;                 // input rows a producer thread may keep in flight (cp.async groups)
 
 struct RArgs {
   cnb_conv_desc d;
@@ -52,6 +52,7 @@ struct RArgs {
   u32 plane_bytes;
   u32 slot_bytes;
   int nslots;
+  int depth;         // input rows in flight per producer thread (<= MAX_DEPTH)
   int nseg;          // Wo / 128
   int units;         // B * nseg * Ho  (one unit = one 128-pixel output row segment)
   int BN;
@@ -67,6 +68,18 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {   // at most n groups still pending
+  switch (n) {
+    case 0: cp_async_wait<0>(); break;
+    case 1: cp_async_wait<1>(); break;
+    case 2: cp_async_wait<2>(); break;
+    case 3: cp_async_wait<3>(); break;
+    case 4: cp_async_wait<4>(); break;
+    case 5: cp_async_wait<5>(); break;
+    case 6: cp_async_wait<6>(); break;
+    default: cp_async_wait<7>(); break;
+  }
 }
 
 // Walks the CTA's units in order and tells, for every unit, which input rows are new.  Used identically by the
@@ -156,14 +169,16 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
     RowWalk w;
     w.start(u_begin, d.Ho, a.s, d.pad, d.KH);
     const int items = a.s * a.nch * a.PW;
-    int pending[DEPTH];   // load indices whose copies are in flight (oldest first)
-    int npend = 0;
+    const int nch_sh = a.nch == 1 ? 0 : (a.nch == 2 ? 1 : (a.nch == 4 ? 2 : 3));
+    const int per_phase = a.nch * a.PW;
+    // A row's copies are only *issued* here; its arrival on the full barrier happens `depth - 1` rows later, so
+    // that many rows of latency are in flight per thread (pend_head .. pend_head + npend are their load indices).
+    int pend_head = 0, npend = 0;
     auto complete_oldest = [&]() {   // the oldest row's copies have landed (caller waited on the group)
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_full[pending[0] % a.nslots]);
-#pragma unroll
-      for (int i = 1; i < DEPTH; ++i) pending[i - 1] = pending[i];
+      if (lane == 0) mbar_arrive(&s_full[pend_head % a.nslots]);
+      ++pend_head;
       --npend;
     };
     for (int u = u_begin; u < u_end; ++u) {
@@ -178,25 +193,27 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
         const bool row_ok = iy >= 0 && iy < d.Hi;
         const __nv_bfloat16* rowp = a.x + ((size_t)(n * d.Hi + (row_ok ? iy : 0)) * d.Wi) * d.x_cstride + d.x_coffset;
         for (int it = tid; it < items; it += NPT) {
-          const int c = it % a.nch;
-          const int r = it / a.nch;
-          const int j = r % a.PW, p = r / a.PW;
+          const int p = it >= per_phase ? 1 : 0;     // stride <= 2: at most two phases
+          const int r = it - p * per_phase;
+          const int c = r & (a.nch - 1);
+          const int j = r >> nch_sh;
           const int xg = a.s * (q0 + j) + p;
           const bool ok = row_ok && xg >= 0 && xg < d.Wi;
           const __nv_bfloat16* src = ok ? rowp + (size_t)xg * d.x_cstride + c * 8 : a.x;
           cp_async16(dst0 + (u32)(p * a.nch + c) * a.plane_bytes + (u32)j * 16u, src, ok ? 16u : 0u);
         }
         cp_async_commit();
-        pending[npend++] = L;
-        if (npend == DEPTH) {
-          cp_async_wait<DEPTH - 1>();
+        if (npend == 0) pend_head = L;
+        ++npend;
+        if (npend == a.depth) {
+          cp_async_wait_dyn(a.depth - 1);
           complete_oldest();
         }
       }
       w.next();
     }
     while (npend > 0) {   // drain
-      cp_async_wait<0>();
+      cp_async_wait_dyn(npend - 1);
       complete_oldest();
     }
   } else if (warp == W_MMA) {
@@ -321,8 +338,10 @@ static bool plan_rows(const cnb_conv_desc* d, RPlan* p) {
     while ((pw_alloc * 16) % 128 != 16) ++pw_alloc;  // fall into distinct banks for the producers' stores
   a.plane_bytes = (u32)pw_alloc * 16u;
   a.slot_bytes = (u32)(s * a.nch) * a.plane_bytes;
-  a.nslots = d->KH + s + DEPTH;
-  if (a.nslots > MAX_SLOTS) return false;
+  // ring: the KH rows of the current unit + the next unit's new rows + the rows in flight
+  static const int env_depth = [] { const char* e = getenv("CNB_ROWS_DEPTH"); return e ? atoi(e) : 0; }();
+  a.depth = env_depth > 0 ? env_depth : MAX_DEPTH;
+  if (a.depth > MAX_DEPTH) a.depth = MAX_DEPTH;
   a.nseg = d->Wo / BM;
   const long long units = (long long)d->B * a.nseg * d->Ho;
   if (units >= (1ll << 31)) return false;
@@ -340,8 +359,13 @@ static bool plan_rows(const cnb_conv_desc* d, RPlan* p) {
   a.tmem_cols = 32;
   while (a.tmem_cols < 2 * a.acc_stride) a.tmem_cols <<= 1;
   a.idesc = make_idesc_bf16(BM, a.BN);
-  p->smem = (size_t)a.b_bytes + (size_t)a.nslots * a.slot_bytes + (size_t)a.BN * 8 + 1024;
-  return p->smem <= 200 * 1024;
+  for (;; --a.depth) {
+    if (a.depth < 2) return false;
+    a.nslots = d->KH + s + a.depth;
+    p->smem = (size_t)a.b_bytes + (size_t)a.nslots * a.slot_bytes + (size_t)a.BN * 8 + 1024;
+    if (a.nslots <= MAX_SLOTS && p->smem <= 200 * 1024) break;
+  }
+  return true;
 }
 
 }  // namespace

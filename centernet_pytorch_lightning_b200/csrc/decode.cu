@@ -77,7 +77,24 @@ struct ScanArgs {
   const float* reg;
   float* out;        // [B,K,6]
   int fuse_ctdet;
+  int debug;         // CNB_DECODE_DEBUG=1: per-CTA phase timestamps into g_dbg (tools/decode_timeline.py)
 };
+
+constexpr int DBG_SLOTS = 8;
+__device__ unsigned long long g_dbg[1024 * DBG_SLOTS];
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define DBG_MARK(slot)                                                                      \
+  do {                                                                                      \
+    if (a.debug && threadIdx.x == 0 && blockIdx.x < 1024) g_dbg[blockIdx.x * DBG_SLOTS + (slot)] = gtimer(); \
+  } while (0)
+#define DBG_ADD(slot, v)                                                                    \
+  do {                                                                                      \
+    if (a.debug && threadIdx.x == 0 && blockIdx.x < 1024) g_dbg[blockIdx.x * DBG_SLOTS + (slot)] += (v); \
+  } while (0)
 
 __device__ __forceinline__ u64 make_key(float score, u32 flat) {
   return ((u64)__float_as_uint(score) << 32) | (u64)(0xFFFFFFFFu - flat);
@@ -364,6 +381,9 @@ __global__ void __launch_bounds__(NT, 2) decode_scan_kernel(const ScanArgs a) {
     return g;
   };
 
+  if (a.debug && tid == 0 && blockIdx.x < 1024)
+    for (int i = 0; i < DBG_SLOTS; ++i) g_dbg[blockIdx.x * DBG_SLOTS + i] = 0;
+  DBG_MARK(0);
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) mbar_init(&s_full[s], 1);
     fence_mbar_init();
@@ -616,6 +636,8 @@ __global__ void __launch_bounds__(NT, 2) decode_scan_kernel(const ScanArgs a) {
 
     // ---- flush: tighten the group's bound, append what can still matter --------------------------------
     if (carry > 0 && (group_ends || carry >= FLUSH_AT)) {   // block-uniform
+      const unsigned long long tf0 = a.debug ? gtimer() : 0ull;
+      DBG_ADD(5, 1);
       if (carry > a.acap) {   // never hand more than acap (>= K) keys per flush to the group's list
         const SmemCands smc{s_list, carry};
         const u64 kth = block_kth_key(smc, a.K, sc);
@@ -728,11 +750,15 @@ __global__ void __launch_bounds__(NT, 2) decode_scan_kernel(const ScanArgs a) {
       learned = thr;   // what this CTA just learnt applies to its next chunks of the group
       learned_g = g;
       __syncthreads();
+      if (a.debug) DBG_ADD(4, gtimer() - tf0);
     }
 
     if (VEC == 4 && tid == 0 && c + NST < c_end) issue_load(lg, lpg, lband, stage);
     advance(lg, lpg, lband);
     ++done_in_group;
+    if (k == 0) DBG_MARK(1);
+    if (nh > 0) DBG_ADD(6, 1);
+    if (c + 1 == c_end) DBG_MARK(2);
 
     // ---- group boundary: account for the chunks done; the CTA that completes the group merges it -------
     if (group_ends) {
@@ -814,6 +840,7 @@ __global__ void __launch_bounds__(NT, 2) decode_scan_kernel(const ScanArgs a) {
     }
     advance(g, pg, band);
   }
+  DBG_MARK(3);
 }
 
 // =================================================================================================
@@ -1023,6 +1050,11 @@ static cudaError_t launch_scan(const ScanArgs& a, size_t smem, cudaStream_t st) 
   return cudaGetLastError();
 }
 
+static int debug_on() {
+  static const int on = env_int("CNB_DECODE_DEBUG", 0);
+  return on;
+}
+
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 static void fill_scan_args(ScanArgs& a, const ScanGeom& g, const WsLayout& w, unsigned char* ws) {
@@ -1044,6 +1076,14 @@ static void fill_scan_args(ScanArgs& a, const ScanGeom& g, const WsLayout& w, un
 }  // namespace cnb
 
 using namespace cnb;
+
+// debug aid (not part of the public header): copies the per-CTA phase timestamps of the last decode launch
+extern "C" int cnb_decode_debug_dump(unsigned long long* host, int n_words) {
+  if (n_words > 1024 * DBG_SLOTS) n_words = 1024 * DBG_SLOTS;
+  CNB_CUDA(cudaDeviceSynchronize());
+  CNB_CUDA(cudaMemcpyFromSymbol(host, g_dbg, (size_t)n_words * sizeof(unsigned long long)));
+  return CNB_OK;
+}
 
 extern "C" size_t cnb_ctdet_decode_workspace_bytes(int B, int C, int H, int W, int K) {
   ScanGeom g;
@@ -1080,6 +1120,7 @@ extern "C" int cnb_ctdet_decode(const float* heat, const float* wh, const float*
   a.topk = nullptr; a.have = nullptr;
   a.wh = wh; a.reg = reg; a.out = out;
   a.fuse_ctdet = 1;
+  a.debug = debug_on();
   CNB_CUDA(cudaMemsetAsync(ws, 0, w.zero_bytes, st));
   cudaError_t e = g.vec == 4 ? launch_scan<4>(a, g.smem, st) : launch_scan<1>(a, g.smem, st);
   if (e != cudaSuccess) {
@@ -1131,6 +1172,7 @@ extern "C" int cnb_multi_pose_decode(const float* heat, const float* wh, const f
   a.have = (int*)(ws + w.have_off);
   a.wh = nullptr; a.reg = nullptr; a.out = nullptr;
   a.fuse_ctdet = 0;
+  a.debug = debug_on();
   CNB_CUDA(cudaMemsetAsync(ws, 0, w.zero_bytes, st));
   cudaError_t e = g.vec == 4 ? launch_scan<4>(a, g.smem, st) : launch_scan<1>(a, g.smem, st);
   if (e != cudaSuccess) {
