@@ -35,6 +35,7 @@ constexpr int W_MMA = NPW;                   // warp 4
 constexpr int W_EPI0 = NPW + 1;              // warps 5..8 (TMEM lane quarters 1,2,3,0)
 constexpr int NTHREADS = (W_EPI0 + 4) * 32;  // 288
 constexpr int MAX_SLOTS = 20;
+constexpr int MAX_STEPS = 64;                // K=16 steps per output tile
 constexpr int MAX_DEPTH = 8;                 // input rows a producer thread may keep in flight (cp.async groups)
 
 struct RArgs {
@@ -83,35 +84,50 @@ __device__ __forceinline__ void cp_async_wait_dyn(int n) {   // at most n groups
 }
 
 // Walks the CTA's units in order and tells, for every unit, which input rows are new.  Used identically by the
-// producer and the MMA warp so that both agree on the load index L of every input row (slot = L % nslots).
+// producer and the MMA warp so that both agree on the ring slot of every input row.  Input row i (0..KH-1) of the
+// current unit has load index Lbase + i; slot and use-parity advance incrementally (no divisions in the loops).
 struct RowWalk {
-  int Ho, s, pad, KH;
+  int Ho, s, KH, nslots;
   int strip, oy;       // current unit
-  int Lbase;           // load index of the unit's first input row (iy0 = oy*s - pad)
-  int Lnext;           // next load index to be assigned
+  int sb;              // ring slot of the unit's first input row (iy0 = oy*s - pad)
+  u32 pb;              // parity of how often the ring has wrapped at that row
   bool fresh;          // first unit of a run (strip start): all KH rows are new
-  __device__ void start(int u, int Ho_, int s_, int pad_, int KH_) {
-    Ho = Ho_; s = s_; pad = pad_; KH = KH_;
+  __device__ void start(int u, int Ho_, int s_, int KH_, int nslots_) {
+    Ho = Ho_; s = s_; KH = KH_; nslots = nslots_;
     strip = u / Ho;
     oy = u - strip * Ho;
-    Lbase = 0;
-    Lnext = KH;
+    sb = 0;
+    pb = 0;
     fresh = true;
   }
-  __device__ int first_new() const { return fresh ? Lbase : Lbase + KH - s; }   // load indices [first_new, Lnext)
+  __device__ int first_new() const { return fresh ? 0 : KH - s; }   // rows [first_new, KH) are new
+  __device__ void slot_of(int i, int* slot, u32* par) const {       // i < nslots
+    int sl = sb + i;
+    u32 p = pb;
+    if (sl >= nslots) {
+      sl -= nslots;
+      p ^= 1u;
+    }
+    *slot = sl;
+    *par = p;
+  }
   __device__ bool last_of_run(int u, int u_end) const { return u + 1 == u_end || oy == Ho - 1; }
   __device__ void next() {   // advance to the following unit
+    int adv;
     if (oy == Ho - 1) {      // next strip: every row is reloaded
       ++strip;
       oy = 0;
-      Lbase = Lnext;
-      Lnext = Lbase + KH;
+      adv = KH;
       fresh = true;
     } else {
       ++oy;
-      Lbase += s;
-      Lnext = Lbase + KH;
+      adv = s;
       fresh = false;
+    }
+    sb += adv;
+    if (sb >= nslots) {
+      sb -= nslots;
+      pb ^= 1u;
     }
   }
 };
@@ -124,6 +140,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
   __shared__ __align__(8) u64 s_tfull[2];
   __shared__ __align__(8) u64 s_tempty[2];
   __shared__ __align__(8) u64 s_bfull;
+  __shared__ __align__(8) u64 s_bdesc[MAX_STEPS];
   __shared__ u32 s_tmem;
 
   const cnb_conv_desc& d = a.d;
@@ -133,6 +150,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
   float* s_scale = reinterpret_cast<float*>(smem_dyn + (smem_base - smem_u32(smem_dyn)) + a.b_bytes +
                                             (size_t)a.nslots * a.slot_bytes);
   float* s_shift = s_scale + a.BN;
+  u64* s_adesc = reinterpret_cast<u64*>(s_shift + a.BN);   // [nslots][steps_per_kh] A-window descriptors
 
   if (tid == 0) {
     for (int i = 0; i < a.nslots; ++i) {
@@ -167,28 +185,31 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
   if (warp < NPW) {
     // =============================== producers: input rows -> ring slots =====================================
     RowWalk w;
-    w.start(u_begin, d.Ho, a.s, d.pad, d.KH);
+    w.start(u_begin, d.Ho, a.s, d.KH, a.nslots);
     const int items = a.s * a.nch * a.PW;
     const int nch_sh = a.nch == 1 ? 0 : (a.nch == 2 ? 1 : (a.nch == 4 ? 2 : 3));
     const int per_phase = a.nch * a.PW;
     // A row's copies are only *issued* here; its arrival on the full barrier happens `depth - 1` rows later, so
-    // that many rows of latency are in flight per thread (pend_head .. pend_head + npend are their load indices).
-    int pend_head = 0, npend = 0;
+    // that many rows of latency are in flight per thread.  Rows are issued in ring order, so the oldest pending
+    // row's slot simply advances by one.
+    int pend_slot = 0, npend = 0;
     auto complete_oldest = [&]() {   // the oldest row's copies have landed (caller waited on the group)
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_full[pend_head % a.nslots]);
-      ++pend_head;
+      if (lane == 0) mbar_arrive(&s_full[pend_slot]);
+      if (++pend_slot == a.nslots) pend_slot = 0;
       --npend;
     };
+    int n = w.strip / a.nseg, seg = w.strip - n * a.nseg;
     for (int u = u_begin; u < u_end; ++u) {
-      const int n = w.strip / a.nseg, seg = w.strip - n * a.nseg;
       const int q0 = seg * BM + a.q_off;            // q of plane pixel 0
       const int iy0 = w.oy * a.s - d.pad;
-      for (int L = w.first_new(); L < w.Lnext; ++L) {
-        const int iy = iy0 + (L - w.Lbase);
-        const int slot = L % a.nslots;
-        mbar_wait(&s_empty[slot], (((u32)(L / a.nslots)) & 1u) ^ 1u);
+      for (int i = w.first_new(); i < d.KH; ++i) {
+        const int iy = iy0 + i;
+        int slot;
+        u32 par;
+        w.slot_of(i, &slot, &par);
+        mbar_wait(&s_empty[slot], par ^ 1u);
         const u32 dst0 = ring_base + (u32)slot * a.slot_bytes;
         const bool row_ok = iy >= 0 && iy < d.Hi;
         const __nv_bfloat16* rowp = a.x + ((size_t)(n * d.Hi + (row_ok ? iy : 0)) * d.Wi) * d.x_cstride + d.x_coffset;
@@ -203,12 +224,16 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
           cp_async16(dst0 + (u32)(p * a.nch + c) * a.plane_bytes + (u32)j * 16u, src, ok ? 16u : 0u);
         }
         cp_async_commit();
-        if (npend == 0) pend_head = L;
+        if (npend == 0) pend_slot = slot;
         ++npend;
         if (npend == a.depth) {
           cp_async_wait_dyn(a.depth - 1);
           complete_oldest();
         }
+      }
+      if (w.oy == d.Ho - 1 && ++seg == a.nseg) {   // the next unit starts another strip
+        seg = 0;
+        ++n;
       }
       w.next();
     }
@@ -218,52 +243,80 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
     }
   } else if (warp == W_MMA) {
     // =============================== MMA issuer ==============================================================
+    // Step table (built once, all 32 lanes): for K=16 step ks the filter row kh, the byte offset of the A window
+    // inside a row slot and the weight descriptor -- the issue loop itself is adds and one tcgen05.mma per step.
+    const int ncp = a.nch >= 2 ? a.nch / 2 : 0;
+    const int steps_per_kh = ncp ? d.KW * ncp : a.KWp / 2;
+    const int nsteps = d.KH * steps_per_kh;
+    const u32 lbo = ncp ? a.plane_bytes : 16u;
+    for (int r = lane; r < steps_per_kh; r += 32) {
+      u32 aoff;
+      if (ncp) {
+        const int kw = r / ncp, cp = r - kw * ncp;
+        const int off = kw - d.pad;                      // input x = s*ox + kw - pad = s*(ox + dq) + phase
+        const int dq = off >= 0 ? off / a.s : -((-off + a.s - 1) / a.s);
+        const int p = off - dq * a.s;
+        aoff = (u32)(p * a.nch + 2 * cp) * a.plane_bytes + (u32)(dq - a.q_off) * 16u;
+      } else {
+        aoff = (u32)(2 * r) * 16u;                       // 8 channels: one step = the taps kw = 2r, 2r+1
+      }
+      for (int sl = 0; sl < a.nslots; ++sl)
+        s_adesc[sl * steps_per_kh + r] = make_sdesc(ring_base + (u32)sl * a.slot_bytes + aoff, lbo, 128, 0);
+    }
+    for (int ks = lane; ks < nsteps; ks += 32)
+      s_bdesc[ks] = make_sdesc(smem_base + (u32)(ks >> 2) * a.b_slab_bytes, 16, 1024, 2) + (u64)(2 * (ks & 3));
+    __syncwarp();
     if (lane == 0) {
       // resident weights
       mbar_expect_tx(&s_bfull, a.b_bytes);
       for (int sl = 0; sl < a.nslab; ++sl) tma_load_2d(smem_base + (u32)sl * a.b_slab_bytes, &tmB, sl * 64, 0, &s_bfull);
       mbar_wait(&s_bfull, 0);
       RowWalk w;
-      w.start(u_begin, d.Ho, a.s, d.pad, d.KH);
-      const int ncp = a.nch >= 2 ? a.nch / 2 : 0;
+      w.start(u_begin, d.Ho, a.s, d.KH, a.nslots);
       u32 t = 0;
       for (int u = u_begin; u < u_end; ++u, ++t) {
-        for (int L = w.first_new(); L < w.Lnext; ++L) mbar_wait(&s_full[L % a.nslots], ((u32)(L / a.nslots)) & 1u);
+        for (int i = w.first_new(); i < d.KH; ++i) {
+          int slot;
+          u32 par;
+          w.slot_of(i, &slot, &par);
+          mbar_wait(&s_full[slot], par);
+        }
         const u32 acc = t & 1u, acc_ph = (t >> 1) & 1u;
         mbar_wait(&s_tempty[acc], acc_ph ^ 1u);
         tc_fence_after();
         const u32 tmem_d = tmem_base + acc * a.acc_stride;
         u32 accumulate = 0;
         int ks = 0;
+        int slot = w.sb;
         for (int kh = 0; kh < d.KH; ++kh) {
-          const u32 slot_addr = ring_base + (u32)((w.Lbase + kh) % a.nslots) * a.slot_bytes;
-          if (ncp) {
-            for (int kw = 0; kw < d.KW; ++kw) {
-              // input x = s*ox + kw - pad = s*(ox + dq) + phase
-              const int off = kw - d.pad;
-              const int dq = off >= 0 ? off / a.s : -((-off + a.s - 1) / a.s);
-              const int p = off - dq * a.s;
-              for (int cp = 0; cp < ncp; ++cp, ++ks) {
-                const u32 astart = slot_addr + (u32)(p * a.nch + 2 * cp) * a.plane_bytes + (u32)(dq - a.q_off) * 16u;
-                const u64 da = make_sdesc(astart, a.plane_bytes, 128, 0);
-                const u64 db = make_sdesc(smem_base + (u32)(ks >> 2) * a.b_slab_bytes, 16, 1024, 2) + (u64)(2 * (ks & 3));
-                umma_bf16(tmem_d, da, db, a.idesc, accumulate);
+          const u64* ad = s_adesc + slot * steps_per_kh;
+          // table entries are fetched four steps ahead of the MMAs that use them: the issue loop is latency
+          // bound (one thread), so the LDS latency must not sit between two tcgen05.mma
+          for (int r0 = 0; r0 < steps_per_kh; r0 += 4) {
+            u64 da[4], bd[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              da[j] = ad[min(r0 + j, steps_per_kh - 1)];
+              bd[j] = s_bdesc[min(ks + j, nsteps - 1)];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (r0 + j < steps_per_kh) {
+                umma_bf16(tmem_d, da[j], bd[j], a.idesc, accumulate);
                 accumulate = 1;
               }
             }
-          } else {
-            for (int j = 0; j < a.KWp / 2; ++j, ++ks) {   // 8 channels: one K=16 step = the taps kw = 2j, 2j+1
-              const u32 astart = slot_addr + (u32)(2 * j) * 16u;
-              const u64 da = make_sdesc(astart, 16, 128, 0);
-              const u64 db = make_sdesc(smem_base + (u32)(ks >> 2) * a.b_slab_bytes, 16, 1024, 2) + (u64)(2 * (ks & 3));
-              umma_bf16(tmem_d, da, db, a.idesc, accumulate);
-              accumulate = 1;
-            }
+            ks += min(4, steps_per_kh - r0);
           }
+          if (++slot == a.nslots) slot = 0;
         }
         // release the input rows no later unit needs
         const int nrel = w.last_of_run(u, u_end) ? d.KH : a.s;
-        for (int i = 0; i < nrel; ++i) umma_commit(&s_empty[(w.Lbase + i) % a.nslots]);
+        slot = w.sb;
+        for (int i = 0; i < nrel; ++i) {
+          umma_commit(&s_empty[slot]);
+          if (++slot == a.nslots) slot = 0;
+        }
         umma_commit(&s_tfull[acc]);
         w.next();
       }
@@ -274,9 +327,9 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
     const int HoWo = d.Ho * d.Wo;
     int strip = u_begin / d.Ho;
     int oy = u_begin - strip * d.Ho;
+    int n = strip / a.nseg, seg = strip - n * a.nseg;
     u32 t = 0;
     for (int u = u_begin; u < u_end; ++u, ++t) {
-      const int n = strip / a.nseg, seg = strip - n * a.nseg;
       const u32 acc = t & 1u, acc_ph = (t >> 1) & 1u;
       const int opix = oy * d.Wo + seg * BM + 32 * q + lane;
       const int m = n * HoWo + opix;
@@ -296,7 +349,10 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
       if (lane == 0) mbar_arrive(&s_tempty[acc]);
       if (++oy == d.Ho) {
         oy = 0;
-        ++strip;
+        if (++seg == a.nseg) {
+          seg = 0;
+          ++n;
+        }
       }
     }
   }
@@ -350,7 +406,7 @@ static bool plan_rows(const cnb_conv_desc* d, RPlan* p) {
   if (a.BN > 256) return false;
   const int Ktot = d->KH * KWp * Ci;
   const int Kpad = round_up(Ktot, 64);
-  if (Ktot % 16 != 0) return false;
+  if (Ktot % 16 != 0 || Ktot / 16 > MAX_STEPS) return false;
   a.nslab = Kpad / 64;
   a.b_slab_bytes = (u32)a.BN * 128u;
   a.b_bytes = (u32)a.nslab * a.b_slab_bytes;
@@ -362,7 +418,8 @@ static bool plan_rows(const cnb_conv_desc* d, RPlan* p) {
   for (;; --a.depth) {
     if (a.depth < 2) return false;
     a.nslots = d->KH + s + a.depth;
-    p->smem = (size_t)a.b_bytes + (size_t)a.nslots * a.slot_bytes + (size_t)a.BN * 8 + 1024;
+    p->smem = (size_t)a.b_bytes + (size_t)a.nslots * a.slot_bytes + (size_t)a.BN * 8 + 1024 +
+              (size_t)a.nslots * (Ktot / 16 / d->KH) * 8;
     if (a.nslots <= MAX_SLOTS && p->smem <= 200 * 1024) break;
   }
   return true;

@@ -37,14 +37,22 @@ constexpr int NT = 256;          // threads per CTA
 constexpr int NW = NT / 32;
 constexpr int MAX_K = 512;
 constexpr int NST = 4;           // tile stages in flight per CTA
-constexpr int NB = 1026;         // score histogram bins
-constexpr int BIN_BASE = 0x3B7F; // (bits >> 16) of 2^-8, minus 1: bin 0 = everything below 2^-8
-constexpr int FB0 = 513;         // first coarse bin (score 2^-4) that has fine sub-bins
-constexpr int FSUB = 32;         // fine sub-bins per coarse bin (5 more mantissa bits)
-constexpr int NBF = (NB - FB0) * FSUB;
+// Score histogram, three levels (all counts of NMS survivors, per group):
+//   octave : exponent of the score, 2^-16 .. 1            (NOCT counters)
+//   coarse : 7 mantissa bits, 128 bins per octave         (NCB counters)
+//   fine   : 4 more mantissa bits, 16 sub-bins per coarse (NBF counters; large groups only)
+constexpr int EXP0 = 111;                      // scores below 2^-16 are not counted (never bound anything)
+constexpr int CB_BASE = EXP0 << 7;             // (bits >> 16) of 2^-16
+constexpr int NOCT = 17;                       // octave 16 = scores >= 1
+constexpr int NCB = 16 * 128 + 1;
+constexpr int FSUB = 16;
+constexpr int NBF = NCB * FSUB;
+constexpr int OCT_PAD = 32;                    // ints reserved per group for the octave sums
+constexpr int NCB_PAD = NCB + 3;               // keeps the per-group arrays 16-byte aligned
 constexpr int MCAP = 2048;       // merge candidates staged in shared memory
 constexpr int RANK_DIRECT = 384; // up to this many candidates are ranked by direct counting
 constexpr int HCAP = 512;        // hit positions recorded per chunk before the dense path takes over
+constexpr int SMALL_FLUSH = 128;   // flushes up to this size reserve their list space up front
 constexpr int FLUSH_AT = 64;     // live survivors a CTA carries across chunks before it talks to global memory
 
 struct ScanArgs {
@@ -66,9 +74,9 @@ struct ScanArgs {
   u64* thr;          // [G]
   int* gcount;       // [G]
   int* gdone;        // [G]
-  int* gtop;         // [G]
-  int* ghist;        // [G][NB]
-  int* gfine;        // [G][NBF] or nullptr: sub-bins of the coarse bins >= FB0 (large groups only)
+  int* goct;         // [G][OCT_PAD]
+  int* ghist;        // [G][NCB_PAD]
+  int* gfine;        // [G][NBF] or nullptr (small groups resolve well enough with the coarse bins)
   u64* lists;        // [G][gcap]
   // results
   u64* topk;         // multi_pose: [G][K] sorted keys
@@ -102,11 +110,14 @@ __device__ __forceinline__ u64 make_key(float score, u32 flat) {
 __device__ __forceinline__ u32 key_hi(u64 k) { return (u32)(k >> 32); }
 __device__ __forceinline__ u32 key_idx(u64 k) { return 0xFFFFFFFFu - (u32)(k & 0xFFFFFFFFull); }
 
-__device__ __forceinline__ int score_bin(u32 bits) {
-  const int b = (int)(bits >> 16) - BIN_BASE;
-  return min(max(b, 0), NB - 1);
+// coarse bin of a score (bits of a positive float); < 0: below the histogram's range
+__device__ __forceinline__ int coarse_bin(u32 bits) {
+  const int b = (int)(bits >> 16) - CB_BASE;
+  return min(b, NCB - 1);
 }
-__device__ __forceinline__ u32 bin_edge_bits(int bin) { return (u32)(bin + BIN_BASE) << 16; }   // bin >= 1
+__device__ __forceinline__ u32 bin_edge_bits(int cb, int sub) {
+  return ((u32)(cb + CB_BASE) << 16) | ((u32)sub << 12);
+}
 
 __device__ __forceinline__ u64 ldcg_u64(const u64* p) {
   return __ldcg(reinterpret_cast<const unsigned long long*>(p));
@@ -337,7 +348,8 @@ __global__ void __launch_bounds__(NT, 2) decode_scan_kernel(const ScanArgs a) {
   __shared__ int s_misc[8];
   __shared__ int s_cnt;        // live survivors carried in s_list
   __shared__ int s_nhit[3];    // hits of chunk k in s_hits[k % 3]
-  __shared__ __align__(8) u64 s_thrq[3];   // the group's bound for chunk k, fetched by thread 0 one chunk ahead
+  __shared__ __align__(8) u64 s_ref_thr;   // periodic refresh of the group's bound from global memory
+  __shared__ int s_ref_g;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int NSTAGE = VEC == 4 ? NST : 1;
@@ -410,17 +422,19 @@ __global__ void __launch_bounds__(NT, 2) decode_scan_kernel(const ScanArgs a) {
     if (VEC == 4 && tid == 0 && c_begin + s < c_end) issue_load(lg, lpg, lband, s);
     advance(lg, lpg, lband);
   }
-  // The group's bound for chunk k is fetched by thread 0 three chunks ahead (register) and handed over through
-  // s_thrq two chunks ahead, so its L2 latency never sits on a barrier.
-  u64 tq = 0ull;           // thread 0: bound fetched for chunk k + 2
-  u64 learned = 0ull;      // the best bound this CTA computed itself for group `learned_g`
-  int learned_g = -1;
-  if (tid == 0 && c_begin < c_end) {
-    s_thrq[0] = ldcg_u64(a.thr + g);
-    if (c_begin + 1 < c_end) s_thrq[1] = ldcg_u64(a.thr + group_after(g, pg, band, 1));
-    if (c_begin + 2 < c_end) tq = ldcg_u64(a.thr + group_after(g, pg, band, 2));
+  // The group's bound lives in a block-uniform register: fetched once when the CTA enters a group, raised by the
+  // CTA's own flushes (which read the group's histogram) and by a background refresh every 8 chunks whose L2
+  // latency is given 4 chunks to hide.
+  u64 tq = 0ull;           // thread 0: refresh in flight ...
+  int tq_g = -1;           // ... and the group it was issued for
+  u64 cur_thr = 0ull;
+  if (tid == 0) {
+    s_thr = c_begin < c_end ? ldcg_u64(a.thr + g) : 0ull;
+    s_ref_thr = 0ull;
+    s_ref_g = -1;
   }
   __syncthreads();
+  cur_thr = s_thr;
 
   for (int c = c_begin; c < c_end; ++c) {
     const int k = c - c_begin;
@@ -434,8 +448,12 @@ __global__ void __launch_bounds__(NT, 2) decode_scan_kernel(const ScanArgs a) {
     u32* hits = s_hits + (k % 3) * HCAP;
     if (tid == 0) s_nhit[(k + 1) % 3] = 0;
 
-    u64 thr = s_thrq[k % 3];                      // a (slightly stale, hence sound) bound of the group
-    if (learned_g == g && learned > thr) thr = learned;
+    if (s_ref_g == g && s_ref_thr > cur_thr) cur_thr = s_ref_thr;   // (written before the previous barrier)
+    u64 thr = cur_thr;                            // a (possibly stale, hence sound) bound of the group
+    if (tid == 0 && (k & 7) == 0) {
+      tq = ldcg_u64(a.thr + g);
+      tq_g = g;
+    }
     if (VEC == 4) {
       mbar_wait(&s_full[stage], (u32)(k / NST) & 1u);
     } else {   // unaligned / odd widths: plain cooperative loads, no pipelining
@@ -527,9 +545,9 @@ __global__ void __launch_bounds__(NT, 2) decode_scan_kernel(const ScanArgs a) {
         }
       }
     }
-    if (tid == 0) {
-      if (c + 2 < c_end) s_thrq[(k + 2) % 3] = tq;
-      if (c + 3 < c_end) tq = ldcg_u64(a.thr + group_after(g, pg, band, 3));
+    if (tid == 0 && (k & 7) == 4) {
+      s_ref_thr = tq;
+      s_ref_g = tq_g;   // tagged with the group it was read for
     }
     __syncthreads();
     const int nh = dense0 ? HCAP + 1 : *nhit;
@@ -629,7 +647,7 @@ __global__ void __launch_bounds__(NT, 2) decode_scan_kernel(const ScanArgs a) {
         s_cnt = n;
         atomicMax(reinterpret_cast<unsigned long long*>(a.thr + g), (unsigned long long)kth);
       }
-      if (kth > thr) thr = kth;
+      if (kth > cur_thr) cur_thr = kth;
       __syncthreads();
     }
     carry = n;
@@ -638,117 +656,155 @@ __global__ void __launch_bounds__(NT, 2) decode_scan_kernel(const ScanArgs a) {
     if (carry > 0 && (group_ends || carry >= FLUSH_AT)) {   // block-uniform
       const unsigned long long tf0 = a.debug ? gtimer() : 0ull;
       DBG_ADD(5, 1);
-      if (carry > a.acap) {   // never hand more than acap (>= K) keys per flush to the group's list
-        const SmemCands smc{s_list, carry};
-        const u64 kth = block_kth_key(smc, a.K, sc);
-        u64 mine[(HCAP + FLUSH_AT + NT - 1) / NT];
-        int nm = 0;
-        for (int i = tid; i < carry; i += NT) mine[nm++] = s_list[i];
-        if (tid == 0) s_cnt = 0;
-        __syncthreads();
-        for (int j = 0; j < nm; ++j)
-          if (mine[j] >= kth) s_list[atomicAdd(&s_cnt, 1)] = mine[j];
-        if (tid == 0) atomicMax(reinterpret_cast<unsigned long long*>(a.thr + g), (unsigned long long)kth);
-        if (kth > thr) thr = kth;
-        __syncthreads();
-        carry = s_cnt;   // == K
-        __syncthreads();
-      }
       const int nf = carry;
+      const bool small = nf <= SMALL_FLUSH;
+      // small flush: room for all nf keys is reserved right away (the merge filters by the final bound anyway),
+      // so the reservation's round trip overlaps the histogram's
+      if (small && tid == 32) s_misc[5] = atomicAdd(a.gcount + g, nf);
+      int* oct = a.goct + (size_t)g * OCT_PAD;
+      int* hist = a.ghist + (size_t)g * NCB_PAD;
+      int* fine = a.gfine ? a.gfine + (size_t)g * NBF : nullptr;
+      if (tid < NOCT) s_hist[tid] = 0;   // octave counts are aggregated per flush: every CTA of a group would
+      __syncthreads();                   // otherwise hammer the same few global counters
       for (int i = tid; i < nf; i += NT) {
         const u64 key = s_list[i];
-        if (key >= thr) {
+        if (key >= cur_thr) {
           const u32 bits = key_hi(key);
-          const int bin = score_bin(bits);
-          if (bin >= 1) atomicAdd(a.ghist + (size_t)g * NB + bin, 1);
-          if (a.gfine && bin >= FB0)
-            atomicAdd(a.gfine + (size_t)g * NBF + (bin - FB0) * FSUB + (int)((bits >> 11) & (FSUB - 1)), 1);
+          const int cb = coarse_bin(bits);
+          if (cb >= 0) {
+            atomicAdd(&s_hist[cb >> 7], 1u);
+            atomicAdd(hist + cb, 1);
+            if (fine) atomicAdd(fine + cb * FSUB + (int)((bits >> 12) & (FSUB - 1)), 1);
+          }
         }
       }
+      __syncthreads();
+      if (tid >= 64 && tid < 64 + NOCT && s_hist[tid - 64]) atomicAdd(oct + (tid - 64), (int)s_hist[tid - 64]);
       // No fence: the histogram is read right away, possibly without this CTA's own increments -- counts only
       // grow, so a stale read gives a weaker but still sound bound; the next flush catches up.
       if (warp == 0) {
-        // largest bin t such that count(bins >= t) >= K  ->  (edge(t) << 32) bounds the K-th key from below
-        int hi = NB - 1;
-        int acc = 0, found = 0, above = 0;
-        const int* hist = a.ghist + (size_t)g * NB;
-        while (hi >= 1 && !found) {
-          int cb[8], sum = 0;
+        // Largest threshold t with count(score >= t) >= K, resolved octave -> coarse bin -> fine sub-bin.  The
+        // three levels are read in ONE round trip, speculating that the crossing octave / bin are the ones of
+        // the bound we already hold; a level is re-read only when the crossing moved.
+        const u32 tb = key_hi(cur_thr);
+        const int cb_prev = cur_thr ? coarse_bin(tb) : -1;
+        const int o_prev = cb_prev >= 0 ? cb_prev >> 7 : 15;
+        int vo = lane < NOCT ? __ldcg(oct + (NOCT - 1 - lane)) : 0;           // lane 0 = top octave
+        auto load_coarse = [&](int o, int (&cv)[4]) {                          // lane 0 = the octave's top bins
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int bin = hi - (lane * 8 + j);
-            cb[j] = bin >= 1 ? __ldcg(hist + bin) : 0;
-            sum += cb[j];
+          for (int j = 0; j < 4; ++j) {
+            const int cb = o * 128 + 127 - (lane * 4 + j);
+            cv[j] = cb < NCB ? __ldcg(hist + cb) : 0;
           }
-          int incl = sum;
+        };
+        int cv[4];
+        load_coarse(o_prev, cv);
+        int fv = (fine && cb_prev >= 0 && lane < FSUB) ? __ldcg(fine + cb_prev * FSUB + (FSUB - 1 - lane)) : 0;
+        // octave level
+        int incl = vo;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int up = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += up;
+        }
+        u32 ok = __ballot_sync(0xffffffffu, incl >= a.K);
+        u64 nt = 0ull;
+        if (ok) {
+          const int lo = __ffs(ok) - 1;                       // lane of the crossing octave
+          const int ostar = NOCT - 1 - lo;
+          int above = __shfl_sync(0xffffffffu, incl - vo, lo);   // survivors counted in the octaves above it
+          if (ostar != o_prev) load_coarse(ostar, cv);
+          // coarse level (descending bins: lane 0 holds the octave's 4 largest)
+          const int csum = cv[0] + cv[1] + cv[2] + cv[3];
+          incl = csum;
 #pragma unroll
           for (int o = 1; o < 32; o <<= 1) {
             const int up = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += up;
           }
-          const int total = __shfl_sync(0xffffffffu, incl, 31);
-          if (acc + total >= a.K) {
-            const int excl = acc + incl - sum;
-            int mybin = 0, myabove = 0;
-            if (excl < a.K && acc + incl >= a.K) {
-              int r = excl;
+          ok = __ballot_sync(0xffffffffu, above + incl >= a.K);
+          if (ok) {
+            const int lc = __ffs(ok) - 1;
+            int mycb = -1, myabove = 0;
+            if (lane == lc) {
+              int r = above + incl - csum;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                if (r + cb[j] >= a.K && !mybin) {
-                  mybin = hi - (lane * 8 + j);
-                  myabove = r;               // survivors counted in the bins above the crossing bin
+              for (int j = 0; j < 4; ++j) {
+                if (r + cv[j] >= a.K && mycb < 0) {
+                  mycb = ostar * 128 + 127 - (lane * 4 + j);
+                  myabove = r;
                 }
-                r += cb[j];
+                r += cv[j];
               }
             }
-            found = __reduce_max_sync(0xffffffffu, mybin);
-            above = __reduce_max_sync(0xffffffffu, myabove);
-          } else {
-            acc += total;
-            hi -= 256;
-          }
-        }
-        u32 sub_bits = 0;
-        if (found >= FB0 && a.gfine) {   // refine inside the crossing bin with its 32 sub-bins
-          const int f = __ldcg(a.gfine + (size_t)g * NBF + (found - FB0) * FSUB + (FSUB - 1 - lane));
-          int incl = f;
+            const int cbstar = __shfl_sync(0xffffffffu, mycb, lc);
+            above = __shfl_sync(0xffffffffu, myabove, lc);
+            int sub = 0;
+            if (fine) {
+              if (cbstar != cb_prev) fv = lane < FSUB ? __ldcg(fine + cbstar * FSUB + (FSUB - 1 - lane)) : 0;
+              incl = fv;
 #pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const int up = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += up;
+              for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+              }
+              ok = __ballot_sync(0xffffffffu, lane < FSUB && above + incl >= a.K);
+              if (ok) sub = FSUB - 1 - (__ffs(ok) - 1);
+            }
+            nt = (u64)bin_edge_bits(cbstar, sub) << 32;
+          } else {
+            nt = (u64)bin_edge_bits(ostar * 128, 0) << 32;   // (stale coarse counts) the octave's lower edge
           }
-          const u32 ok = __ballot_sync(0xffffffffu, above + incl >= a.K);
-          if (ok) sub_bits = (u32)(FSUB - 1 - (__ffs(ok) - 1)) << 11;
         }
         if (lane == 0) {
-          u64 t = thr;
-          if (found >= 1) {
-            const u64 nt = (u64)(bin_edge_bits(found) | sub_bits) << 32;
+          u64 t = cur_thr;
+          if (nt > t) {
             atomicMax(reinterpret_cast<unsigned long long*>(a.thr + g), (unsigned long long)nt);
-            if (nt > t) t = nt;
+            t = nt;
           }
           s_thr = t;
           s_cnt = 0;
         }
       }
       __syncthreads();
-      thr = s_thr;
-      for (int i0 = 0; i0 < nf; i0 += NT) {   // warp-aggregated append to the group's candidate list
-        const int i = i0 + tid;
-        const u64 key = i < nf ? s_list[i] : 0ull;
-        const bool keep = i < nf && key >= thr;
-        const u32 bal = __ballot_sync(0xffffffffu, keep);
-        if (bal) {
-          int base = 0;
-          if (lane == 0) base = atomicAdd(a.gcount + g, __popc(bal));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          const int pos = base + __popc(bal & ((1u << lane) - 1u));
-          if (keep && pos < a.gcap) a.lists[(size_t)g * a.gcap + pos] = key;
+      cur_thr = s_thr;
+      if (small) {
+        const int base = s_misc[5];
+        for (int i = tid; i < nf; i += NT)
+          if (base + i < a.gcap) a.lists[(size_t)g * a.gcap + base + i] = s_list[i];
+      } else {
+        // large flush (the first chunks of a group): append only what the new bound lets through
+        int kept = 0;
+        for (int i = tid; i < nf; i += NT) kept += s_list[i] >= cur_thr;
+        kept = warp_sum(kept);
+        if (lane == 0) s_red[warp] = kept;
+        __syncthreads();
+        kept = 0;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) kept += s_red[i];
+        __syncthreads();
+        u64 cut = cur_thr;
+        if (kept > a.acap) {   // plateaus: never hand more than acap (>= K) keys per flush to the group's list
+          const SmemCands smc{s_list, nf};
+          cut = block_kth_key(smc, a.K, sc);
+          if (tid == 0) atomicMax(reinterpret_cast<unsigned long long*>(a.thr + g), (unsigned long long)cut);
+          if (cut > cur_thr) cur_thr = cut;
+        }
+        for (int i0 = 0; i0 < nf; i0 += NT) {   // warp-aggregated append
+          const int i = i0 + tid;
+          const u64 key = i < nf ? s_list[i] : 0ull;
+          const bool keep = i < nf && key >= cut;
+          const u32 bal = __ballot_sync(0xffffffffu, keep);
+          if (bal) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(a.gcount + g, __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const int pos = base + __popc(bal & ((1u << lane) - 1u));
+            if (keep && pos < a.gcap) a.lists[(size_t)g * a.gcap + pos] = key;
+          }
         }
       }
       carry = 0;
-      learned = thr;   // what this CTA just learnt applies to its next chunks of the group
-      learned_g = g;
       __syncthreads();
       if (a.debug) DBG_ADD(4, gtimer() - tf0);
     }
@@ -837,6 +893,12 @@ __global__ void __launch_bounds__(NT, 2) decode_scan_kernel(const ScanArgs a) {
         }
         __syncthreads();
       }
+    }
+    if (group_ends && c + 1 < c_end) {   // entering the next group: fetch its bound (once per group and CTA)
+      if (tid == 0) s_thr = ldcg_u64(a.thr + g + 1);
+      __syncthreads();
+      cur_thr = s_thr;
+      __syncthreads();
     }
     advance(g, pg, band);
   }
@@ -995,9 +1057,9 @@ static bool plan_scan(int H, int W, int K, bool aligned, ScanGeom* g) {
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// workspace: [thr G*8 | gcount G*4 | gdone G*4 | gtop G*4 | ghist G*NB*4] (zeroed per call) | lists | topk | have
+// workspace: [thr | gcount | gdone | octave sums | coarse bins | fine bins] (zeroed per call) | lists | topk | have
 struct WsLayout {
-  size_t thr_off, gcount_off, gdone_off, gtop_off, ghist_off, gfine_off, zero_bytes, lists_off, topk_off, have_off, total;
+  size_t thr_off, gcount_off, gdone_off, goct_off, ghist_off, gfine_off, zero_bytes, lists_off, topk_off, have_off, total;
   bool fine;
   int gcap;
 };
@@ -1011,10 +1073,10 @@ static WsLayout ws_layout(int G, int PG, int K, const ScanGeom& g, bool want_top
   w.thr_off = 0;
   w.gcount_off = align_up((size_t)G * sizeof(u64), 256);
   w.gdone_off = w.gcount_off + align_up((size_t)G * sizeof(int), 256);
-  w.gtop_off = w.gdone_off + align_up((size_t)G * sizeof(int), 256);
-  w.ghist_off = w.gtop_off + align_up((size_t)G * sizeof(int), 256);
+  w.goct_off = w.gdone_off + align_up((size_t)G * sizeof(int), 256);
+  w.ghist_off = w.goct_off + align_up((size_t)G * OCT_PAD * sizeof(int), 256);
   w.fine = fine_for(PG);
-  w.gfine_off = w.ghist_off + align_up((size_t)G * NB * sizeof(int), 256);
+  w.gfine_off = w.ghist_off + align_up((size_t)G * NCB_PAD * sizeof(int), 256);
   w.zero_bytes = w.gfine_off + (w.fine ? align_up((size_t)G * NBF * sizeof(int), 256) : 0);
   w.lists_off = w.zero_bytes;
   w.topk_off = w.lists_off + align_up((size_t)G * w.gcap * sizeof(u64), 256);
@@ -1066,7 +1128,7 @@ static void fill_scan_args(ScanArgs& a, const ScanGeom& g, const WsLayout& w, un
   a.thr = (u64*)(ws + w.thr_off);
   a.gcount = (int*)(ws + w.gcount_off);
   a.gdone = (int*)(ws + w.gdone_off);
-  a.gtop = (int*)(ws + w.gtop_off);
+  a.goct = (int*)(ws + w.goct_off);
   a.ghist = (int*)(ws + w.ghist_off);
   a.gfine = w.fine ? (int*)(ws + w.gfine_off) : nullptr;
   a.lists = (u64*)(ws + w.lists_off);
