@@ -87,6 +87,30 @@ __device__ __forceinline__ void mbar_wait(void* bar, u32 parity) {
     if (++spins > (1u << 27)) __trap();
   }
 }
+// The same with a suspend-time hint, for the warp-specialised kernels: the hardware parks the waiting thread
+// until the phase completes (or the hint expires) instead of returning at once, so an idle role does not burn
+// issue slots that the working warps of the same SM sub-partition need.
+__device__ __forceinline__ bool mbar_try_wait_parked(void* bar, u32 parity) {
+  u32 ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_parked(void* bar, u32 parity) {
+  if (mbar_try_wait_parked(bar, parity)) return;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (!mbar_try_wait_parked(bar, parity)) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 4000000000ull) __trap();   // 4 s: a lost arrival becomes a CUDA error, not a hang
+  }
+}
 // 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP); bytes % 16 == 0, 16B-aligned.
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u32 bytes, void* bar) {
   asm volatile(

@@ -31,12 +31,14 @@ namespace {
 constexpr int BM = 128;
 constexpr int NPW = 4;                       // producer warps
 constexpr int NPT = NPW * 32;
-constexpr int W_MMA = NPW;                   // warp 4
-constexpr int W_EPI0 = NPW + 1;              // warps 5..8 (TMEM lane quarters 1,2,3,0)
-constexpr int NTHREADS = (W_EPI0 + 4) * 32;  // 288
-constexpr int MAX_SLOTS = 20;
+constexpr int NMW = 4;                       // MMA warps: one per output row of a unit (independent issue streams)
+constexpr int W_MMA = NPW;                   // warps 4..7
+constexpr int W_EPI0 = NPW + NMW;            // warps 8..11 (TMEM lane quarters 0,1,2,3)
+constexpr int NTHREADS = (W_EPI0 + 4) * 32;  // 384
+constexpr int MAX_SLOTS = 48;
+constexpr int MAX_ACC = 8;                   // TMEM accumulators in rotation (epilogue latency hiding)
 constexpr int MAX_STEPS = 64;                // K=16 steps per output tile
-constexpr int MAX_DEPTH = 8;                 // input rows a producer thread may keep in flight (cp.async groups)
+constexpr int MAX_DEPTH = 24;                // input rows a producer thread may keep in flight (cp.async groups)
 
 struct RArgs {
   cnb_conv_desc d;
@@ -55,11 +57,17 @@ struct RArgs {
   int nslots;
   int depth;         // input rows in flight per producer thread (<= MAX_DEPTH)
   int nseg;          // Wo / 128
-  int units;         // B * nseg * Ho  (one unit = one 128-pixel output row segment)
+  int R;             // output rows per unit (accumulators interleaved by the MMA warp)
+  int upr;           // units per strip = ceil(Ho / R)
+  int units;         // B * nseg * upr
   int BN;
   int nslab;         // 64-wide K slabs of the resident weights
   u32 b_slab_bytes, b_bytes;
   u32 tmem_cols, acc_stride, idesc;
+  int nbuf;          // unit buffers in TMEM (each R accumulators), power of two
+  int nbuf_sh;
+  int spk;           // K=16 steps per filter row
+  u32 aoff16[16];    // per step of a filter row: offset of its A window inside a row slot, in 16-byte units
 };
 
 __device__ __forceinline__ void cp_async16(u32 dst, const void* src, u32 src_bytes) {
@@ -71,37 +79,42 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_dyn(int n) {   // at most n groups still pending
+#define CNB_CASE(N) case N: cp_async_wait<N>(); break;
   switch (n) {
-    case 0: cp_async_wait<0>(); break;
-    case 1: cp_async_wait<1>(); break;
-    case 2: cp_async_wait<2>(); break;
-    case 3: cp_async_wait<3>(); break;
-    case 4: cp_async_wait<4>(); break;
-    case 5: cp_async_wait<5>(); break;
-    case 6: cp_async_wait<6>(); break;
-    default: cp_async_wait<7>(); break;
+    CNB_CASE(0) CNB_CASE(1) CNB_CASE(2) CNB_CASE(3) CNB_CASE(4) CNB_CASE(5) CNB_CASE(6) CNB_CASE(7)
+    CNB_CASE(8) CNB_CASE(9) CNB_CASE(10) CNB_CASE(11) CNB_CASE(12) CNB_CASE(13) CNB_CASE(14) CNB_CASE(15)
+    CNB_CASE(16) CNB_CASE(17) CNB_CASE(18) CNB_CASE(19) CNB_CASE(20) CNB_CASE(21) CNB_CASE(22)
+    default: cp_async_wait<23>(); break;
   }
+#undef CNB_CASE
 }
 
-// Walks the CTA's units in order and tells, for every unit, which input rows are new.  Used identically by the
-// producer and the MMA warp so that both agree on the ring slot of every input row.  Input row i (0..KH-1) of the
-// current unit has load index Lbase + i; slot and use-parity advance incrementally (no divisions in the loops).
+// Walks the CTA's units in order.  A unit = up to R consecutive output rows of one strip (their K-step chains
+// are interleaved on R accumulators: back-to-back MMAs into one accumulator are latency bound, ~120 clocks
+// each, however small N is).  The unit's input rows i = 0..cnt-1 have ring slots sb+i; the walker tells which of
+// them are new.  Used identically by the producer and the MMA warp so that both agree on every row's slot.
 struct RowWalk {
-  int Ho, s, KH, nslots;
-  int strip, oy;       // current unit
-  int sb;              // ring slot of the unit's first input row (iy0 = oy*s - pad)
+  int Ho, s, KH, R, upr, nslots;
+  int strip, ug;       // current unit: strip and unit index inside the strip
+  int nr, cnt;         // output rows of the unit, input rows it needs ((nr-1)*s + KH)
+  int sb;              // ring slot of the unit's first input row (iy0 = ug*R*s - pad)
   u32 pb;              // parity of how often the ring has wrapped at that row
-  bool fresh;          // first unit of a run (strip start): all KH rows are new
-  __device__ void start(int u, int Ho_, int s_, int KH_, int nslots_) {
-    Ho = Ho_; s = s_; KH = KH_; nslots = nslots_;
-    strip = u / Ho;
-    oy = u - strip * Ho;
+  bool fresh;          // first unit of a run (strip start): all rows are new
+  __device__ void set_rows() {
+    nr = min(R, Ho - ug * R);
+    cnt = (nr - 1) * s + KH;
+  }
+  __device__ void start(int u, int Ho_, int s_, int KH_, int R_, int upr_, int nslots_) {
+    Ho = Ho_; s = s_; KH = KH_; R = R_; upr = upr_; nslots = nslots_;
+    strip = u / upr;
+    ug = u - strip * upr;
     sb = 0;
     pb = 0;
     fresh = true;
+    set_rows();
   }
-  __device__ int first_new() const { return fresh ? 0 : KH - s; }   // rows [first_new, KH) are new
-  __device__ void slot_of(int i, int* slot, u32* par) const {       // i < nslots
+  __device__ int first_new() const { return fresh ? 0 : cnt - nr * s; }   // rows [first_new, cnt) are new
+  __device__ void slot_of(int i, int* slot, u32* par) const {             // i < nslots
     int sl = sb + i;
     u32 p = pb;
     if (sl >= nslots) {
@@ -111,24 +124,27 @@ struct RowWalk {
     *slot = sl;
     *par = p;
   }
-  __device__ bool last_of_run(int u, int u_end) const { return u + 1 == u_end || oy == Ho - 1; }
+  __device__ bool last_of_run(int u, int u_end) const { return u + 1 == u_end || ug == upr - 1; }
+  // input rows that no later unit needs once this one is done
+  __device__ int released(int u, int u_end) const { return last_of_run(u, u_end) ? cnt : R * s; }
   __device__ void next() {   // advance to the following unit
     int adv;
-    if (oy == Ho - 1) {      // next strip: every row is reloaded
+    if (ug == upr - 1) {     // next strip: every row is reloaded
+      adv = cnt;
       ++strip;
-      oy = 0;
-      adv = KH;
+      ug = 0;
       fresh = true;
     } else {
-      ++oy;
-      adv = s;
+      adv = R * s;
+      ++ug;
       fresh = false;
     }
     sb += adv;
-    if (sb >= nslots) {
+    while (sb >= nslots) {
       sb -= nslots;
       pb ^= 1u;
     }
+    set_rows();
   }
 };
 
@@ -137,10 +153,9 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
   extern __shared__ unsigned char smem_dyn[];
   __shared__ __align__(8) u64 s_full[MAX_SLOTS];
   __shared__ __align__(8) u64 s_empty[MAX_SLOTS];
-  __shared__ __align__(8) u64 s_tfull[2];
-  __shared__ __align__(8) u64 s_tempty[2];
+  __shared__ __align__(8) u64 s_tfull[MAX_ACC];
+  __shared__ __align__(8) u64 s_tempty[MAX_ACC];
   __shared__ __align__(8) u64 s_bfull;
-  __shared__ __align__(8) u64 s_bdesc[MAX_STEPS];
   __shared__ u32 s_tmem;
 
   const cnb_conv_desc& d = a.d;
@@ -150,15 +165,14 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
   float* s_scale = reinterpret_cast<float*>(smem_dyn + (smem_base - smem_u32(smem_dyn)) + a.b_bytes +
                                             (size_t)a.nslots * a.slot_bytes);
   float* s_shift = s_scale + a.BN;
-  u64* s_adesc = reinterpret_cast<u64*>(s_shift + a.BN);   // [nslots][steps_per_kh] A-window descriptors
 
   if (tid == 0) {
     for (int i = 0; i < a.nslots; ++i) {
       mbar_init(&s_full[i], NPW);
-      mbar_init(&s_empty[i], 1);
+      mbar_init(&s_empty[i], NMW);      // every MMA warp commits (its own chain of the unit must have retired)
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_tfull[i], 1);
+    for (int i = 0; i < MAX_ACC; ++i) {
+      mbar_init(&s_tfull[i], NMW);
       mbar_init(&s_tempty[i], 4);
     }
     mbar_init(&s_bfull, 1);
@@ -185,7 +199,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
   if (warp < NPW) {
     // =============================== producers: input rows -> ring slots =====================================
     RowWalk w;
-    w.start(u_begin, d.Ho, a.s, d.KH, a.nslots);
+    w.start(u_begin, d.Ho, a.s, d.KH, a.R, a.upr, a.nslots);
     const int items = a.s * a.nch * a.PW;
     const int nch_sh = a.nch == 1 ? 0 : (a.nch == 2 ? 1 : (a.nch == 4 ? 2 : 3));
     const int per_phase = a.nch * a.PW;
@@ -203,13 +217,13 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
     int n = w.strip / a.nseg, seg = w.strip - n * a.nseg;
     for (int u = u_begin; u < u_end; ++u) {
       const int q0 = seg * BM + a.q_off;            // q of plane pixel 0
-      const int iy0 = w.oy * a.s - d.pad;
-      for (int i = w.first_new(); i < d.KH; ++i) {
+      const int iy0 = w.ug * a.R * a.s - d.pad;
+      for (int i = w.first_new(); i < w.cnt; ++i) {
         const int iy = iy0 + i;
         int slot;
         u32 par;
         w.slot_of(i, &slot, &par);
-        mbar_wait(&s_empty[slot], par ^ 1u);
+        mbar_wait_parked(&s_empty[slot], par ^ 1u);
         const u32 dst0 = ring_base + (u32)slot * a.slot_bytes;
         const bool row_ok = iy >= 0 && iy < d.Hi;
         const __nv_bfloat16* rowp = a.x + ((size_t)(n * d.Hi + (row_ok ? iy : 0)) * d.Wi) * d.x_cstride + d.x_coffset;
@@ -231,7 +245,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
           complete_oldest();
         }
       }
-      if (w.oy == d.Ho - 1 && ++seg == a.nseg) {   // the next unit starts another strip
+      if (w.ug == a.upr - 1 && ++seg == a.nseg) {   // the next unit starts another strip
         seg = 0;
         ++n;
       }
@@ -241,83 +255,67 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
       cp_async_wait_dyn(npend - 1);
       complete_oldest();
     }
-  } else if (warp == W_MMA) {
-    // =============================== MMA issuer ==============================================================
-    // Step table (built once, all 32 lanes): for K=16 step ks the filter row kh, the byte offset of the A window
-    // inside a row slot and the weight descriptor -- the issue loop itself is adds and one tcgen05.mma per step.
+  } else if (warp < W_EPI0) {
+    // =============================== MMA issuers (warp W_MMA + j drives output row j of every unit) =========== ==============================================================
+    // Descriptors are pure integer arithmetic on kernel parameters and loop counters (uniform datapath): the
+    // per-step A offsets come from the parameter block (host-computed), nothing is loaded from memory between
+    // two tcgen05.mma.
     const int ncp = a.nch >= 2 ? a.nch / 2 : 0;
-    const int steps_per_kh = ncp ? d.KW * ncp : a.KWp / 2;
-    const int nsteps = d.KH * steps_per_kh;
-    const u32 lbo = ncp ? a.plane_bytes : 16u;
-    for (int r = lane; r < steps_per_kh; r += 32) {
-      u32 aoff;
-      if (ncp) {
-        const int kw = r / ncp, cp = r - kw * ncp;
-        const int off = kw - d.pad;                      // input x = s*ox + kw - pad = s*(ox + dq) + phase
-        const int dq = off >= 0 ? off / a.s : -((-off + a.s - 1) / a.s);
-        const int p = off - dq * a.s;
-        aoff = (u32)(p * a.nch + 2 * cp) * a.plane_bytes + (u32)(dq - a.q_off) * 16u;
-      } else {
-        aoff = (u32)(2 * r) * 16u;                       // 8 channels: one step = the taps kw = 2r, 2r+1
-      }
-      for (int sl = 0; sl < a.nslots; ++sl)
-        s_adesc[sl * steps_per_kh + r] = make_sdesc(ring_base + (u32)sl * a.slot_bytes + aoff, lbo, 128, 0);
-    }
-    for (int ks = lane; ks < nsteps; ks += 32)
-      s_bdesc[ks] = make_sdesc(smem_base + (u32)(ks >> 2) * a.b_slab_bytes, 16, 1024, 2) + (u64)(2 * (ks & 3));
-    __syncwarp();
+    const int steps_per_kh = a.spk;
     if (lane == 0) {
-      // resident weights
-      mbar_expect_tx(&s_bfull, a.b_bytes);
-      for (int sl = 0; sl < a.nslab; ++sl) tma_load_2d(smem_base + (u32)sl * a.b_slab_bytes, &tmB, sl * 64, 0, &s_bfull);
-      mbar_wait(&s_bfull, 0);
+      const int j = warp - W_MMA;
+      if (j == 0) {   // resident weights
+        mbar_expect_tx(&s_bfull, a.b_bytes);
+        for (int sl = 0; sl < a.nslab; ++sl)
+          tma_load_2d(smem_base + (u32)sl * a.b_slab_bytes, &tmB, sl * 64, 0, &s_bfull);
+      }
+      mbar_wait_parked(&s_bfull, 0);
       RowWalk w;
-      w.start(u_begin, d.Ho, a.s, d.KH, a.nslots);
+      w.start(u_begin, d.Ho, a.s, d.KH, a.R, a.upr, a.nslots);
+      const u32 lbo = ncp ? a.plane_bytes : 16u;
+      const u64 dslot0 = make_sdesc(ring_base, lbo, 128, 0);   // slot i adds i * slot_bytes / 16
+      const u32 slot16 = a.slot_bytes >> 4;
+      const u64 db0 = make_sdesc(smem_base, 16, 1024, 2);      // K slab j adds j * b_slab_bytes / 16, step +2
+      const u32 bslab16 = a.b_slab_bytes >> 4;
       u32 t = 0;
       for (int u = u_begin; u < u_end; ++u, ++t) {
-        for (int i = w.first_new(); i < d.KH; ++i) {
+        for (int i = w.first_new(); i < w.cnt; ++i) {
           int slot;
           u32 par;
           w.slot_of(i, &slot, &par);
-          mbar_wait(&s_full[slot], par);
+          mbar_wait_parked(&s_full[slot], par);
         }
-        const u32 acc = t & 1u, acc_ph = (t >> 1) & 1u;
-        mbar_wait(&s_tempty[acc], acc_ph ^ 1u);
+        const u32 buf = t & (u32)(a.nbuf - 1), buf_ph = (t >> a.nbuf_sh) & 1u;
+        mbar_wait_parked(&s_tempty[buf], buf_ph ^ 1u);
         tc_fence_after();
-        const u32 tmem_d = tmem_base + acc * a.acc_stride;
-        u32 accumulate = 0;
-        int ks = 0;
-        int slot = w.sb;
-        for (int kh = 0; kh < d.KH; ++kh) {
-          const u64* ad = s_adesc + slot * steps_per_kh;
-          // table entries are fetched four steps ahead of the MMAs that use them: the issue loop is latency
-          // bound (one thread), so the LDS latency must not sit between two tcgen05.mma
-          for (int r0 = 0; r0 < steps_per_kh; r0 += 4) {
-            u64 da[4], bd[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              da[j] = ad[min(r0 + j, steps_per_kh - 1)];
-              bd[j] = s_bdesc[min(ks + j, nsteps - 1)];
+        if (j < w.nr) {
+          const u32 tmem_d = tmem_base + (buf * (u32)a.R + (u32)j) * a.acc_stride;
+          int sl = w.sb + j * a.s;            // slot of this output row's first input row
+          if (sl >= a.nslots) sl -= a.nslots;
+          u32 rowoff = (u32)sl * slot16;
+          const u32 wrap16 = (u32)a.nslots * slot16;
+          u32 accumulate = 0;
+          u32 ks = 0;
+          for (int kh = 0; kh < d.KH; ++kh) {
+            const u64 dbase = dslot0 + (u64)rowoff;
+            for (int r = 0; r < steps_per_kh; ++r, ++ks) {
+              const u64 da = dbase + (u64)a.aoff16[r];
+              const u64 db = db0 + (u64)((ks >> 2) * bslab16 + 2u * (ks & 3u));
+              umma_bf16(tmem_d, da, db, a.idesc, accumulate);
+              accumulate = 1;
             }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (r0 + j < steps_per_kh) {
-                umma_bf16(tmem_d, da[j], bd[j], a.idesc, accumulate);
-                accumulate = 1;
-              }
-            }
-            ks += min(4, steps_per_kh - r0);
+            rowoff += slot16;                 // next filter row: one slot further
+            if (rowoff >= wrap16) rowoff -= wrap16;
           }
-          if (++slot == a.nslots) slot = 0;
         }
         // release the input rows no later unit needs
-        const int nrel = w.last_of_run(u, u_end) ? d.KH : a.s;
-        slot = w.sb;
+        const int nrel = w.released(u, u_end);
+        int slot = w.sb;
         for (int i = 0; i < nrel; ++i) {
           umma_commit(&s_empty[slot]);
           if (++slot == a.nslots) slot = 0;
         }
-        umma_commit(&s_tfull[acc]);
+        umma_commit(&s_tfull[buf]);
         w.next();
       }
     }
@@ -325,30 +323,33 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
     // =============================== epilogue ================================================================
     const int q = warp & 3;
     const int HoWo = d.Ho * d.Wo;
-    int strip = u_begin / d.Ho;
-    int oy = u_begin - strip * d.Ho;
+    int strip = u_begin / a.upr;
+    int ug = u_begin - strip * a.upr;
     int n = strip / a.nseg, seg = strip - n * a.nseg;
     u32 t = 0;
     for (int u = u_begin; u < u_end; ++u, ++t) {
-      const u32 acc = t & 1u, acc_ph = (t >> 1) & 1u;
-      const int opix = oy * d.Wo + seg * BM + 32 * q + lane;
-      const int m = n * HoWo + opix;
-      mbar_wait(&s_tfull[acc], acc_ph);
+      const u32 buf = t & (u32)(a.nbuf - 1), buf_ph = (t >> a.nbuf_sh) & 1u;
+      const int nr = min(a.R, d.Ho - ug * a.R);
+      mbar_wait_parked(&s_tfull[buf], buf_ph);
       tc_fence_after();
-      const u32 taddr = tmem_base + acc * a.acc_stride + ((u32)(32 * q) << 16);
       const int ngroups = a.BN / 16;
-      for (int g = 0; g < ngroups; ++g) {
-        u32 v[16];
-        tmem_ld16_nowait(taddr + (u32)(g * 16), v);
-        tmem_ld_wait();
-        const int co0 = g * 16;
-        if (co0 < d.Co) epilogue_store(a, s_scale, s_shift, v, m, co0, co0, HoWo, n, opix);
+      for (int j = 0; j < nr; ++j) {
+        const int opix = (ug * a.R + j) * d.Wo + seg * BM + 32 * q + lane;
+        const int m = n * HoWo + opix;
+        const u32 taddr = tmem_base + (buf * (u32)a.R + (u32)j) * a.acc_stride + ((u32)(32 * q) << 16);
+        for (int g = 0; g < ngroups; ++g) {
+          u32 v[16];
+          tmem_ld16_nowait(taddr + (u32)(g * 16), v);
+          tmem_ld_wait();
+          const int co0 = g * 16;
+          if (co0 < d.Co) epilogue_store(a, s_scale, s_shift, v, m, co0, co0, HoWo, n, opix);
+        }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_tempty[acc]);
-      if (++oy == d.Ho) {
-        oy = 0;
+      if (lane == 0) mbar_arrive(&s_tempty[buf]);
+      if (++ug == a.upr) {
+        ug = 0;
         if (++seg == a.nseg) {
           seg = 0;
           ++n;
@@ -399,9 +400,6 @@ static bool plan_rows(const cnb_conv_desc* d, RPlan* p) {
   a.depth = env_depth > 0 ? env_depth : MAX_DEPTH;
   if (a.depth > MAX_DEPTH) a.depth = MAX_DEPTH;
   a.nseg = d->Wo / BM;
-  const long long units = (long long)d->B * a.nseg * d->Ho;
-  if (units >= (1ll << 31)) return false;
-  a.units = (int)units;
   a.BN = round_up(d->Co, 16);
   if (a.BN > 256) return false;
   const int Ktot = d->KH * KWp * Ci;
@@ -412,16 +410,54 @@ static bool plan_rows(const cnb_conv_desc* d, RPlan* p) {
   a.b_bytes = (u32)a.nslab * a.b_slab_bytes;
   a.b_bytes = (a.b_bytes + 1023u) & ~1023u;
   a.acc_stride = (u32)round_up(a.BN, 32);
-  a.tmem_cols = 32;
-  while (a.tmem_cols < 2 * a.acc_stride) a.tmem_cols <<= 1;
-  a.idesc = make_idesc_bf16(BM, a.BN);
-  for (;; --a.depth) {
-    if (a.depth < 2) return false;
-    a.nslots = d->KH + s + a.depth;
-    p->smem = (size_t)a.b_bytes + (size_t)a.nslots * a.slot_bytes + (size_t)a.BN * 8 + 1024 +
-              (size_t)a.nslots * (Ktot / 16 / d->KH) * 8;
-    if (a.nslots <= MAX_SLOTS && p->smem <= 200 * 1024) break;
+  {
+    const int ncp = a.nch >= 2 ? a.nch / 2 : 0;
+    a.spk = ncp ? d->KW * ncp : KWp / 2;
+    if (a.spk > 16) return false;
+    for (int r = 0; r < a.spk; ++r) {
+      u32 aoff;
+      if (ncp) {
+        const int kw = r / ncp, cp = r - kw * ncp;
+        const int off = kw - d->pad;                     // input x = s*ox + kw - pad = s*(ox + dq) + phase
+        const int dq = off >= 0 ? off / s : -((-off + s - 1) / s);
+        const int ph = off - dq * s;
+        aoff = (u32)(ph * a.nch + 2 * cp) * a.plane_bytes + (u32)(dq - a.q_off) * 16u;
+      } else {
+        aoff = (u32)(2 * r) * 16u;                       // 8 channels: one step = the taps kw = 2r, 2r+1
+      }
+      a.aoff16[r] = aoff >> 4;
+    }
   }
+  static const int env_r = [] { const char* e = getenv("CNB_ROWS_R"); return e ? atoi(e) : 0; }();
+  a.idesc = make_idesc_bf16(BM, a.BN);
+  // rows per unit: as many interleaved accumulators as TMEM (2 unit buffers) and the ring (shared memory) allow
+  for (a.R = env_r > 0 ? (env_r > 4 ? 4 : env_r) : 4;; --a.R) {
+    if (a.R < 1) return false;
+    if (2u * (u32)a.R * a.acc_stride > 512u) continue;
+    a.nbuf = 2;
+    while (a.nbuf < MAX_ACC && (u32)(2 * a.nbuf * a.R) * a.acc_stride <= 512u) a.nbuf *= 2;
+    a.nbuf_sh = a.nbuf == 8 ? 3 : (a.nbuf == 4 ? 2 : 1);
+    a.tmem_cols = 32;
+    while (a.tmem_cols < (u32)(a.nbuf * a.R) * a.acc_stride) a.tmem_cols <<= 1;
+    bool fits = false;
+    for (int depth = a.depth; depth >= 2; --depth) {
+      // ring: the unit's rows + the next unit's new rows + the rows in flight
+      const int nslots = (a.R - 1) * s + d->KH + a.R * s + depth;
+      const size_t smem = (size_t)a.b_bytes + (size_t)nslots * a.slot_bytes + (size_t)a.BN * 8 + 1024;
+      if (nslots <= MAX_SLOTS && smem <= 224 * 1024) {
+        a.nslots = nslots;
+        a.depth = depth;
+        p->smem = smem;
+        fits = true;
+        break;
+      }
+    }
+    if (fits) break;
+  }
+  a.upr = (d->Ho + a.R - 1) / a.R;
+  const long long units = (long long)d->B * a.nseg * a.upr;
+  if (units >= (1ll << 31)) return false;
+  a.units = (int)units;
   return true;
 }
 
@@ -465,7 +501,7 @@ int conv_rows_run(const cnb_conv_desc* d, const void* x, const void* wpk, const 
   }
   static bool configured = false;
   if (!configured) {
-    CNB_CUDA(cudaFuncSetAttribute(conv_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    CNB_CUDA(cudaFuncSetAttribute(conv_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     configured = true;
   }
   const int grid = a.units < drv.num_sms ? a.units : drv.num_sms;

@@ -106,7 +106,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int n0 = n_tile * a.BN;
         for (int ks = 0; ks < a.nsteps; ++ks, ++it) {
           const u32 s = it % (u32)a.stages, ph = (it / (u32)a.stages) & 1u;
-          mbar_wait(&s_empty[s], ph ^ 1u);
+          mbar_wait_parked(&s_empty[s], ph ^ 1u);
           const int sl0 = ks * a.g;
           const int nsl = min(a.g, a.nslabs - sl0);
           mbar_expect_tx(&s_full[s], (u32)nsl * (a.a_slab_bytes + a.b_slab_bytes));
@@ -133,13 +133,13 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int mma_per_slab = a.slabW >= 16 ? a.slabW / 16 : 1;
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++t) {
         const u32 acc = t & 1u, acc_ph = (t >> 1) & 1u;
-        mbar_wait(&s_tempty[acc], acc_ph ^ 1u);
+        mbar_wait_parked(&s_tempty[acc], acc_ph ^ 1u);
         tc_fence_after();
         const u32 tmem_d = tmem_base + acc * a.acc_stride;
         u32 accumulate = 0;
         for (int ks = 0; ks < a.nsteps; ++ks, ++it) {
           const u32 s = it % (u32)a.stages, ph = (it / (u32)a.stages) & 1u;
-          mbar_wait(&s_full[s], ph);
+          mbar_wait_parked(&s_full[s], ph);
           tc_fence_after();
           const u32 sa = smem_base + s * a.stage_bytes;
           const u32 sb = sa + a.a_bytes;
@@ -181,7 +181,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         on = m / HoWo;
         opix = m - on * HoWo;
       }
-      mbar_wait(&s_tfull[acc], acc_ph);
+      mbar_wait_parked(&s_tfull[acc], acc_ph);
       tc_fence_after();
       const u32 taddr = tmem_base + acc * a.acc_stride + ((u32)(32 * q) << 16);
       const int ngroups = a.BN / 16;

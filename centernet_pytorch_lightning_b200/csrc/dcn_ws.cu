@@ -141,12 +141,12 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
     u32 s = 0, ph = 0, t = 0;
     for (int tile = tile_begin; tile < tile_end; ++tile, ++t) {
       const u32 tb = t & 1u;
-      mbar_wait(&s_tabfull[tb], (t >> 1) & 1u);
+      mbar_wait_parked(&s_tabfull[tb], (t >> 1) & 1u);
       const float4* tw = s_tabw + tb * NTAB;
       const u32* tbs = s_tabb + tb * NTAB;
       int slab = 0, tap = 0;
       for (int kb = 0; kb < a.nkb; ++kb) {
-        mbar_wait(&s_empty[s], ph ^ 1u);
+        mbar_wait_parked(&s_empty[s], ph ^ 1u);
         const u32 sa = smem_base + s * a.stage_bytes;
         if (tid == 0) {
           mbar_expect_tx(&s_full[s], a.b_bytes);
@@ -229,8 +229,8 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
     u32 t = 0;
     for (int tile = tile_begin; tile < tile_end; ++tile, ++t) {
       const u32 tb = t & 1u;
-      mbar_wait(&s_tabempty[tb], ((t >> 1) & 1u) ^ 1u);
-      mbar_wait(&s_omfull[tb], (t >> 1) & 1u);
+      mbar_wait_parked(&s_tabempty[tb], ((t >> 1) & 1u) ^ 1u);
+      mbar_wait_parked(&s_omfull[tb], (t >> 1) & 1u);
       const float* oms = s_om + tb * (BM * OM_CS);
       const int m0 = tile * BM;
 #pragma unroll 3
@@ -280,12 +280,12 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
       u32 s = 0, ph = 0, t = 0;
       for (int tile = tile_begin; tile < tile_end; ++tile, ++t) {
         const u32 acc = t & 1u, acc_ph = (t >> 1) & 1u;
-        mbar_wait(&s_tempty[acc], acc_ph ^ 1u);
+        mbar_wait_parked(&s_tempty[acc], acc_ph ^ 1u);
         tc_fence_after();
         const u32 tmem_d = tmem_base + acc * a.acc_stride;
         u32 accumulate = 0;
         for (int kb = 0; kb < a.nkb; ++kb) {
-          mbar_wait(&s_full[s], ph);
+          mbar_wait_parked(&s_full[s], ph);
           tc_fence_after();
           const u32 sa = smem_base + s * a.stage_bytes;
           const u64 da = make_sdesc(sa, 16, 1024, 2);
@@ -311,7 +311,7 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
     for (int tile = tile_begin; tile < tile_end; ++tile, ++t) {
       const u32 acc = t & 1u, acc_ph = (t >> 1) & 1u;
       const int m = tile * BM + 32 * q + lane;
-      mbar_wait(&s_tfull[acc], acc_ph);
+      mbar_wait_parked(&s_tfull[acc], acc_ph);
       tc_fence_after();
       const u32 taddr = tmem_base + acc * a.acc_stride + ((u32)(32 * q) << 16);
       const int ngroups = a.BN / 16;

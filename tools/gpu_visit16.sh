@@ -1,0 +1,4 @@
+bash tools_gpu_tests.sh tests/test_conv_gpu.py
+python tools/rows_bench.py
+CNB_ROWS_R=2 python tools/rows_bench.py c16 stem c64
+CNB_ROWS_R=1 python tools/rows_bench.py c16 stem
