@@ -29,12 +29,13 @@ namespace cnb {
 namespace {
 
 constexpr int BM = 128;
-constexpr int NPW = 4;                       // producer warps
+constexpr int NPW = 8;                       // producer warps
 constexpr int NPT = NPW * 32;
+constexpr int MAXI = 5;                      // 16-byte copies per producer thread and input row (<= 1280 per row)
 constexpr int NMW = 4;                       // MMA warps: one per output row of a unit (independent issue streams)
-constexpr int W_MMA = NPW;                   // warps 4..7
-constexpr int W_EPI0 = NPW + NMW;            // warps 8..11 (TMEM lane quarters 0,1,2,3)
-constexpr int NTHREADS = (W_EPI0 + 4) * 32;  // 384
+constexpr int W_MMA = NPW;                   // warps 8..11
+constexpr int W_EPI0 = NPW + NMW;            // warps 12..15 (TMEM lane quarters 0,1,2,3)
+constexpr int NTHREADS = (W_EPI0 + 4) * 32;  // 512
 constexpr int MAX_SLOTS = 48;
 constexpr int MAX_ACC = 8;                   // TMEM accumulators in rotation (epilogue latency hiding)
 constexpr int MAX_STEPS = 64;                // K=16 steps per output tile
@@ -215,8 +216,27 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
       --npend;
     };
     int n = w.strip / a.nseg, seg = w.strip - n * a.nseg;
+    // A thread copies the same (phase, chunk, pixel) cells of every input row of a strip: their source and
+    // destination offsets are worked out once per strip, the per-row loop is one cp.async per cell.
+    int src_off[MAXI];     // element offset inside the input row, < 0: outside the image in x (zero fill)
+    u32 dst_off[MAXI];
+    int strip_done = -1;
     for (int u = u_begin; u < u_end; ++u) {
-      const int q0 = seg * BM + a.q_off;            // q of plane pixel 0
+      if (w.strip != strip_done) {
+        strip_done = w.strip;
+        const int q0 = seg * BM + a.q_off;            // q of plane pixel 0
+#pragma unroll
+        for (int i = 0; i < MAXI; ++i) {
+          const int it = tid + i * NPT;
+          const int p = it >= per_phase ? 1 : 0;       // stride <= 2: at most two phases
+          const int r = it - p * per_phase;
+          const int c = r & (a.nch - 1);
+          const int j = r >> nch_sh;
+          const int xg = a.s * (q0 + j) + p;
+          src_off[i] = (it < items && xg >= 0 && xg < d.Wi) ? xg * d.x_cstride + c * 8 : -1;
+          dst_off[i] = (u32)(p * a.nch + c) * a.plane_bytes + (u32)j * 16u;
+        }
+      }
       const int iy0 = w.ug * a.R * a.s - d.pad;
       for (int i = w.first_new(); i < w.cnt; ++i) {
         const int iy = iy0 + i;
@@ -227,15 +247,12 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
         const u32 dst0 = ring_base + (u32)slot * a.slot_bytes;
         const bool row_ok = iy >= 0 && iy < d.Hi;
         const __nv_bfloat16* rowp = a.x + ((size_t)(n * d.Hi + (row_ok ? iy : 0)) * d.Wi) * d.x_cstride + d.x_coffset;
-        for (int it = tid; it < items; it += NPT) {
-          const int p = it >= per_phase ? 1 : 0;     // stride <= 2: at most two phases
-          const int r = it - p * per_phase;
-          const int c = r & (a.nch - 1);
-          const int j = r >> nch_sh;
-          const int xg = a.s * (q0 + j) + p;
-          const bool ok = row_ok && xg >= 0 && xg < d.Wi;
-          const __nv_bfloat16* src = ok ? rowp + (size_t)xg * d.x_cstride + c * 8 : a.x;
-          cp_async16(dst0 + (u32)(p * a.nch + c) * a.plane_bytes + (u32)j * 16u, src, ok ? 16u : 0u);
+#pragma unroll
+        for (int k = 0; k < MAXI; ++k) {
+          if (tid + k * NPT < items) {
+            const bool ok = row_ok && src_off[k] >= 0;
+            cp_async16(dst0 + dst_off[k], ok ? rowp + src_off[k] : a.x, ok ? 16u : 0u);
+          }
         }
         cp_async_commit();
         if (npend == 0) pend_slot = slot;
@@ -395,6 +412,7 @@ static bool plan_rows(const cnb_conv_desc* d, RPlan* p) {
     while ((pw_alloc * 16) % 128 != 16) ++pw_alloc;  // fall into distinct banks for the producers' stores
   a.plane_bytes = (u32)pw_alloc * 16u;
   a.slot_bytes = (u32)(s * a.nch) * a.plane_bytes;
+  if (s * a.nch * a.PW > MAXI * NPT) return false;
   // ring: the KH rows of the current unit + the next unit's new rows + the rows in flight
   static const int env_depth = [] { const char* e = getenv("CNB_ROWS_DEPTH"); return e ? atoi(e) : 0; }();
   a.depth = env_depth > 0 ? env_depth : MAX_DEPTH;

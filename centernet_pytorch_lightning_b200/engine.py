@@ -49,7 +49,10 @@ class CtdetEngine:
                 torch.cuda.synchronize(self.device)
 
     def _step(self, x):
-        o = self.head(self.model(x)[-1], sigmoid=(self.heat_name,))
+        # the NHWC bf16 feature map goes straight to the heads; the NCHW fp32 copy that `model(x)` returns for
+        # the reference's API (a 134 MB write per batch) is not needed here
+        feat = self.model.forward_nhwc(x) if hasattr(self.model, "forward_nhwc") else self.model(x)[-1]
+        o = self.head(feat, sigmoid=(self.heat_name,))
         det = ctdet_decode(o[self.heat_name], o["width_height"], reg=o.get("regression"), K=self.K)
         return det, o
 
