@@ -47,6 +47,8 @@ def _declare(lib):
         "cnb_conv2d_fprop": (c_int, [POINTER(ConvDesc), P, P, P, P, P, P, P]),
         "cnb_dcnv2_fprop": (c_int, [POINTER(ConvDesc), P, P, c_int, P, P, P, P, P]),
         "cnb_maxpool2d": (c_int, [P, P] + [c_int] * 9 + [P]),
+        "cnb_maxpool2d_pad": (c_int, [P, P] + [c_int] * 7 + [P]),
+        "cnb_depth_to_space2": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
         "cnb_dw_deconv_relayout_weights": (c_int, [P, P, c_int, c_int, P]),
         "cnb_dw_deconv_up": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
         "cnb_nchw_f32_to_nhwc_bf16": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),

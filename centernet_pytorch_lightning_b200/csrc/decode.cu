@@ -455,7 +455,9 @@ __global__ void __launch_bounds__(NT, 2) decode_scan_kernel(const ScanArgs a) {
       tq_g = g;
     }
     if (VEC == 4) {
+      const unsigned long long tw0 = a.debug ? gtimer() : 0ull;
       mbar_wait(&s_full[stage], (u32)(k / NST) & 1u);
+      if (a.debug) DBG_ADD(7, gtimer() - tw0);
     } else {   // unaligned / odd widths: plain cooperative loads, no pipelining
       const int g0 = max(r0 - 1, 0), g1 = min(r1 + 1, a.H);
       const int n = (g1 - g0) * a.W;

@@ -58,6 +58,56 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* 
   }
 }
 
+// ---- MaxPool2d(k, stride, pad) with -inf padding (resnet stem: 3x3, stride 2, pad 1) ------------------------
+__global__ void maxpool_pad_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H,
+                                   int W, int C, int Ho, int Wo, int k, int stride, int pad) {
+  const int groups = C / 8;
+  const long long total = (long long)B * Ho * Wo * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    long long p = i / groups;
+    const int ox = (int)(p % Wo);
+    p /= Wo;
+    const int oy = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    uint4 m = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);   // bf16 -inf pairs
+    for (int dy = 0; dy < k; ++dy) {
+      const int iy = oy * stride - pad + dy;
+      if (iy < 0 || iy >= H) continue;
+      for (int dx = 0; dx < k; ++dx) {
+        const int ix = ox * stride - pad + dx;
+        if (ix < 0 || ix >= W) continue;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + ((size_t)(b * H + iy) * W + ix) * C + g * 8));
+        m.x = bf2_max(m.x, v.x); m.y = bf2_max(m.y, v.y); m.z = bf2_max(m.z, v.z); m.w = bf2_max(m.w, v.w);
+      }
+    }
+    *reinterpret_cast<uint4*>(y + ((size_t)(b * Ho + oy) * Wo + ox) * C + g * 8) = m;
+  }
+}
+
+// ---- depth-to-space (pixel shuffle) by 2: x [B,H,W,4*C] (phase-major channel blocks, phase = py*2+px) ->
+//      y [B,2H,2W,C];  the second half of a dense ConvTranspose2d(4, stride 2, pad 1) run as one 3x3 conv ------
+__global__ void depth_to_space2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B,
+                                       int H, int W, int C) {
+  const int groups = C / 8;
+  const long long total = (long long)B * H * W * 4 * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    long long p = i / groups;
+    const int ph = (int)(p % 4);
+    p /= 4;
+    const int ix = (int)(p % W);
+    p /= W;
+    const int iy = (int)(p % H);
+    const int b = (int)(p / H);
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)(b * H + iy) * W + ix) * 4 + ph) * C + g * 8));
+    const int oy = 2 * iy + (ph >> 1), ox = 2 * ix + (ph & 1);
+    *reinterpret_cast<uint4*>(y + ((size_t)(b * 2 * H + oy) * (2 * W) + ox) * C + g * 8) = v;
+  }
+}
+
 // ---- MaxPool2d(k, stride=k), floor mode -----------------------------------------------------------------
 __global__ void maxpool_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H,
                                int W, int C, int xcs, int xco, int ycs, int yco, int k) {
@@ -206,6 +256,29 @@ extern "C" int cnb_dw_deconv_up(const void* x, const float* wt, const void* add,
   dw_deconv_kernel<<<grid_for(total), 256, 0, (cudaStream_t)s>>>((const __nv_bfloat16*)x, wt,
                                                                  (const __nv_bfloat16*)add, (__nv_bfloat16*)y, B, H,
                                                                  W, C, f);
+  CNB_LAUNCH_CHECK();
+  return CNB_OK;
+}
+
+extern "C" int cnb_maxpool2d_pad(const void* x, void* y, int B, int H, int W, int C, int k, int stride, int pad,
+                                 cnb_stream_t stream) {
+  CNB_CHECK_ARG(x && y && B >= 1 && H >= 1 && W >= 1 && C >= 8 && C % 8 == 0, "maxpool2d_pad: bad argument");
+  CNB_CHECK_ARG(k >= 1 && stride >= 1 && pad >= 0 && 2 * pad <= k, "maxpool2d_pad: bad window");
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  CNB_CHECK_ARG(Ho >= 1 && Wo >= 1, "maxpool2d_pad: empty output");
+  const long long total = (long long)B * Ho * Wo * (C / 8);
+  const int grid = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+  maxpool_pad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, B, H, W, C,
+                                                             Ho, Wo, k, stride, pad);
+  CNB_LAUNCH_CHECK();
+  return CNB_OK;
+}
+
+extern "C" int cnb_depth_to_space2(const void* x, void* y, int B, int H, int W, int C, cnb_stream_t stream) {
+  CNB_CHECK_ARG(x && y && B >= 1 && H >= 1 && W >= 1 && C >= 8 && C % 8 == 0, "depth_to_space2: bad argument");
+  const long long total = (long long)B * H * W * 4 * (C / 8);
+  const int grid = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+  depth_to_space2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, B, H, W, C);
   CNB_LAUNCH_CHECK();
   return CNB_OK;
 }

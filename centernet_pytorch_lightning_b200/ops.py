@@ -211,6 +211,50 @@ def maxpool2d(x, k, out=None):
     return o.buf if out is None else o
 
 
+def maxpool2d_pad(x, k, stride, pad):
+    """MaxPool2d(k, stride, pad) on a dense NHWC bf16 tensor (-inf padding)."""
+    x = as_view(x)
+    assert x.coffset == 0 and x.cstride == x.C, "maxpool2d_pad needs a dense NHWC input"
+    Ho, Wo = (x.H + 2 * pad - k) // stride + 1, (x.W + 2 * pad - k) // stride + 1
+    y = torch.empty((x.B, Ho, Wo, x.C), dtype=torch.bfloat16, device=x.buf.device)
+    with torch.cuda.device(x.buf.device):
+        _lib.check(_lib.lib().cnb_maxpool2d_pad(_lib.ptr(x.buf), _lib.ptr(y), x.B, x.H, x.W, x.C, k, stride, pad,
+                                                 _stream(x.buf)), "cnb_maxpool2d_pad")
+    return y
+
+
+def pack_deconv4x4s2_weights(w):
+    """ConvTranspose2d(Ci, Co, 4, stride 2, padding 1) weight [Ci,Co,4,4] -> packed weights of the equivalent
+    3x3 / stride 1 / pad 1 convolution with 4*Co output channels (channel block = output phase py*2+px):
+    out[2y+py, 2x+px] = sum over the 2x2 input window {y-1+py, y+py} x {x-1+px, x+px} of in * W[kh, kw] with
+    kh = 3 - 2*dy - py... written out: phase 0 uses kernel rows (3, 1) at input rows (y-1, y); phase 1 uses
+    kernel rows (2, 0) at input rows (y, y+1); the same along x."""
+    w = w.detach().float()
+    Ci, Co = w.shape[0], w.shape[1]
+    w3 = torch.zeros(4, Co, Ci, 3, 3, dtype=torch.float32, device=w.device)
+    taps = {0: ((0, 3), (1, 1)), 1: ((1, 2), (2, 0))}      # phase -> ((3x3 tap index, transposed-kernel index), ...)
+    for py in (0, 1):
+        for px in (0, 1):
+            for ty, kh in taps[py]:
+                for tx, kw in taps[px]:
+                    w3[py * 2 + px, :, :, ty, tx] = w[:, :, kh, kw].t()
+    return pack_conv_weights(w3.reshape(4 * Co, Ci, 3, 3))
+
+
+def deconv4x4s2(x, wpk, Co, scale, shift, act=1):
+    """Dense ConvTranspose2d(4, stride 2, pad 1) + per-channel scale/shift (+ReLU): one 3x3 conv producing the
+    four output phases as channel blocks, then a pixel shuffle.  scale/shift are per output channel [Co]."""
+    x = as_view(x)
+    s4 = scale.repeat(4).contiguous() if scale is not None else None
+    b4 = shift.repeat(4).contiguous() if shift is not None else None
+    y4 = conv2d(x, wpk, 4 * Co, 3, 1, 1, s4, b4, act=act)
+    y = torch.empty((x.B, 2 * x.H, 2 * x.W, Co), dtype=torch.bfloat16, device=x.buf.device)
+    with torch.cuda.device(x.buf.device):
+        _lib.check(_lib.lib().cnb_depth_to_space2(_lib.ptr(y4), _lib.ptr(y), x.B, x.H, x.W, Co, _stream(x.buf)),
+                   "cnb_depth_to_space2")
+    return y
+
+
 def relayout_dw_weights(w, f):
     """[C,1,2f,2f] fp32 -> [(2f)^2, C] fp32 for `dw_deconv_up`."""
     w = w.detach().float().contiguous()

@@ -157,6 +157,14 @@ int cnb_dcnv2_fprop(const cnb_conv_desc* d, const void* x, const float* om, int 
  * the pooled map can be written straight into a Root concat buffer (pose_dla_dcn.py:182). */
 int cnb_maxpool2d(const void* x, void* y, int B, int H, int W, int C, int x_cstride, int x_coffset,
                   int y_cstride, int y_coffset, int k, cnb_stream_t stream);
+/* MaxPool2d(k, stride, padding) with -inf padding, dense NHWC bf16 (the ResNet stem's 3x3 / stride 2 / pad 1 pool,
+ * resnet_dcn.py:139, msra_resnet.py:112). */
+int cnb_maxpool2d_pad(const void* x, void* y, int B, int H, int W, int C, int k, int stride, int pad,
+                      cnb_stream_t stream);
+/* Pixel shuffle by 2: x [B,H,W,4C] (channel blocks ordered by output phase py*2+px) -> y [B,2H,2W,C] NHWC bf16.
+ * Second half of the dense ConvTranspose2d(4, stride 2, pad 1) of resnet_dcn.py:212-220 / msra_resnet.py:165-175,
+ * whose four output phases are computed together by ONE 3x3 tensor-core conv with 4C output channels. */
+int cnb_depth_to_space2(const void* x, void* y, int B, int H, int W, int C, cnb_stream_t stream);
 /* depthwise ConvTranspose2d(C,C,2f,stride=f,padding=f/2,groups=C,bias=False) (pose_dla_dcn.py:466-475).
  * w [C,1,2f,2f] fp32 is first re-laid-out to wt [(2f)^2][C] fp32; then y = up(x) (+ add if add != NULL:
  * fuses `layers[i] + layers[i-1]`, pose_dla_dcn.py:488).  x [B,H,W,C], y/add [B,H*f,W*f,C] NHWC bf16. */

@@ -108,4 +108,44 @@ def center_head_forward(sd, x, names, prefix=""):
     return out
 
 
+# ---- ResNet backbones ------------------------------------------------------------------------------------------
+RESNET_SPEC = {18: ("basic", [2, 2, 2, 2]), 34: ("basic", [3, 4, 6, 3]), 50: ("bottle", [3, 4, 6, 3]),
+               101: ("bottle", [3, 4, 23, 3]), 152: ("bottle", [3, 8, 36, 3])}
+
+
+def _res_block(sd, p, x, kind, stride):
+    residual = x
+    if (p + ".downsample.0.weight") in sd:
+        residual = _bn(sd, p + ".downsample.1", F.conv2d(x, sd[p + ".downsample.0.weight"], stride=stride))
+    if kind == "basic":      # resnet_dcn.py:47-65
+        out = F.relu(_bn(sd, p + ".bn1", _conv(sd, p + ".conv1", x, stride)))
+        out = _bn(sd, p + ".bn2", _conv(sd, p + ".conv2", out))
+    else:                    # resnet_dcn.py:85-106 (stride on the 3x3)
+        out = F.relu(_bn(sd, p + ".bn1", _conv(sd, p + ".conv1", x)))
+        out = F.relu(_bn(sd, p + ".bn2", _conv(sd, p + ".conv2", out, stride)))
+        out = _bn(sd, p + ".bn3", _conv(sd, p + ".conv3", out))
+    return F.relu(out + residual)
+
+
+def pose_resnet_forward(sd, x, num_layers, dcn_variant):
+    """PoseResNet.forward of resnet_dcn.py:233-249 (dcn_variant) / msra_resnet.py:183-199 -> [B,C,H/4,W/4]."""
+    kind, layers = RESNET_SPEC[num_layers]
+    h = F.relu(_bn(sd, "bn1", F.conv2d(x, sd["conv1.weight"], stride=2, padding=3)))
+    h = F.max_pool2d(h, 3, 2, 1)
+    for li, nblocks in enumerate(layers, start=1):
+        for bi in range(nblocks):
+            h = _res_block(sd, f"layer{li}.{bi}", h, kind, 2 if (li > 1 and bi == 0) else 1)
+    for i in range(3):
+        if dcn_variant:
+            b = 6 * i
+            h = F.relu(_bn(sd, f"deconv_layers.{b + 1}", dcn(sd, f"deconv_layers.{b}", h)))
+            h = F.conv_transpose2d(h, sd[f"deconv_layers.{b + 3}.weight"], stride=2, padding=1)
+            h = F.relu(_bn(sd, f"deconv_layers.{b + 4}", h))
+        else:
+            b = 3 * i
+            h = F.conv_transpose2d(h, sd[f"deconv_layers.{b}.weight"], stride=2, padding=1)
+            h = F.relu(_bn(sd, f"deconv_layers.{b + 1}", h))
+    return h
+
+
 from centernet_pytorch_lightning_b200.utils.synthetic import randomize_  # noqa: E402,F401 (seeded weights shared with bench.py)

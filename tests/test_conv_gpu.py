@@ -173,3 +173,22 @@ def test_layout_roundtrip(cuda_dev):
     assert torch.equal(xn[..., :3].permute(0, 3, 1, 2).float(), x) and torch.all(xn[..., 3:] == 0)
     back = ops.to_nchw_f32(ops.View(xn, 3, 0))
     assert torch.equal(back, x)
+
+
+def test_dense_deconv_and_padded_maxpool(cuda_dev):
+    """ConvTranspose2d(4, stride 2, pad 1) as one 3x3 conv + pixel shuffle (resnet_dcn.py:212-220), and the
+    ResNet stem's MaxPool2d(3, 2, 1)."""
+    g = torch.Generator().manual_seed(21)
+    for B, Ci, Co, H, W in [(2, 64, 32, 12, 20), (1, 128, 64, 8, 8)]:
+        x = _bf(torch.randn(B, Ci, H, W, generator=g)).to(cuda_dev)
+        w = _bf(torch.randn(Ci, Co, 4, 4, generator=g) / (Ci * 4) ** 0.5).to(cuda_dev)
+        scale = (0.5 + torch.rand(Co, generator=g)).to(cuda_dev)
+        shift = torch.randn(Co, generator=g).to(cuda_dev)
+        ref = F.conv_transpose2d(x, w, stride=2, padding=1) * scale[None, :, None, None] + shift[None, :, None, None]
+        got = ops.deconv4x4s2(ops.to_nhwc_bf16(x), ops.pack_deconv4x4s2_weights(w), Co, scale, shift, act=1)
+        torch.cuda.synchronize()
+        assert got.shape == (B, 2 * H, 2 * W, Co)
+        _check(got.permute(0, 3, 1, 2), ref.relu(), 2e-2)
+    x = _bf(torch.randn(2, 64, 17, 30, generator=g)).to(cuda_dev)
+    got = ops.maxpool2d_pad(ops.to_nhwc_bf16(x), 3, 2, 1)
+    assert torch.equal(got.permute(0, 3, 1, 2).float(), F.max_pool2d(x, 3, 2, 1))

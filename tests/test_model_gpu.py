@@ -97,3 +97,36 @@ def test_end_to_end_detections_close_to_oracle(cuda_dev):
     assert det.shape == (100, 6) and np.isfinite(det).all()
     assert np.all(np.diff(det[:, 4]) <= 0)
     assert abs(det[0, 4] - ref[0, 4]) <= 5e-2
+
+
+@pytest.mark.parametrize("arch,B,H,W,head_conv", [("res_18", 2, 256, 256, 64),      # BASELINE config 1 geometry
+                                                    ("resdcn_18", 1, 128, 160, 64),
+                                                    ("resdcn_50", 1, 128, 128, 64)])  # config 4 architecture
+def test_resnet_backbones_match_oracle(cuda_dev, arch, B, H, W, head_conv):
+    """ResNet / ResNet-DCN backbones + ctdet heads + decode vs the CPU fp32 oracle (bf16 bound as for DLA-34)."""
+    torch.manual_seed(11)
+    name, n = arch.split("_")
+    m = create_model(arch).eval()
+    h = CenterHead(HEADS, m.out_channels, head_conv).eval()
+    randomize_(m.state_dict(), 11)
+    randomize_(h.state_dict(), 12)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    hd = {k: v.clone() for k, v in h.state_dict().items()}
+    x = torch.rand(B, 3, H, W, generator=torch.Generator().manual_seed(4))
+    with torch.no_grad():
+        ref_feat = net_torch.pose_resnet_forward(sd, x, int(n), name == "resdcn")
+        ref_heads = net_torch.center_head_forward(hd, ref_feat, HEADS)
+        m, h = m.to(cuda_dev), h.to(cuda_dev)
+        out = m(x.to(cuda_dev))
+        assert isinstance(out, list) and len(out) == 1 and out[0].shape == (B, m.out_channels, H // 4, W // 4)
+        heads = h(out[-1])
+        det = ctdet_decode(heads["heatmap"].sigmoid(), heads["width_height"], reg=heads["regression"])
+    torch.cuda.synchronize()
+    l2, mx = _rel(out[0], ref_feat)
+    print(f"{arch} backbone rel-L2 {l2:.4f} max-rel {mx:.4f}")
+    assert l2 <= 3e-2 and mx <= 8e-2
+    for k in HEADS:
+        l2, mx = _rel(heads[k], ref_heads[k])
+        print(f"{arch} head {k} rel-L2 {l2:.4f} max-rel {mx:.4f}")
+        assert l2 <= 3e-2 and mx <= 8e-2
+    assert det.shape == (B, 100, 6) and torch.isfinite(det).all()

@@ -61,3 +61,26 @@ def test_net_oracle_fixture():
         y = net_torch.dla34_seg_forward(sd, x)
     g = np.load(os.path.join(GOLD, "dla34_oracle.npz"))
     np.testing.assert_allclose(y.numpy(), g["feat"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("arch,num_layers", [("res", 18), ("resdcn", 18), ("resdcn", 50)])
+def test_resnet_schema_and_oracle_match_reference(arch, num_layers):
+    """ResNet backbones (msra_resnet.py / resnet_dcn.py): same state-dict schema as the reference modules and the
+    functional oracle reproduces their eval forward exactly."""
+    if not ref_shim.available():
+        pytest.skip("reference sources not present on this machine")
+    from centernet_pytorch_lightning_b200.models import create_model
+    mine = create_model(f"{arch}_{num_layers}")
+    ref = (ref_shim.ref_msra_resnet if arch == "res" else ref_shim.ref_resnet_dcn)(num_layers).eval()
+    a, b = mine.state_dict(), ref.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    assert all(a[k].shape == b[k].shape for k in a)
+    assert mine.out_channels == ref.out_channels
+    sd = {k: v.clone() for k, v in a.items()}
+    net_torch.randomize_(sd, 7)
+    ref.load_state_dict(sd)
+    x = torch.rand(1, 3, 64, 96, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        want = ref(x)[-1]
+        got = net_torch.pose_resnet_forward(sd, x, num_layers, arch == "resdcn")
+    assert torch.equal(got, want)
