@@ -11,7 +11,7 @@
 //     the hardware) straight into the K-major swizzled shared-memory layout tcgen05.mma consumes.
 //   * W tiles come from the packed [Co_pad][Kpad] bf16 matrix with a tiled tensor map, same swizzle.
 //   * Persistent CTAs (one per SM) loop over 128 x BN output tiles.  Warp roles: warp 0 = TMA producer,
-//     warp 1 = MMA issuer (one elected lane), warps 2-5 = epilogue.  Rings: smem stages (full/empty
+//     warp 1 = MMA issuer (one elected lane), warps 2-9 = epilogue (two per TMEM lane quarter).  Rings: smem stages (full/empty
 //     mbarriers) and TWO TMEM accumulators (tmem_full/tmem_empty), so the epilogue of tile i overlaps the
 //     main loop of tile i+1.
 //   * Epilogue: tcgen05.ld (lane = output pixel) -> scale/shift (folded BN or bias) -> (+residual) ->
@@ -24,7 +24,8 @@ namespace cnb {
 namespace {
 
 constexpr int BM = 128;
-constexpr int NTHREADS = 192;
+constexpr int NEPI = 8;                      // epilogue warps: two per TMEM lane quarter, alternating 16-column groups
+constexpr int NTHREADS = (2 + NEPI) * 32;   // 320
 constexpr int MAX_STAGES = 8;
 
 struct TArgs {
@@ -73,7 +74,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_tfull[i], 1);
-      mbar_init(&s_tempty[i], 4);   // one arrival per epilogue warp
+      mbar_init(&s_tempty[i], NEPI);   // one arrival per epilogue warp
     }
     fence_mbar_init();
   }
@@ -170,6 +171,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else {
     // =============================== epilogue (warps 2..5) ================================================
     const int q = warp & 3;              // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;    // which of the quarter's two warps: even / odd column groups
     u32 t = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++t) {
       const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
@@ -185,7 +187,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tc_fence_after();
       const u32 taddr = tmem_base + acc * a.acc_stride + ((u32)(32 * q) << 16);
       const int ngroups = a.BN / 16;
-      for (int g = 0; g < ngroups; ++g) {
+      for (int g = half; g < ngroups; g += 2) {
         u32 v[16];
         tmem_ld16_nowait(taddr + (u32)(g * 16), v);
         tmem_ld_wait();

@@ -121,7 +121,7 @@ __device__ __forceinline__ void epilogue_store(const Args& a, const float* s_sca
     for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
   } else if (d.act == 2) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) f[j] = 1.f / (1.f + __expf(-f[j]));
+    for (int j = 0; j < 16; ++j) f[j] = __fdividef(1.f, 1.f + __expf(-f[j]));   // MUFU.EX2 + MUFU.RCP, ~2 ulp
   }
   if (d.out_nchw_f32 == 0) {          // NHWC bf16 (optionally a channel slice of a concat buffer)
     __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(a.y) + (size_t)m * d.y_cstride + d.y_coffset + co0;
@@ -138,9 +138,12 @@ __device__ __forceinline__ void epilogue_store(const Args& a, const float* s_sca
     }
   } else if (d.out_nchw_f32 == 1) {   // NCHW fp32 (head maps for decode / losses): lanes = consecutive pixels
     float* yp = reinterpret_cast<float*>(a.y) + ((size_t)on * d.Co + co0) * HoWo + opix;
+    const int nj = min(16, d.Co - co0);
 #pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (co0 + j < d.Co) yp[(size_t)j * HoWo] = f[j];
+    for (int j = 0; j < 16; ++j) {
+      if (j < nj) *yp = f[j];
+      yp += HoWo;
+    }
   } else {                            // NHWC fp32 (offset/mask maps feeding the DCN sampler)
     float* yp = reinterpret_cast<float*>(a.y) + (size_t)m * d.y_cstride + d.y_coffset + co0;
 #pragma unroll

@@ -17,7 +17,7 @@ overlap the replay of batch i.
 import torch
 
 from . import _lib
-from .decode import ctdet_decode
+from .decode import ctdet_decode, multi_pose_decode
 
 
 class CtdetEngine:
@@ -26,7 +26,7 @@ class CtdetEngine:
         if self.device.type != "cuda":
             raise _lib.CnbError("CtdetEngine needs a CUDA device (sm_100a kernels; no CPU fallback)")
         self.model, self.head, self.K = model.eval(), head.eval(), K
-        self.heat_name = next(n for n in head.heads if n.startswith("heatmap"))
+        self.heat_name = "heatmap" if "heatmap" in head.heads else next(n for n in head.heads if n.startswith("heatmap"))
         self.inputs = [torch.zeros(batch, 3, height, width, device=self.device) for _ in range(slots)]
         self.outputs = [None] * slots
         self.maps = [None] * slots
@@ -48,11 +48,14 @@ class CtdetEngine:
                     self.graphs[i] = g
                 torch.cuda.synchronize(self.device)
 
-    def _step(self, x):
+    def _heads(self, x, sigmoid):
         # the NHWC bf16 feature map goes straight to the heads; the NCHW fp32 copy that `model(x)` returns for
         # the reference's API (a 134 MB write per batch) is not needed here
         feat = self.model.forward_nhwc(x) if hasattr(self.model, "forward_nhwc") else self.model(x)[-1]
-        o = self.head(feat, sigmoid=(self.heat_name,))
+        return self.head(feat, sigmoid=sigmoid)
+
+    def _step(self, x):
+        o = self._heads(x, (self.heat_name,))
         det = ctdet_decode(o[self.heat_name], o["width_height"], reg=o.get("regression"), K=self.K)
         return det, o
 
@@ -72,3 +75,15 @@ class CtdetEngine:
     def head_maps(self, slot=0):
         """The head maps of the slot's last run (name -> [B,C,H,W] fp32; the heat map is already sigmoided)."""
         return self.maps[slot]
+
+
+class MultiPoseEngine(CtdetEngine):
+    """The same for `CenterNetMultiPose.forward` + `multi_pose_decode` (centernet_multi_pose.py:213-231): heads
+    heatmap / width_height / regression / heatmap_keypoints / keypoints / heatmap_keypoints_offset ->
+    [B,K,3J+6] detections (decode/multi_pose.py:7-96)."""
+
+    def _step(self, x):
+        o = self._heads(x, (self.heat_name, "heatmap_keypoints"))
+        det = multi_pose_decode(o[self.heat_name], o["width_height"], o["keypoints"], reg=o.get("regression"),
+                                hm_hp=o["heatmap_keypoints"], hp_offset=o.get("heatmap_keypoints_offset"), K=self.K)
+        return det, o

@@ -17,9 +17,15 @@ if what == "decode":
     heat, wh, reg = (torch.from_numpy(a).to(dev) for a in (heat, wh, reg))
     for _ in range(4):
         ctdet_decode(heat, wh, reg)
+elif what == "head1x1":
+    mid = torch.randn(B, 128, 128, 768, device=dev).to(torch.bfloat16)
+    w = ops.pack_conv_weights(torch.randn(80, 256, 1, 1, device=dev) * 0.05)
+    bias = torch.zeros(80, device=dev)
+    for _ in range(4):
+        ops.conv2d(ops.View(mid, 256, 0), w, 80, 1, 1, 0, None, bias, act=2, out_mode=1)
 else:
     ci, co, hw, k = {"conv64": (64, 64, 128, 3), "dcn64": (64, 64, 128, 3), "head": (64, 768, 128, 3),
-                     "conv256": (256, 256, 32, 3), "conv16": (16, 16, 512, 3), "stem": (8, 16, 512, 7)}[what]
+                     "conv256": (256, 256, 32, 3), "conv128": (128, 128, 64, 3), "conv16": (16, 16, 512, 3), "stem": (8, 16, 512, 7)}[what]
     x = torch.randn(B, hw, hw, ci, device=dev).to(torch.bfloat16)
     w = ops.pack_conv_weights(torch.randn(co, ci, k, k, device=dev) * 0.05)
     sc, sh = torch.ones(co, device=dev), torch.zeros(co, device=dev)
