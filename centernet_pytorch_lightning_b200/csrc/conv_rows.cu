@@ -32,10 +32,10 @@ constexpr int BM = 128;
 constexpr int NPW = 8;                       // producer warps
 constexpr int NPT = NPW * 32;
 constexpr int MAXI = 5;                      // 16-byte copies per producer thread and input row (<= 1280 per row)
-constexpr int NMW = 4;                       // MMA warps: one per output row of a unit (independent issue streams)
-constexpr int W_MMA = NPW;                   // warps 8..11
-constexpr int W_EPI0 = NPW + NMW;            // warps 12..15 (TMEM lane quarters 0,1,2,3)
-constexpr int NTHREADS = (W_EPI0 + 4) * 32;  // 512
+constexpr int NMW = 8;                       // MMA warps: one per output row of a unit (independent issue streams)
+constexpr int W_MMA = NPW;                   // warps 8..15
+constexpr int W_EPI0 = NPW + NMW;            // warps 16..19 (TMEM lane quarters 0,1,2,3)
+constexpr int NTHREADS = (W_EPI0 + 4) * 32;  // 640
 constexpr int MAX_SLOTS = 48;
 constexpr int MAX_ACC = 8;                   // TMEM accumulators in rotation (epilogue latency hiding)
 constexpr int MAX_STEPS = 64;                // K=16 steps per output tile
@@ -57,6 +57,8 @@ struct RArgs {
   u32 slot_bytes;
   int nslots;
   int depth;         // input rows in flight per producer thread (<= MAX_DEPTH)
+  int npw;           // producer warps that take part (rows with few 16-byte cells do not need all NPW)
+  int nk;            // cells per participating producer thread and row (<= MAXI)
   int nseg;          // Wo / 128
   int R;             // output rows per unit (accumulators interleaved by the MMA warp)
   int upr;           // units per strip = ceil(Ho / R)
@@ -169,7 +171,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
 
   if (tid == 0) {
     for (int i = 0; i < a.nslots; ++i) {
-      mbar_init(&s_full[i], NPW);
+      mbar_init(&s_full[i], a.npw);
       mbar_init(&s_empty[i], NMW);      // every MMA warp commits (its own chain of the unit must have retired)
     }
     for (int i = 0; i < MAX_ACC; ++i) {
@@ -198,6 +200,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
   }
 
   if (warp < NPW) {
+    if (warp >= a.npw) goto done;   // small rows: fewer producer warps, fewer arrivals per row
     // =============================== producers: input rows -> ring slots =====================================
     RowWalk w;
     w.start(u_begin, d.Ho, a.s, d.KH, a.R, a.upr, a.nslots);
@@ -218,6 +221,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
     int n = w.strip / a.nseg, seg = w.strip - n * a.nseg;
     // A thread copies the same (phase, chunk, pixel) cells of every input row of a strip: their source and
     // destination offsets are worked out once per strip, the per-row loop is one cp.async per cell.
+    const int npt = a.npw * 32;
     int src_off[MAXI];     // element offset inside the input row, < 0: outside the image in x (zero fill)
     u32 dst_off[MAXI];
     int strip_done = -1;
@@ -227,7 +231,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
         const int q0 = seg * BM + a.q_off;            // q of plane pixel 0
 #pragma unroll
         for (int i = 0; i < MAXI; ++i) {
-          const int it = tid + i * NPT;
+          const int it = tid + i * npt;
           const int p = it >= per_phase ? 1 : 0;       // stride <= 2: at most two phases
           const int r = it - p * per_phase;
           const int c = r & (a.nch - 1);
@@ -249,7 +253,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
         const __nv_bfloat16* rowp = a.x + ((size_t)(n * d.Hi + (row_ok ? iy : 0)) * d.Wi) * d.x_cstride + d.x_coffset;
 #pragma unroll
         for (int k = 0; k < MAXI; ++k) {
-          if (tid + k * NPT < items) {
+          if (k < a.nk && tid + k * npt < items) {
             const bool ok = row_ok && src_off[k] >= 0;
             cp_async16(dst0 + dst_off[k], ok ? rowp + src_off[k] : a.x, ok ? 16u : 0u);
           }
@@ -374,6 +378,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
       }
     }
   }
+done:
   tc_fence_before();
   __syncthreads();
   if (warp == W_MMA) tmem_dealloc(tmem_base, a.tmem_cols);
@@ -413,6 +418,13 @@ static bool plan_rows(const cnb_conv_desc* d, RPlan* p) {
   a.plane_bytes = (u32)pw_alloc * 16u;
   a.slot_bytes = (u32)(s * a.nch) * a.plane_bytes;
   if (s * a.nch * a.PW > MAXI * NPT) return false;
+  {
+    const int items = s * a.nch * a.PW;
+    a.npw = (items + 63) / 64;             // about two cells per thread
+    if (a.npw > NPW) a.npw = NPW;
+    if (a.npw < 1) a.npw = 1;
+    a.nk = (items + a.npw * 32 - 1) / (a.npw * 32);
+  }
   // ring: the KH rows of the current unit + the next unit's new rows + the rows in flight
   static const int env_depth = [] { const char* e = getenv("CNB_ROWS_DEPTH"); return e ? atoi(e) : 0; }();
   a.depth = env_depth > 0 ? env_depth : MAX_DEPTH;
@@ -449,7 +461,7 @@ static bool plan_rows(const cnb_conv_desc* d, RPlan* p) {
   static const int env_r = [] { const char* e = getenv("CNB_ROWS_R"); return e ? atoi(e) : 0; }();
   a.idesc = make_idesc_bf16(BM, a.BN);
   // rows per unit: as many interleaved accumulators as TMEM (2 unit buffers) and the ring (shared memory) allow
-  for (a.R = env_r > 0 ? (env_r > 4 ? 4 : env_r) : 4;; --a.R) {
+  for (a.R = env_r > 0 ? (env_r > NMW ? NMW : env_r) : NMW;; --a.R) {
     if (a.R < 1) return false;
     if (2u * (u32)a.R * a.acc_stride > 512u) continue;
     a.nbuf = 2;

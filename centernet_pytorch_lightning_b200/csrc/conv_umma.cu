@@ -1,4 +1,8 @@
-// Implicit-GEMM convolution and DCNv2 on the 5th-gen tensor cores (tcgen05.mma, accumulator in TMEM).
+// Implicit-GEMM convolution and DCNv2 on the 5th-gen tensor cores (tcgen05.mma, accumulator in TMEM): the general
+// cp.async-gather kernel, and the dispatch of cnb_conv2d_fprop / cnb_dcnv2_fprop to the specialised kernels
+// (conv_rows.cu: wide thin layers; conv_tma.cu: Ci >= 32 TMA im2col; dcn_ws.cu: warp-specialised DCNv2).  This kernel
+// keeps every remaining geometry correct (thin inputs at widths that are not a multiple of 128, Ci % 64 != 0 DCN,
+// CNB_CONV_IMPL=v1 / CNB_DCN_IMPL=v1 for A/B runs).
 //
 // Replaces (reference file:line under CenterNet/models/):
 //   nn.Conv2d + nn.BatchNorm2d(eval) [+ residual add] [+ nn.ReLU] chains of
@@ -442,8 +446,6 @@ static int run_conv(const cnb_conv_desc* d, const void* x, const float* om, int 
     // plain convolutions: TMA-im2col warp-specialised kernel (conv_tma.cu); CNB_CONV_IMPL=v1 keeps the
     // cp.async gather kernel below for A/B comparisons
     static const bool use_v1 = [] { const char* e = getenv("CNB_CONV_IMPL"); return e && e[0] == 'v' && e[1] == '1'; }();
-    // thin inputs (Ci < 32: 16/32-byte im2col rows) are far below the TMA engine's efficient row size; they
-    // stay on the cp.async gather until the shared-memory patch kernel covers them
     CNB_CHECK_ARG(d->w_kw == 0 || d->w_kw >= d->KW, "conv: w_kw=%d smaller than KW=%d", d->w_kw, d->KW);
     // wide thin layers (W_out % 128 == 0, Ci <= 64, KxK): row-window kernel, every input pixel fetched once
     if (!use_v1 && conv_rows_supported(d)) return conv_rows_run(d, x, wpk, scale, shift, res, y, st);
