@@ -188,6 +188,61 @@ __global__ void dw_deconv_kernel(const __nv_bfloat16* __restrict__ x, const floa
   }
 }
 
+// The same with the taps held in registers.  All outputs of one phase (py, px) = ((oy + f/2) % f, (ox + f/2) % f) use
+// the same four filter taps {py, py+f} x {px, px+f}; blockIdx.y picks the phase, a thread keeps its 8-channel group
+// fixed, so its 4 x 8 weights are loaded once and every output costs 4 input loads + (add) + 1 store instead of
+// 13 loads (the weight loads were most of the L1 wavefronts of the generic kernel above).
+__global__ void __launch_bounds__(256)
+dw_deconv_phase_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wt,
+                       const __nv_bfloat16* __restrict__ add, __nv_bfloat16* __restrict__ y, int B, int H, int W,
+                       int C, int f) {
+  const int Ho = H * f, Wo = W * f, groups = C / 8, ks = 2 * f, pad = f / 2;
+  const int py = blockIdx.y / f, px = blockIdx.y - py * f;
+  const int g = threadIdx.x % groups;               // blockDim.x and the grid stride are multiples of `groups`
+  float w[4][8];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int ky = py + (t >> 1) * f, kx = px + (t & 1) * f;
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(wt + (size_t)(ky * ks + kx) * C + g * 8));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(wt + (size_t)(ky * ks + kx) * C + g * 8 + 4));
+    w[t][0] = w0.x; w[t][1] = w0.y; w[t][2] = w0.z; w[t][3] = w0.w;
+    w[t][4] = w1.x; w[t][5] = w1.y; w[t][6] = w1.z; w[t][7] = w1.w;
+  }
+  const int QW = W + 1, QH = H + 1;
+  const long long total = (long long)B * QH * QW * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long p = i / groups;
+    const int qx = (int)(p % QW);
+    p /= QW;
+    const int qy = (int)(p % QH);
+    const int b = (int)(p / QH);
+    const int oy = qy * f + py - pad, ox = qx * f + px - pad;
+    if (oy < 0 || oy >= Ho || ox < 0 || ox >= Wo) continue;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {                    // tap (ky, kx) = (py + a*f, px + c*f) reads input (qy - a, qx - c)
+      const int iy = qy - (t >> 1), ix = qx - (t & 1);
+      if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + ((size_t)(b * H + iy) * W + ix) * C + g * 8));
+      const float2 a0 = bf2_to_f2(v.x), a1 = bf2_to_f2(v.y), a2 = bf2_to_f2(v.z), a3 = bf2_to_f2(v.w);
+      acc[0] += w[t][0] * a0.x; acc[1] += w[t][1] * a0.y; acc[2] += w[t][2] * a1.x; acc[3] += w[t][3] * a1.y;
+      acc[4] += w[t][4] * a2.x; acc[5] += w[t][5] * a2.y; acc[6] += w[t][6] * a3.x; acc[7] += w[t][7] * a3.y;
+    }
+    const size_t o = ((size_t)(b * Ho + oy) * Wo + ox) * C + g * 8;
+    if (add) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(add + o));
+      const float2 a0 = bf2_to_f2(v.x), a1 = bf2_to_f2(v.y), a2 = bf2_to_f2(v.z), a3 = bf2_to_f2(v.w);
+      acc[0] += a0.x; acc[1] += a0.y; acc[2] += a1.x; acc[3] += a1.y;
+      acc[4] += a2.x; acc[5] += a2.y; acc[6] += a3.x; acc[7] += a3.y;
+    }
+    *reinterpret_cast<uint4*>(y + o) = make_uint4(f2_to_bf2(acc[0], acc[1]), f2_to_bf2(acc[2], acc[3]),
+                                                  f2_to_bf2(acc[4], acc[5]), f2_to_bf2(acc[6], acc[7]));
+  }
+}
+
 // [C,1,ks,ks] fp32 -> [ks*ks][C] fp32
 __global__ void dw_weight_relayout_kernel(const float* __restrict__ w, float* __restrict__ wt, int C, int kk) {
   const int total = C * kk;
@@ -252,7 +307,18 @@ extern "C" int cnb_dw_deconv_up(const void* x, const float* wt, const void* add,
                                 int C, int f, cnb_stream_t s) {
   CNB_CHECK_ARG(x && wt && y && B >= 1 && H >= 1 && W >= 1, "dw_deconv_up: bad argument");
   CNB_CHECK_ARG(C % 8 == 0 && f >= 1 && f % 2 == 0, "dw_deconv_up: C %% 8 == 0 and even upsampling factor required");
-  const long long total = (long long)B * H * f * W * f * (C / 8);
+  const int groups = C / 8;
+  if (256 % groups == 0 && f <= 8) {   // phase kernel: taps in registers (every geometry of the DLA-34 / ResNet nets)
+    const long long per_phase = (long long)B * (H + 1) * (W + 1) * groups;
+    long long gx = (per_phase + 255) / 256;
+    const long long cap = 148LL * 16 / (f * f) > 148 ? 148LL * 16 / (f * f) : 148;
+    if (gx > cap) gx = cap;
+    dw_deconv_phase_kernel<<<dim3((unsigned)gx, (unsigned)(f * f)), 256, 0, (cudaStream_t)s>>>(
+        (const __nv_bfloat16*)x, wt, (const __nv_bfloat16*)add, (__nv_bfloat16*)y, B, H, W, C, f);
+    CNB_LAUNCH_CHECK();
+    return CNB_OK;
+  }
+  const long long total = (long long)B * H * f * W * f * groups;
   dw_deconv_kernel<<<grid_for(total), 256, 0, (cudaStream_t)s>>>((const __nv_bfloat16*)x, wt,
                                                                  (const __nv_bfloat16*)add, (__nv_bfloat16*)y, B, H,
                                                                  W, C, f);
