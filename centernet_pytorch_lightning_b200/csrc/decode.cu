@@ -85,6 +85,7 @@ struct ScanArgs {
   const float* reg;
   float* out;        // [B,K,6]
   int fuse_ctdet;
+  int wflush;        // streaming scan: list fill level at which a warp flushes
   int debug;         // CNB_DECODE_DEBUG=1: per-CTA phase timestamps into g_dbg (tools/decode_timeline.py)
 };
 
@@ -332,6 +333,166 @@ __device__ __forceinline__ const float* plane_ptr(const ScanArgs& a, int g, int 
   const int b = P / ppi, p = P - b * ppi;
   *flat_base = (u32)(pg * HW);
   return p < a.C0 ? a.t0 + ((size_t)b * a.C0 + p) * HW : a.t1 + ((size_t)b * a.C1 + (p - a.C0)) * HW;
+}
+
+// Warp-collective: the largest sound lower bound of the group's K-th key that its survivor histogram supports
+// (0 when fewer than K survivors are counted yet).
+__device__ u64 warp_bound_from_hist(const int* oct, const int* hist, const int* fine, int K, u64 cur_thr) {
+  const int lane = threadIdx.x & 31;
+  // Largest threshold t with count(score >= t) >= K, resolved octave -> coarse bin -> fine sub-bin.  The
+  // three levels are read in ONE round trip, speculating that the crossing octave / bin are the ones of
+  // the bound we already hold; a level is re-read only when the crossing moved.
+  const u32 tb = key_hi(cur_thr);
+  const int cb_prev = cur_thr ? coarse_bin(tb) : -1;
+  const int o_prev = cb_prev >= 0 ? cb_prev >> 7 : 15;
+  int vo = lane < NOCT ? __ldcg(oct + (NOCT - 1 - lane)) : 0;           // lane 0 = top octave
+  auto load_coarse = [&](int o, int (&cv)[4]) {                          // lane 0 = the octave's top bins
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int cb = o * 128 + 127 - (lane * 4 + j);
+      cv[j] = cb < NCB ? __ldcg(hist + cb) : 0;
+    }
+  };
+  int cv[4];
+  load_coarse(o_prev, cv);
+  int fv = (fine && cb_prev >= 0 && lane < FSUB) ? __ldcg(fine + cb_prev * FSUB + (FSUB - 1 - lane)) : 0;
+  // octave level
+  int incl = vo;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  u32 ok = __ballot_sync(0xffffffffu, incl >= K);
+  u64 nt = 0ull;
+  if (ok) {
+    const int lo = __ffs(ok) - 1;                       // lane of the crossing octave
+    const int ostar = NOCT - 1 - lo;
+    int above = __shfl_sync(0xffffffffu, incl - vo, lo);   // survivors counted in the octaves above it
+    if (ostar != o_prev) load_coarse(ostar, cv);
+    // coarse level (descending bins: lane 0 holds the octave's 4 largest)
+    const int csum = cv[0] + cv[1] + cv[2] + cv[3];
+    incl = csum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    ok = __ballot_sync(0xffffffffu, above + incl >= K);
+    if (ok) {
+      const int lc = __ffs(ok) - 1;
+      int mycb = -1, myabove = 0;
+      if (lane == lc) {
+        int r = above + incl - csum;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (r + cv[j] >= K && mycb < 0) {
+            mycb = ostar * 128 + 127 - (lane * 4 + j);
+            myabove = r;
+          }
+          r += cv[j];
+        }
+      }
+      const int cbstar = __shfl_sync(0xffffffffu, mycb, lc);
+      above = __shfl_sync(0xffffffffu, myabove, lc);
+      int sub = 0;
+      if (fine) {
+        if (cbstar != cb_prev) fv = lane < FSUB ? __ldcg(fine + cbstar * FSUB + (FSUB - 1 - lane)) : 0;
+        incl = fv;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int up = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += up;
+        }
+        ok = __ballot_sync(0xffffffffu, lane < FSUB && above + incl >= K);
+        if (ok) sub = FSUB - 1 - (__ffs(ok) - 1);
+      }
+      nt = (u64)bin_edge_bits(cbstar, sub) << 32;
+    } else {
+      nt = (u64)bin_edge_bits(ostar * 128, 0) << 32;   // (stale coarse counts) the octave's lower edge
+    }
+  }
+  return nt;
+}
+
+// Exact, sorted top-K of a finished group: candidates >= the final bound are staged in shared memory, cut with a
+// radix select when there are many, ranked by counting; then the [K,6] rows (ctdet) or the sorted key list
+// (multi_pose) are written.  Block-collective (NT threads).  s_sel holds >= K keys.
+__device__ void merge_group(const ScanArgs& a, int g, u64* s_mlist, u64* s_list, u64* s_out, const Scratch& sc) {
+  const int tid = threadIdx.x;
+  const int HW = a.H * a.W;
+    __threadfence();
+    const int n_all = min(__ldcg(a.gcount + g), a.gcap);
+    const u64 floor = ldcg_u64(a.thr + g);
+    const u64* gl = a.lists + (size_t)g * a.gcap;
+    if (tid == 0) sc.misc[4] = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n_all; i0 += NT * 8) {   // 8 independent loads per thread in flight (the list sits in L2)
+      u64 kk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = i0 + j * NT + tid;
+        kk[j] = i < n_all ? ldcg_u64(gl + i) : 0ull;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (kk[j] != 0ull && kk[j] >= floor) {
+          const int slot = atomicAdd(&sc.misc[4], 1);
+          if (slot < MCAP) s_mlist[slot] = kk[j];
+        }
+      }
+    }
+    __syncthreads();
+    int m = sc.misc[4];
+    __syncthreads();
+    const u64* L = s_mlist;
+    if (m > MCAP) {   // more candidates than the staging area holds: exact K-th straight from global memory
+      const GlobalCands gc{gl, n_all, floor};
+      const u64 kth = block_kth_key(gc, a.K, sc);
+      if (tid == 0) sc.misc[4] = 0;
+      __syncthreads();
+      gc.for_each([&](u64 key) {
+        if (key >= kth) s_mlist[atomicAdd(&sc.misc[4], 1)] = key;
+      });
+      __syncthreads();
+      m = sc.misc[4];
+    } else if (m > RANK_DIRECT && m > a.K) {
+      const SmemCands smc{s_mlist, m};
+      const u64 kth = block_kth_key(smc, a.K, sc);
+      if (tid == 0) sc.misc[4] = 0;
+      __syncthreads();
+      smc.for_each([&](u64 key) {
+        if (key >= kth) s_list[atomicAdd(&sc.misc[4], 1)] = key;   // exactly K <= acap entries
+      });
+      __syncthreads();
+      m = sc.misc[4];
+      L = s_list;
+    }
+    for (int i = tid; i < m; i += NT) {   // exact rank by counting (keys distinct)
+      const u64 key = L[i];
+      int r = 0;
+      for (int j = 0; j < m; ++j) r += (L[j] > key);
+      if (r < a.K) s_out[r] = key;
+    }
+    __syncthreads();
+    int have = min(m, a.K);
+    if (a.fuse_ctdet) {
+      if (have < a.K) {
+        block_zero_fill(a.t0 + (size_t)g * a.C0 * HW, a.C0 * HW, a.H, a.W, have, a.K, s_out, sc.red);
+        __syncthreads();
+      }
+      ctdet_write_rows(a, g, s_out);
+    } else {
+      const int ppi = a.C0 + a.C1;
+      const int b = g / ppi, p = g - b * ppi;
+      if (p < a.C0 && have < a.K) {   // detection heat map: zero-filled like torch.topk
+        block_zero_fill(a.t0 + ((size_t)b * a.C0 + p) * HW, HW, a.H, a.W, have, a.K, s_out, sc.red);
+        __syncthreads();
+        have = a.K;
+      }
+      for (int i = tid; i < have; i += NT) a.topk[(size_t)g * a.K + i] = s_out[i];
+      if (tid == 0) a.have[g] = have;
+    }
 }
 
 // =================================================================================================
@@ -685,79 +846,7 @@ __global__ void __launch_bounds__(NT, 2) decode_scan_kernel(const ScanArgs a) {
       // No fence: the histogram is read right away, possibly without this CTA's own increments -- counts only
       // grow, so a stale read gives a weaker but still sound bound; the next flush catches up.
       if (warp == 0) {
-        // Largest threshold t with count(score >= t) >= K, resolved octave -> coarse bin -> fine sub-bin.  The
-        // three levels are read in ONE round trip, speculating that the crossing octave / bin are the ones of
-        // the bound we already hold; a level is re-read only when the crossing moved.
-        const u32 tb = key_hi(cur_thr);
-        const int cb_prev = cur_thr ? coarse_bin(tb) : -1;
-        const int o_prev = cb_prev >= 0 ? cb_prev >> 7 : 15;
-        int vo = lane < NOCT ? __ldcg(oct + (NOCT - 1 - lane)) : 0;           // lane 0 = top octave
-        auto load_coarse = [&](int o, int (&cv)[4]) {                          // lane 0 = the octave's top bins
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int cb = o * 128 + 127 - (lane * 4 + j);
-            cv[j] = cb < NCB ? __ldcg(hist + cb) : 0;
-          }
-        };
-        int cv[4];
-        load_coarse(o_prev, cv);
-        int fv = (fine && cb_prev >= 0 && lane < FSUB) ? __ldcg(fine + cb_prev * FSUB + (FSUB - 1 - lane)) : 0;
-        // octave level
-        int incl = vo;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int up = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += up;
-        }
-        u32 ok = __ballot_sync(0xffffffffu, incl >= a.K);
-        u64 nt = 0ull;
-        if (ok) {
-          const int lo = __ffs(ok) - 1;                       // lane of the crossing octave
-          const int ostar = NOCT - 1 - lo;
-          int above = __shfl_sync(0xffffffffu, incl - vo, lo);   // survivors counted in the octaves above it
-          if (ostar != o_prev) load_coarse(ostar, cv);
-          // coarse level (descending bins: lane 0 holds the octave's 4 largest)
-          const int csum = cv[0] + cv[1] + cv[2] + cv[3];
-          incl = csum;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const int up = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += up;
-          }
-          ok = __ballot_sync(0xffffffffu, above + incl >= a.K);
-          if (ok) {
-            const int lc = __ffs(ok) - 1;
-            int mycb = -1, myabove = 0;
-            if (lane == lc) {
-              int r = above + incl - csum;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                if (r + cv[j] >= a.K && mycb < 0) {
-                  mycb = ostar * 128 + 127 - (lane * 4 + j);
-                  myabove = r;
-                }
-                r += cv[j];
-              }
-            }
-            const int cbstar = __shfl_sync(0xffffffffu, mycb, lc);
-            above = __shfl_sync(0xffffffffu, myabove, lc);
-            int sub = 0;
-            if (fine) {
-              if (cbstar != cb_prev) fv = lane < FSUB ? __ldcg(fine + cbstar * FSUB + (FSUB - 1 - lane)) : 0;
-              incl = fv;
-#pragma unroll
-              for (int o = 1; o < 32; o <<= 1) {
-                const int up = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += up;
-              }
-              ok = __ballot_sync(0xffffffffu, lane < FSUB && above + incl >= a.K);
-              if (ok) sub = FSUB - 1 - (__ffs(ok) - 1);
-            }
-            nt = (u64)bin_edge_bits(cbstar, sub) << 32;
-          } else {
-            nt = (u64)bin_edge_bits(ostar * 128, 0) << 32;   // (stale coarse counts) the octave's lower edge
-          }
-        }
+        const u64 nt = warp_bound_from_hist(oct, hist, fine, a.K, cur_thr);
         if (lane == 0) {
           u64 t = cur_thr;
           if (nt > t) {
@@ -829,70 +918,7 @@ __global__ void __launch_bounds__(NT, 2) decode_scan_kernel(const ScanArgs a) {
       __syncthreads();
       done_in_group = 0;
       if (s_misc[3]) {
-        __threadfence();
-        const int n_all = min(__ldcg(a.gcount + g), a.gcap);
-        const u64 floor = ldcg_u64(a.thr + g);
-        const u64* gl = a.lists + (size_t)g * a.gcap;
-        if (tid == 0) s_misc[4] = 0;
-        __syncthreads();
-        for (int i = tid; i < n_all; i += NT) {
-          const u64 key = ldcg_u64(gl + i);
-          if (key >= floor) {
-            const int slot = atomicAdd(&s_misc[4], 1);
-            if (slot < MCAP) s_mlist[slot] = key;
-          }
-        }
-        __syncthreads();
-        int m = s_misc[4];
-        __syncthreads();
-        const u64* L = s_mlist;
-        if (m > MCAP) {   // more candidates than the staging area holds: exact K-th straight from global memory
-          const GlobalCands gc{gl, n_all, floor};
-          const u64 kth = block_kth_key(gc, a.K, sc);
-          if (tid == 0) s_misc[4] = 0;
-          __syncthreads();
-          gc.for_each([&](u64 key) {
-            if (key >= kth) s_mlist[atomicAdd(&s_misc[4], 1)] = key;
-          });
-          __syncthreads();
-          m = s_misc[4];
-        } else if (m > RANK_DIRECT && m > a.K) {
-          const SmemCands smc{s_mlist, m};
-          const u64 kth = block_kth_key(smc, a.K, sc);
-          if (tid == 0) s_misc[4] = 0;
-          __syncthreads();
-          smc.for_each([&](u64 key) {
-            if (key >= kth) s_list[atomicAdd(&s_misc[4], 1)] = key;   // exactly K <= acap entries
-          });
-          __syncthreads();
-          m = s_misc[4];
-          L = s_list;
-        }
-        for (int i = tid; i < m; i += NT) {   // exact rank by counting (keys distinct)
-          const u64 key = L[i];
-          int r = 0;
-          for (int j = 0; j < m; ++j) r += (L[j] > key);
-          if (r < a.K) s_out[r] = key;
-        }
-        __syncthreads();
-        int have = min(m, a.K);
-        if (a.fuse_ctdet) {
-          if (have < a.K) {
-            block_zero_fill(a.t0 + (size_t)g * a.C0 * HW, a.C0 * HW, a.H, a.W, have, a.K, s_out, s_red);
-            __syncthreads();
-          }
-          ctdet_write_rows(a, g, s_out);
-        } else {
-          const int ppi = a.C0 + a.C1;
-          const int b = g / ppi, p = g - b * ppi;
-          if (p < a.C0 && have < a.K) {   // detection heat map: zero-filled like torch.topk
-            block_zero_fill(a.t0 + ((size_t)b * a.C0 + p) * HW, HW, a.H, a.W, have, a.K, s_out, s_red);
-            __syncthreads();
-            have = a.K;
-          }
-          for (int i = tid; i < have; i += NT) a.topk[(size_t)g * a.K + i] = s_out[i];
-          if (tid == 0) a.have[g] = have;
-        }
+        merge_group(a, g, s_mlist, s_list, s_out, sc);
         __syncthreads();
       }
     }
@@ -905,6 +931,261 @@ __global__ void __launch_bounds__(NT, 2) decode_scan_kernel(const ScanArgs a) {
     advance(g, pg, band);
   }
   DBG_MARK(3);
+}
+
+// =================================================================================================
+// decode_stream_kernel: the same scan with autonomous warps -- no block barrier in the steady state.
+// =================================================================================================
+// The barrier-per-chunk structure above makes every chunk pay for its slowest warp (a warp that holds a hit runs
+// a long single-lane path while 7 warps wait; tools/decode_timeline.py).  Here one producer warp keeps the tile ring
+// full (TMA bulk copies, empty/full mbarriers) and each of the 8 consumer warps scans ITS rows of every chunk on
+// its own: private survivor list, private copy of the group's bound, its own flushes (histogram increments, one
+// speculative round trip for the new bound, append).  While one warp waits on L2 the others keep streaming.  The
+// exact top-K of a group is taken afterwards by decode_merge_kernel (one CTA per group).  Used for W % 4 == 0 and
+// K <= STREAM_MAX_K; everything else stays on decode_scan_kernel.
+constexpr int SW = 8;                  // consumer warps
+constexpr int SNT = (SW + 1) * 32;     // + the producer warp
+constexpr int WLC = 544;               // keys a warp can carry: every element of its share of a chunk (<= 512) + what it carried
+constexpr int WFLUSH = 12;             // ... and the fill level at which it flushes (small: the bound of a group is
+                                       // only as good as what its warps have published)
+constexpr int STREAM_MAX_K = 512;
+
+__global__ void __launch_bounds__(SNT, 2) decode_stream_kernel(const ScanArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) u64 s_full[NST];
+  __shared__ __align__(8) u64 s_empty[NST];
+  __shared__ int s_wcnt[SW];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  u64* s_wlist = reinterpret_cast<u64*>(smem_raw + (size_t)NST * a.tile_bytes);   // [SW][WLC]
+  const int c_begin = (int)((long long)blockIdx.x * a.total_chunks / gridDim.x);
+  const int c_end = (int)((long long)(blockIdx.x + 1) * a.total_chunks / gridDim.x);
+
+  if (tid == 0) {
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], SW);
+    }
+    fence_mbar_init();
+    fence_proxy_async_smem();
+  }
+  if (tid < SW) s_wcnt[tid] = 0;
+  __syncthreads();
+  if (c_begin >= c_end) return;
+
+  int g = c_begin / a.cpg, pg, band;
+  {
+    const int rem = c_begin - g * a.cpg;
+    pg = rem / a.nbands;
+    band = rem - pg * a.nbands;
+  }
+  auto advance = [&](int& g_, int& pg_, int& band_) {
+    if (++band_ == a.nbands) {
+      band_ = 0;
+      if (++pg_ == a.PG) {
+        pg_ = 0;
+        ++g_;
+      }
+    }
+  };
+
+  if (warp == SW) {
+    // =============================== producer ================================================================
+    if (lane == 0) {
+      for (int c = c_begin; c < c_end; ++c) {
+        const int k = c - c_begin, stage = k & (NST - 1);
+        if (k >= NST) mbar_wait(&s_empty[stage], (u32)((k / NST) - 1) & 1u);
+        u32 fb;
+        const float* plane = plane_ptr(a, g, pg, &fb);
+        const int r0 = band * a.R, r1 = min(r0 + a.R, a.H);
+        const int g0 = max(r0 - 1, 0), g1 = min(r1 + 1, a.H);
+        const u32 bytes = (u32)((g1 - g0) * a.W * sizeof(float));
+        float* tile = reinterpret_cast<float*>(smem_raw + (size_t)stage * a.tile_bytes);
+        mbar_expect_tx(&s_full[stage], bytes);
+        bulk_g2s(tile + (size_t)(g0 - (r0 - 1)) * a.W, plane + (size_t)g0 * a.W, bytes, &s_full[stage]);
+        advance(g, pg, band);
+      }
+    }
+    return;
+  }
+
+  // ================================= consumers ================================================================
+  int* wcnt = &s_wcnt[warp];
+  u64* wl = s_wlist + warp * WLC;
+  const int W4 = a.W / 4;
+  const int cg = tid % W4;
+  const int seg = tid / W4;
+  int n = 0;               // entries in the warp's list (warp-uniform)
+  int cur_g = -1;
+  u64 cur_thr = 0ull;
+  u64 tq = 0ull;           // refresh of the group's bound in flight
+  int tq_g = -1;
+
+  // hand the warp's list to the group: histogram increments, new bound, append
+  auto warp_flush = [&](int fg) {
+    int* oct = a.goct + (size_t)fg * OCT_PAD;
+    int* hist = a.ghist + (size_t)fg * NCB_PAD;
+    int* fine = a.gfine ? a.gfine + (size_t)fg * NBF : nullptr;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+      const int i = i0 + lane;
+      int fb = -1;     // fine-bin index of this lane's entry (cb * FSUB + sub), -1: not counted
+      if (i < n) {
+        const u64 key = wl[i];
+        if (key >= cur_thr) {
+          const u32 bits = key_hi(key);
+          const int cb = coarse_bin(bits);
+          if (cb >= 0) fb = cb * FSUB + (int)((bits >> 12) & (FSUB - 1));
+        }
+      }
+      // The counters are hot: every warp of a group hits the same octave, and on plateaus the same bin.  Lanes
+      // that share a counter elect one of them to add the whole count (three match rounds: fine, coarse, octave).
+      u32 peers = __match_any_sync(0xffffffffu, fb);
+      if (fb >= 0 && fine && lane == __ffs(peers) - 1) atomicAdd(fine + fb, __popc(peers));
+      const int cbv = fb >= 0 ? fb / FSUB : -1;
+      peers = __match_any_sync(0xffffffffu, cbv);
+      if (cbv >= 0 && lane == __ffs(peers) - 1) atomicAdd(hist + cbv, __popc(peers));
+      const int o = cbv >= 0 ? cbv >> 7 : -1;
+      peers = __match_any_sync(0xffffffffu, o);
+      if (o >= 0 && lane == __ffs(peers) - 1) atomicAdd(oct + o, __popc(peers));
+    }
+    u64 nt = warp_bound_from_hist(oct, hist, fine, a.K, cur_thr);
+    if (n >= a.K) {
+      // The histogram bounds by score only.  A list that alone holds K survivors (plateaus of equal scores, or
+      // a first chunk) also yields an exact key -- score AND index -- below which nothing of this group matters.
+      u64 kand = ~0ull, kor = 0ull;     // bits on which all keys agree need no search step
+      for (int i = lane; i < n; i += 32) {
+        kand &= wl[i];
+        kor |= wl[i];
+      }
+      kand = ((u64)__reduce_and_sync(0xffffffffu, (u32)(kand >> 32)) << 32) | __reduce_and_sync(0xffffffffu, (u32)kand);
+      kor = ((u64)__reduce_or_sync(0xffffffffu, (u32)(kor >> 32)) << 32) | __reduce_or_sync(0xffffffffu, (u32)kor);
+      const u64 varying = kand ^ kor;
+      u64 t = kand & ~varying;
+      for (int bit = 63 - __clzll((long long)(varying | 1ull)); bit >= 0; --bit) {
+        if (!((varying >> bit) & 1ull)) continue;
+        const u64 cand = t | (1ull << bit);
+        int cge = 0;
+        for (int i = lane; i < n; i += 32) cge += (wl[i] >= cand);
+        if (warp_sum(cge) >= a.K) t = cand;
+      }
+      if (t > nt) nt = t;
+    }
+    if (nt > cur_thr) {
+      if (lane == 0) atomicMax(reinterpret_cast<unsigned long long*>(a.thr + fg), (unsigned long long)nt);
+      cur_thr = nt;
+    }
+    // append what the new bound lets through (compacted: count, reserve, write)
+    int kept = 0;
+    for (int i = lane; i < n; i += 32) kept += (wl[i] >= cur_thr);
+    int incl = kept;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int base = 0;
+    if (lane == 0 && total) base = atomicAdd(a.gcount + fg, total);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    int pos = base + incl - kept;
+    for (int i = lane; i < n; i += 32) {
+      const u64 key = wl[i];
+      if (key >= cur_thr) {
+        if (pos < a.gcap) a.lists[(size_t)fg * a.gcap + pos] = key;
+        ++pos;
+      }
+    }
+    n = 0;
+    if (lane == 0) *wcnt = 0;
+    __syncwarp();
+  };
+
+  for (int c = c_begin; c < c_end; ++c) {
+    const int k = c - c_begin, stage = k & (NST - 1);
+    if (g != cur_g) {   // entering a group: hand over what belongs to the previous one, fetch the new bound
+      if (n > 0) warp_flush(cur_g);
+      cur_g = g;
+      cur_thr = ldcg_u64(a.thr + g);
+      tq_g = -1;
+    }
+    // background refresh of the bound: issued every 4 chunks, consumed 2 chunks later
+    if ((k & 3) == 2 && tq_g == g && tq > cur_thr) cur_thr = tq;
+    if ((k & 3) == 0) {
+      tq = ldcg_u64(a.thr + g);
+      tq_g = g;
+    }
+    u32 flat_base;
+    plane_ptr(a, g, pg, &flat_base);
+    const int r0 = band * a.R, r1 = min(r0 + a.R, a.H);
+    const float* tile = reinterpret_cast<const float*>(smem_raw + (size_t)stage * a.tile_bytes);
+    const u64 thr = cur_thr;
+    const float ts = __uint_as_float(key_hi(thr));
+    const int rs = r0 + seg * a.rpt;
+    const int re = min(rs + a.rpt, r1);
+    const int n_before = n;
+
+    mbar_wait(&s_full[stage], (u32)(k / NST) & 1u);
+
+    // one look at the thread's rows: largest value against the bound, one vote per warp
+    float mt = 0.f;
+    for (int row = rs; row < re; ++row) {
+      const float4 q = *reinterpret_cast<const float4*>(tile + (size_t)(row - (r0 - 1)) * a.W + cg * 4);
+      mt = fmaxf(mt, fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)));
+    }
+    if (__any_sync(0xffffffffu, mt >= ts && mt > 0.f)) {
+      for (int row = rs; row < re; ++row) {
+        const float4 q = *reinterpret_cast<const float4*>(tile + (size_t)(row - (r0 - 1)) * a.W + cg * 4);
+        const float v[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float x = v[i];
+          if (!(x >= ts && x > 0.f)) continue;
+          const int col = cg * 4 + i;
+          const u64 key = make_key(x, flat_base + (u32)(row * a.W + col));
+          if (key < thr) continue;
+          bool peak = true;   // 3x3 max-pool NMS (utils/decode.py:5-10): keep iff no neighbour is larger
+#pragma unroll
+          for (int dy = -1; dy <= 1; ++dy) {
+            const int gy = row + dy;
+            if (gy < 0 || gy >= a.H) continue;
+            const float* np = tile + (size_t)(gy - (r0 - 1)) * a.W;
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+              const int gx = col + dx;
+              if (gx < 0 || gx >= a.W) continue;
+              if (np[gx] > x) peak = false;
+            }
+          }
+          if (peak) {
+            const int slot = atomicAdd(wcnt, 1);
+            if (slot < WLC) wl[slot] = key;
+          }
+        }
+      }
+      __syncwarp();
+      n = *reinterpret_cast<volatile int*>(wcnt);
+      if (n > WLC) n = WLC;   // cannot happen: a warp owns at most 512 elements of a chunk (host-side plan)
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s_empty[stage]);   // this warp is done with the tile
+    // flush when the list fills up, and right after a chunk scanned without any bound (the group needs one)
+    if (n >= a.wflush || (n > 0 && thr == 0ull)) warp_flush(g);
+    advance(g, pg, band);
+  }
+  if (n > 0) warp_flush(cur_g);
+}
+
+// one CTA per group: the exact, sorted top-K of the candidates the streaming scan appended
+__global__ void __launch_bounds__(NT) decode_merge_kernel(const ScanArgs a) {
+  __shared__ __align__(8) u64 s_mlist[MCAP];
+  __shared__ __align__(8) u64 s_sel[MAX_K];
+  __shared__ __align__(8) u64 s_out[MAX_K];
+  __shared__ __align__(8) u64 s_keyred[2 * NW];
+  __shared__ u32 s_hist[256];
+  __shared__ int s_red[NW];
+  __shared__ int s_misc[8];
+  const Scratch sc{s_hist, s_red, s_misc, s_keyred};
+  merge_group(a, blockIdx.x, s_mlist, s_sel, s_out, sc);
 }
 
 // =================================================================================================
@@ -1071,7 +1352,8 @@ static bool fine_for(int PG) { return PG >= 8; }
 
 static WsLayout ws_layout(int G, int PG, int K, const ScanGeom& g, bool want_topk) {
   WsLayout w;
-  w.gcap = PG * g.nbands * g.acap;
+  // a warp flush appends at most K keys (an exact bound is taken whenever its list holds K or more)
+  w.gcap = PG * g.nbands * (SW * K > g.acap ? SW * K : g.acap);
   w.thr_off = 0;
   w.gcount_off = align_up((size_t)G * sizeof(u64), 256);
   w.gdone_off = w.gcount_off + align_up((size_t)G * sizeof(int), 256);
@@ -1096,6 +1378,30 @@ static int num_sms() {
     if (n < 1) n = 1;
   }
   return n;
+}
+
+// the warp-autonomous scan + the per-group merge (W % 4 == 0, K <= STREAM_MAX_K; CNB_DECODE_IMPL=v2 disables it)
+static bool stream_ok(const ScanGeom& g, int K) {
+  static const bool off = [] { const char* e = getenv("CNB_DECODE_IMPL"); return e && e[0] == 'v' && e[1] == '2'; }();
+  return !off && g.vec == 4 && K <= STREAM_MAX_K && g.rpt * 4 <= 16;   // a warp owns <= 512 elements of a chunk
+}
+
+static cudaError_t launch_stream(const ScanArgs& a, cudaStream_t st) {
+  static bool configured = false;
+  const size_t smem = (size_t)NST * a.tile_bytes + (size_t)SW * WLC * sizeof(u64);
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(decode_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  int grid = env_int("CNB_DECODE_CTAS", 2 * num_sms());
+  if (grid > a.total_chunks) grid = a.total_chunks;
+  if (grid < 1) grid = 1;
+  decode_stream_kernel<<<grid, SNT, smem, st>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  decode_merge_kernel<<<a.G, NT, 0, st>>>(a);
+  return cudaGetLastError();
 }
 
 template <int VEC>
@@ -1185,8 +1491,15 @@ extern "C" int cnb_ctdet_decode(const float* heat, const float* wh, const float*
   a.wh = wh; a.reg = reg; a.out = out;
   a.fuse_ctdet = 1;
   a.debug = debug_on();
+  a.wflush = env_int("CNB_DECODE_WFLUSH", WFLUSH);
   CNB_CUDA(cudaMemsetAsync(ws, 0, w.zero_bytes, st));
-  cudaError_t e = g.vec == 4 ? launch_scan<4>(a, g.smem, st) : launch_scan<1>(a, g.smem, st);
+  cudaError_t e;
+  if (stream_ok(g, K)) {
+    e = launch_stream(a, st);
+    count_launch();
+  } else {
+    e = g.vec == 4 ? launch_scan<4>(a, g.smem, st) : launch_scan<1>(a, g.smem, st);
+  }
   if (e != cudaSuccess) {
     set_error("ctdet_decode launch failed: %s", cudaGetErrorString(e));
     return CNB_ERR_CUDA;
@@ -1237,8 +1550,15 @@ extern "C" int cnb_multi_pose_decode(const float* heat, const float* wh, const f
   a.wh = nullptr; a.reg = nullptr; a.out = nullptr;
   a.fuse_ctdet = 0;
   a.debug = debug_on();
+  a.wflush = env_int("CNB_DECODE_WFLUSH", WFLUSH);
   CNB_CUDA(cudaMemsetAsync(ws, 0, w.zero_bytes, st));
-  cudaError_t e = g.vec == 4 ? launch_scan<4>(a, g.smem, st) : launch_scan<1>(a, g.smem, st);
+  cudaError_t e;
+  if (stream_ok(g, K)) {
+    e = launch_stream(a, st);
+    count_launch();
+  } else {
+    e = g.vec == 4 ? launch_scan<4>(a, g.smem, st) : launch_scan<1>(a, g.smem, st);
+  }
   if (e != cudaSuccess) {
     set_error("multi_pose_decode scan launch failed: %s", cudaGetErrorString(e));
     return CNB_ERR_CUDA;

@@ -17,6 +17,15 @@ if what == "decode":
     heat, wh, reg = (torch.from_numpy(a).to(dev) for a in (heat, wh, reg))
     for _ in range(4):
         ctdet_decode(heat, wh, reg)
+elif what == "decode_sat":
+    g = torch.Generator().manual_seed(3)
+    lg = torch.randn(32, 80, 16, 16, generator=g) * 30
+    lg = torch.kron(lg, torch.ones(8, 8)) + torch.randn(32, 80, 128, 128, generator=g)
+    heat = torch.sigmoid(lg).to(dev)
+    wh = (torch.rand(32, 2, 128, 128, generator=g) * 30).to(dev)
+    reg = torch.rand(32, 2, 128, 128, generator=g).to(dev)
+    for _ in range(4):
+        ctdet_decode(heat, wh, reg)
 elif what == "head1x1":
     mid = torch.randn(B, 128, 128, 768, device=dev).to(torch.bfloat16)
     w = ops.pack_conv_weights(torch.randn(80, 256, 1, 1, device=dev) * 0.05)
