@@ -171,7 +171,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
 
   if (tid == 0) {
     for (int i = 0; i < a.nslots; ++i) {
-      mbar_init(&s_full[i], a.npw);
+      mbar_init(&s_full[i], 1);         // the one producer warp that copied the row
       mbar_init(&s_empty[i], NMW);      // every MMA warp commits (its own chain of the unit must have retired)
     }
     for (int i = 0; i < MAX_ACC; ++i) {
@@ -207,42 +207,31 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
     const int items = a.s * a.nch * a.PW;
     const int nch_sh = a.nch == 1 ? 0 : (a.nch == 2 ? 1 : (a.nch == 4 ? 2 : 3));
     const int per_phase = a.nch * a.PW;
-    // A row's copies are only *issued* here; its arrival on the full barrier happens `depth - 1` rows later, so
-    // that many rows of latency are in flight per thread.  Rows are issued in ring order, so the oldest pending
-    // row's slot simply advances by one.
-    int pend_slot = 0, npend = 0;
+    // Input rows are dealt out to the producer warps round-robin: ONE warp copies a whole row (lane-strided
+    // 16-byte cp.async, zero fill outside the image) and alone arrives on the slot's full barrier.  The per-row
+    // bookkeeping (slot wait, commit, wait_group, proxy fence, arrive) is a serial chain of ~100 instructions per
+    // warp; with every warp handling every row it capped the whole kernel at one row per ~500 clocks.  A row's
+    // arrival happens `wdepth - 1` of the warp's own rows later, so that many rows stay in flight per warp.
+    // the rows a warp still has to ISSUE before it arrives for an earlier one must fit in the ring's slack:
+    // npw * (wdepth - 1) <= depth, or the MMA warps would wait for an arrival that waits for a free slot
+    const int wdepth = min(8, 1 + a.depth / a.npw);
+    int pend[8];           // slots of this warp's rows whose copies are in flight (oldest first)
+    int npend = 0;
     auto complete_oldest = [&]() {   // the oldest row's copies have landed (caller waited on the group)
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_full[pend_slot]);
-      if (++pend_slot == a.nslots) pend_slot = 0;
+      if (lane == 0) mbar_arrive(&s_full[pend[0]]);
+#pragma unroll
+      for (int i = 1; i < 8; ++i) pend[i - 1] = pend[i];
       --npend;
     };
     int n = w.strip / a.nseg, seg = w.strip - n * a.nseg;
-    // A thread copies the same (phase, chunk, pixel) cells of every input row of a strip: their source and
-    // destination offsets are worked out once per strip, the per-row loop is one cp.async per cell.
-    const int npt = a.npw * 32;
-    int src_off[MAXI];     // element offset inside the input row, < 0: outside the image in x (zero fill)
-    u32 dst_off[MAXI];
-    int strip_done = -1;
+    int rc = 0;            // running row counter (identical in every producer warp): row rc belongs to warp rc % npw
     for (int u = u_begin; u < u_end; ++u) {
-      if (w.strip != strip_done) {
-        strip_done = w.strip;
-        const int q0 = seg * BM + a.q_off;            // q of plane pixel 0
-#pragma unroll
-        for (int i = 0; i < MAXI; ++i) {
-          const int it = tid + i * npt;
-          const int p = it >= per_phase ? 1 : 0;       // stride <= 2: at most two phases
-          const int r = it - p * per_phase;
-          const int c = r & (a.nch - 1);
-          const int j = r >> nch_sh;
-          const int xg = a.s * (q0 + j) + p;
-          src_off[i] = (it < items && xg >= 0 && xg < d.Wi) ? xg * d.x_cstride + c * 8 : -1;
-          dst_off[i] = (u32)(p * a.nch + c) * a.plane_bytes + (u32)j * 16u;
-        }
-      }
+      const int q0 = seg * BM + a.q_off;              // q of plane pixel 0
       const int iy0 = w.ug * a.R * a.s - d.pad;
-      for (int i = w.first_new(); i < w.cnt; ++i) {
+      for (int i = w.first_new(); i < w.cnt; ++i, ++rc) {
+        if (rc % a.npw != warp) continue;
         const int iy = iy0 + i;
         int slot;
         u32 par;
@@ -251,18 +240,20 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
         const u32 dst0 = ring_base + (u32)slot * a.slot_bytes;
         const bool row_ok = iy >= 0 && iy < d.Hi;
         const __nv_bfloat16* rowp = a.x + ((size_t)(n * d.Hi + (row_ok ? iy : 0)) * d.Wi) * d.x_cstride + d.x_coffset;
-#pragma unroll
-        for (int k = 0; k < MAXI; ++k) {
-          if (k < a.nk && tid + k * npt < items) {
-            const bool ok = row_ok && src_off[k] >= 0;
-            cp_async16(dst0 + dst_off[k], ok ? rowp + src_off[k] : a.x, ok ? 16u : 0u);
-          }
+        for (int it = lane; it < items; it += 32) {
+          const int p = it >= per_phase ? 1 : 0;       // stride <= 2: at most two phases
+          const int r = it - p * per_phase;
+          const int c = r & (a.nch - 1);
+          const int j = r >> nch_sh;
+          const int xg = a.s * (q0 + j) + p;
+          const bool ok = row_ok && xg >= 0 && xg < d.Wi;
+          cp_async16(dst0 + (u32)(p * a.nch + c) * a.plane_bytes + (u32)j * 16u,
+                     ok ? rowp + (size_t)xg * d.x_cstride + c * 8 : a.x, ok ? 16u : 0u);
         }
         cp_async_commit();
-        if (npend == 0) pend_slot = slot;
-        ++npend;
-        if (npend == a.depth) {
-          cp_async_wait_dyn(a.depth - 1);
+        pend[npend++] = slot;
+        if (npend == wdepth) {
+          cp_async_wait_dyn(wdepth - 1);
           complete_oldest();
         }
       }
@@ -417,13 +408,10 @@ static bool plan_rows(const cnb_conv_desc* d, RPlan* p) {
     while ((pw_alloc * 16) % 128 != 16) ++pw_alloc;  // fall into distinct banks for the producers' stores
   a.plane_bytes = (u32)pw_alloc * 16u;
   a.slot_bytes = (u32)(s * a.nch) * a.plane_bytes;
-  if (s * a.nch * a.PW > MAXI * NPT) return false;
   {
     const int items = s * a.nch * a.PW;
-    a.npw = (items + 63) / 64;             // about two cells per thread
-    if (a.npw > NPW) a.npw = NPW;
-    if (a.npw < 1) a.npw = 1;
-    a.nk = (items + a.npw * 32 - 1) / (a.npw * 32);
+    a.npw = NPW;                           // rows are dealt out round-robin to the producer warps
+    a.nk = (items + 31) / 32;
   }
   // ring: the KH rows of the current unit + the next unit's new rows + the rows in flight
   static const int env_depth = [] { const char* e = getenv("CNB_ROWS_DEPTH"); return e ? atoi(e) : 0; }();

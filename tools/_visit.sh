@@ -1,2 +1,2 @@
-bash tools_gpu_tests.sh tests/test_decode_gpu.py
-timeout 120 python tools/decode_bench.py
+bash tools_gpu_tests.sh tests/test_conv_gpu.py
+python tools/rows_bench.py
