@@ -286,10 +286,10 @@ def run_b200(args, rank, local_rank, world):
     dec_gbs = dec_bytes / (dec_ms * 1e-3) / 1e9
     try:   # DRAM traffic per launch from the committed ncu --set full capture of the same kernel and shape
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            dec_traffic = json.load(fh)["decode_scan_kernel<4> [32,80,128,128]"]["bytes"]
+            dec_traffic = json.load(fh)["decode [32,80,128,128]"]["bytes"]
     except Exception:
         dec_traffic = None
-    roofline_decode = {"bound": "hbm", "kernel": "decode_scan_kernel<4> (fused nms+topk+gather, persistent streaming scan)",
+    roofline_decode = {"bound": "hbm", "kernel": "decode_stream_kernel + decode_merge_kernel (fused nms+topk+gather: warp-autonomous streaming scan, per-image merge; timed together with the workspace memset)",
                        "achieved": dec_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": dec_gbs / pk["hbm"],
                        "traffic": dec_traffic, "ms": dec_ms, "bytes_per_launch": dec_bytes, "peak_source": pk["src"],
                        "l2": "flushed (256 MB write) before every timed launch"}
