@@ -22,7 +22,7 @@ class ConvDesc(Structure):
     _fields_ = [(n, c_int) for n in (
         "B", "Hi", "Wi", "Ci", "Co", "KH", "KW", "stride", "pad", "dil", "Ho", "Wo",
         "x_cstride", "x_coffset", "y_cstride", "y_coffset", "res_cstride", "res_coffset",
-        "act", "out_nchw_f32", "w_kw")]
+        "act", "out_nchw_f32", "w_kw", "pad_w1")]
 
 
 def _declare(lib):

@@ -34,8 +34,10 @@ constexpr int NPT = NPW * 32;
 constexpr int MAXI = 5;                      // 16-byte copies per producer thread and input row (<= 1280 per row)
 constexpr int NMW = 8;                       // MMA warps: one per output row of a unit (independent issue streams)
 constexpr int W_MMA = NPW;                   // warps 8..15
-constexpr int W_EPI0 = NPW + NMW;            // warps 16..19 (TMEM lane quarters 0,1,2,3)
-constexpr int NTHREADS = (W_EPI0 + 4) * 32;  // 640
+constexpr int W_EPI0 = NPW + NMW;            // warps 16..23: TMEM lane quarter = warp & 3, two warps per quarter
+constexpr int NEW = 8;                       // epilogue warps (the (row, 16-channel group) items of a unit alternate
+                                             // between the two warps of a quarter)
+constexpr int NTHREADS = (W_EPI0 + NEW) * 32;  // 768
 constexpr int MAX_SLOTS = 48;
 constexpr int MAX_ACC = 8;                   // TMEM accumulators in rotation (epilogue latency hiding)
 constexpr int MAX_STEPS = 64;                // K=16 steps per output tile
@@ -70,7 +72,8 @@ struct RArgs {
   int nbuf;          // unit buffers in TMEM (each R accumulators), power of two
   int nbuf_sh;
   int spk;           // K=16 steps per filter row
-  u32 aoff16[16];    // per step of a filter row: offset of its A window inside a row slot, in 16-byte units
+  u32 aoff16[16];
+  int debug;               // CNB_ROWS_DEBUG bit mask (timing experiments only): 1 no input copies, 2 no stores, 4 no MMAs    // per step of a filter row: offset of its A window inside a row slot, in 16-byte units
 };
 
 __device__ __forceinline__ void cp_async16(u32 dst, const void* src, u32 src_bytes) {
@@ -172,11 +175,11 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
   if (tid == 0) {
     for (int i = 0; i < a.nslots; ++i) {
       mbar_init(&s_full[i], 1);         // the one producer warp that copied the row
-      mbar_init(&s_empty[i], NMW);      // every MMA warp commits (its own chain of the unit must have retired)
+      mbar_init(&s_empty[i], 1);        // released by epilogue warp 0 once the unit's accumulators are complete
     }
     for (int i = 0; i < MAX_ACC; ++i) {
       mbar_init(&s_tfull[i], NMW);
-      mbar_init(&s_tempty[i], 4);
+      mbar_init(&s_tempty[i], NEW);
     }
     mbar_init(&s_bfull, 1);
     fence_mbar_init();
@@ -226,12 +229,14 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
       --npend;
     };
     int n = w.strip / a.nseg, seg = w.strip - n * a.nseg;
-    int rc = 0;            // running row counter (identical in every producer warp): row rc belongs to warp rc % npw
+    int turn = 0;          // running row counter mod npw (identical in every producer warp): whose row this is
     for (int u = u_begin; u < u_end; ++u) {
       const int q0 = seg * BM + a.q_off;              // q of plane pixel 0
       const int iy0 = w.ug * a.R * a.s - d.pad;
-      for (int i = w.first_new(); i < w.cnt; ++i, ++rc) {
-        if (rc % a.npw != warp) continue;
+      for (int i = w.first_new(); i < w.cnt; ++i) {
+        const bool mine = turn == warp;
+        if (++turn == a.npw) turn = 0;
+        if (!mine) continue;
         const int iy = iy0 + i;
         int slot;
         u32 par;
@@ -240,7 +245,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
         const u32 dst0 = ring_base + (u32)slot * a.slot_bytes;
         const bool row_ok = iy >= 0 && iy < d.Hi;
         const __nv_bfloat16* rowp = a.x + ((size_t)(n * d.Hi + (row_ok ? iy : 0)) * d.Wi) * d.x_cstride + d.x_coffset;
-        for (int it = lane; it < items; it += 32) {
+        for (int it = lane; it < ((a.debug & 1) ? 0 : items); it += 32) {
           const int p = it >= per_phase ? 1 : 0;       // stride <= 2: at most two phases
           const int r = it - p * per_phase;
           const int c = r & (a.nch - 1);
@@ -300,7 +305,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
         const u32 buf = t & (u32)(a.nbuf - 1), buf_ph = (t >> a.nbuf_sh) & 1u;
         mbar_wait_parked(&s_tempty[buf], buf_ph ^ 1u);
         tc_fence_after();
-        if (j < w.nr) {
+        if (j < w.nr && !(a.debug & 4)) {
           const u32 tmem_d = tmem_base + (buf * (u32)a.R + (u32)j) * a.acc_stride;
           int sl = w.sb + j * a.s;            // slot of this output row's first input row
           if (sl >= a.nslots) sl -= a.nslots;
@@ -320,13 +325,9 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
             if (rowoff >= wrap16) rowoff -= wrap16;
           }
         }
-        // release the input rows no later unit needs
-        const int nrel = w.released(u, u_end);
-        int slot = w.sb;
-        for (int i = 0; i < nrel; ++i) {
-          umma_commit(&s_empty[slot]);
-          if (++slot == a.nslots) slot = 0;
-        }
+        // one commit per MMA warp and unit: s_tfull[buf] completes when every row's chain has retired.  The input
+        // rows the unit frees are released by the epilogue (plain arrives) -- committing every freed slot from every
+        // MMA warp cost ~50 clocks per tcgen05.commit, 72 of them per unit
         umma_commit(&s_tfull[buf]);
         w.next();
       }
@@ -334,27 +335,49 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
   } else {
     // =============================== epilogue ================================================================
     const int q = warp & 3;
+    const int half = (warp - W_EPI0) >> 2;
     const int HoWo = d.Ho * d.Wo;
     int strip = u_begin / a.upr;
     int ug = u_begin - strip * a.upr;
     int n = strip / a.nseg, seg = strip - n * a.nseg;
     u32 t = 0;
+    const bool releaser = warp == W_EPI0 && lane == 0;
+    RowWalk rw;
+    if (releaser) rw.start(u_begin, d.Ho, a.s, d.KH, a.R, a.upr, a.nslots);
     for (int u = u_begin; u < u_end; ++u, ++t) {
       const u32 buf = t & (u32)(a.nbuf - 1), buf_ph = (t >> a.nbuf_sh) & 1u;
       const int nr = min(a.R, d.Ho - ug * a.R);
       mbar_wait_parked(&s_tfull[buf], buf_ph);
       tc_fence_after();
+      if (releaser) {   // every MMA of the unit has read its operands: free the input rows no later unit needs
+        const int nrel = rw.released(u, u_end);
+        int slot = rw.sb;
+        for (int i = 0; i < nrel; ++i) {
+          mbar_arrive(&s_empty[slot]);
+          if (++slot == a.nslots) slot = 0;
+        }
+        rw.next();
+      }
       const int ngroups = a.BN / 16;
-      for (int j = 0; j < nr; ++j) {
+      const int nitems = nr * ngroups;
+      int j = 0, g = half;                 // item = (row j, group g), row-major; this warp takes every second one
+      while (g >= ngroups) {
+        g -= ngroups;
+        ++j;
+      }
+      for (int it = half; it < nitems; it += 2) {
         const int opix = (ug * a.R + j) * d.Wo + seg * BM + 32 * q + lane;
         const int m = n * HoWo + opix;
         const u32 taddr = tmem_base + (buf * (u32)a.R + (u32)j) * a.acc_stride + ((u32)(32 * q) << 16);
-        for (int g = 0; g < ngroups; ++g) {
-          u32 v[16];
-          tmem_ld16_nowait(taddr + (u32)(g * 16), v);
-          tmem_ld_wait();
-          const int co0 = g * 16;
-          if (co0 < d.Co) epilogue_store(a, s_scale, s_shift, v, m, co0, co0, HoWo, n, opix);
+        u32 v[16];
+        tmem_ld16_nowait(taddr + (u32)(g * 16), v);
+        tmem_ld_wait();
+        const int co0 = g * 16;
+        if (co0 < d.Co && !(a.debug & 2)) epilogue_store(a, s_scale, s_shift, v, m, co0, co0, HoWo, n, opix);
+        g += 2;
+        while (g >= ngroups) {
+          g -= ngroups;
+          ++j;
         }
       }
       tc_fence_before();
@@ -388,7 +411,11 @@ static bool plan_rows(const cnb_conv_desc* d, RPlan* p) {
   if (off) return false;
   const int Ci = d->Ci, s = d->stride;
   if (!(Ci == 8 || Ci == 16 || Ci == 32 || Ci == 64)) return false;
-  if (!(s == 1 || s == 2) || d->dil != 1 || d->KH != d->KW || d->KH % 2 == 0 || d->pad != d->KH / 2) return false;
+  // filter KH x KW with vertical padding KH/2 and horizontal padding padx (= pad unless the descriptor says otherwise:
+  // the space-to-depth stem is 7 x 5 with pad 3 / 2)
+  const int padx = d->pad_w1 > 0 ? d->pad_w1 - 1 : d->pad;
+  if (!(s == 1 || s == 2) || d->dil != 1 || d->KH % 2 == 0 || d->pad != d->KH / 2) return false;
+  if (d->KW % 2 == 0 || padx != d->KW / 2) return false;
   if (d->KH < 3) return false;                       // 1x1: nothing to reuse, the im2col kernel is fine
   if (d->Wo % BM != 0 || d->Ho < 1) return false;
   if (d->Wi != d->Wo * s || d->Hi != d->Ho * s) return false;
@@ -400,8 +427,8 @@ static bool plan_rows(const cnb_conv_desc* d, RPlan* p) {
   a.nch = Ci / 8;
   a.KWp = KWp;
   // plane pixel range: q in [ox0 + floor(-pad/s), ox0 + 127 + floor((KWp-1-pad)/s)]
-  a.q_off = -((d->pad + s - 1) / s);
-  const int q_hi = (KWp - 1 - d->pad) / s;           // KWp-1-pad >= 0
+  a.q_off = -((padx + s - 1) / s);
+  const int q_hi = (KWp - 1 - padx) / s;             // KWp-1-pad >= 0
   a.PW = BM + q_hi - a.q_off;
   int pw_alloc = a.PW;
   if (a.nch > 2)                                     // plane stride == 16 B mod 128 B: the 8 chunk planes of a pixel
@@ -436,7 +463,7 @@ static bool plan_rows(const cnb_conv_desc* d, RPlan* p) {
       u32 aoff;
       if (ncp) {
         const int kw = r / ncp, cp = r - kw * ncp;
-        const int off = kw - d->pad;                     // input x = s*ox + kw - pad = s*(ox + dq) + phase
+        const int off = kw - padx;                       // input x = s*ox + kw - pad = s*(ox + dq) + phase
         const int dq = off >= 0 ? off / s : -((-off + s - 1) / s);
         const int ph = off - dq * s;
         aoff = (u32)(ph * a.nch + 2 * cp) * a.plane_bytes + (u32)(dq - a.q_off) * 16u;
@@ -447,6 +474,8 @@ static bool plan_rows(const cnb_conv_desc* d, RPlan* p) {
     }
   }
   static const int env_r = [] { const char* e = getenv("CNB_ROWS_R"); return e ? atoi(e) : 0; }();
+  static const int env_dbg = [] { const char* e = getenv("CNB_ROWS_DEBUG"); return e ? atoi(e) : 0; }();
+  a.debug = env_dbg;
   a.idesc = make_idesc_bf16(BM, a.BN);
   // rows per unit: as many interleaved accumulators as TMEM (2 unit buffers) and the ring (shared memory) allow
   for (a.R = env_r > 0 ? (env_r > NMW ? NMW : env_r) : NMW;; --a.R) {

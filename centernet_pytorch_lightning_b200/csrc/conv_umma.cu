@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(CT) conv_umma_kernel(const ConvArgs a) {
   const int HoWo = d.Ho * d.Wo;
   int r_n[4], r_iy0[4], r_ix0[4];
   bool r_ok[4];
+  const int padx = d.pad_w1 > 0 ? d.pad_w1 - 1 : d.pad;   // rectangular filters: separate horizontal padding
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int m = m0 + (tid >> 3) + 32 * i;
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(CT) conv_umma_kernel(const ConvArgs a) {
     const int oy = rem / d.Wo, ox = rem - oy * d.Wo;
     r_n[i] = n;
     r_iy0[i] = oy * d.stride - d.pad;
-    r_ix0[i] = ox * d.stride - d.pad;
+    r_ix0[i] = ox * d.stride - padx;
   }
 
   auto load_stage = [&](int kb) {
@@ -205,7 +206,7 @@ __global__ void __launch_bounds__(CT) conv_umma_kernel(const ConvArgs a) {
       float wgt[4][4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int oy = r_iy0[i] + d.pad, ox = r_ix0[i] + d.pad;   // stride 1
+        const int oy = r_iy0[i] + d.pad, ox = r_ix0[i] + padx;   // stride 1
         const float* omp = a.om + ((size_t)(r_n[i] * d.Hi + oy) * d.Wi + ox) * a.om_cstride;
         float dy = 0.f, dx = 0.f, mk = 0.f;
         if (r_ok[i] && kvalid) {
@@ -449,7 +450,7 @@ static int run_conv(const cnb_conv_desc* d, const void* x, const float* om, int 
     CNB_CHECK_ARG(d->w_kw == 0 || d->w_kw >= d->KW, "conv: w_kw=%d smaller than KW=%d", d->w_kw, d->KW);
     // wide thin layers (W_out % 128 == 0, Ci <= 64, KxK): row-window kernel, every input pixel fetched once
     if (!use_v1 && conv_rows_supported(d)) return conv_rows_run(d, x, wpk, scale, shift, res, y, st);
-    if (!use_v1 && (d->Ci >= 32) && (d->w_kw == 0 || d->w_kw == d->KW))
+    if (!use_v1 && (d->Ci >= 32) && (d->w_kw == 0 || d->w_kw == d->KW) && d->KH == d->KW && d->pad_w1 == 0)
       return conv_tma_run(d, x, wpk, scale, shift, res, y, st);
   }
   const Plan p = make_plan(*d);

@@ -45,6 +45,22 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* 
   }
 }
 
+// The same for Cp == 4 (C <= 4): 8 bytes per pixel.  Two neighbouring pixels of this tensor are one 8-channel
+// "super-pixel" of the space-to-depth stem (ops.pack_stem_s2d_weights).
+__global__ void nchw_to_nhwc4_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int C,
+                                     int HW) {
+  const long long total = (long long)B * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / HW);
+    const int pix = (int)(i - (long long)b * HW);
+    float v[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) v[c] = c < C ? __ldg(x + ((size_t)b * C + c) * HW + pix) : 0.f;
+    *reinterpret_cast<uint2*>(y + (size_t)i * 4) = make_uint2(f2_to_bf2(v[0], v[1]), f2_to_bf2(v[2], v[3]));
+  }
+}
+
 // ---- NHWC bf16 (channel slice) -> NCHW fp32 -------------------------------------------------------------
 __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int B, int C,
                                     int HW, int cstride, int coffset) {
@@ -266,7 +282,14 @@ using namespace cnb;
 extern "C" int cnb_nchw_f32_to_nhwc_bf16(const float* x, void* y, int B, int C, int H, int W, int C_pad,
                                          cnb_stream_t s) {
   CNB_CHECK_ARG(x && y && B >= 1 && C >= 1 && H >= 1 && W >= 1, "nchw_to_nhwc: bad argument");
-  CNB_CHECK_ARG(C_pad >= C && C_pad % 8 == 0, "nchw_to_nhwc: C_pad must be >= C and a multiple of 8");
+  CNB_CHECK_ARG(C_pad >= C && (C_pad % 8 == 0 || C_pad == 4),
+                "nchw_to_nhwc: C_pad must be >= C and a multiple of 8 (or 4)");
+  if (C_pad == 4) {
+    nchw_to_nhwc4_kernel<<<grid_for((long long)B * H * W), 256, 0, (cudaStream_t)s>>>(x, (__nv_bfloat16*)y, B, C,
+                                                                                      H * W);
+    CNB_LAUNCH_CHECK();
+    return CNB_OK;
+  }
   const long long total = (long long)B * H * W * (C_pad / 8);
   nchw_to_nhwc_kernel<<<grid_for(total), 256, 0, (cudaStream_t)s>>>(x, (__nv_bfloat16*)y, B, C, H * W, C_pad);
   CNB_LAUNCH_CHECK();

@@ -101,8 +101,20 @@ __device__ __forceinline__ void epilogue_store(const Args& a, const float* s_sca
                                                int opix) {
   const cnb_conv_desc& d = a.d;
   float f[16];
+  {  // scale/shift as 8 LDS.128 (cg0 % 16 == 0, arrays 16-byte aligned) instead of 32 scalar loads: the shared-memory
+     // pipe is also carrying the producers' cp.async traffic, and the scalar form made this line the epilogue's
+     // dominant stall
+    const float4* sc4 = reinterpret_cast<const float4*>(s_scale + cg0);
+    const float4* sh4 = reinterpret_cast<const float4*>(s_shift + cg0);
 #pragma unroll
-  for (int j = 0; j < 16; ++j) f[j] = fmaf(__uint_as_float(v[j]), s_scale[cg0 + j], s_shift[cg0 + j]);
+    for (int q = 0; q < 4; ++q) {
+      const float4 sc = sc4[q], sh = sh4[q];
+      f[4 * q + 0] = fmaf(__uint_as_float(v[4 * q + 0]), sc.x, sh.x);
+      f[4 * q + 1] = fmaf(__uint_as_float(v[4 * q + 1]), sc.y, sh.y);
+      f[4 * q + 2] = fmaf(__uint_as_float(v[4 * q + 2]), sc.z, sh.z);
+      f[4 * q + 3] = fmaf(__uint_as_float(v[4 * q + 3]), sc.w, sh.w);
+    }
+  }
   if (a.res) {
     const uint4* rp = reinterpret_cast<const uint4*>(a.res + (size_t)m * d.res_cstride + d.res_coffset + co0);
 #pragma unroll
@@ -125,16 +137,18 @@ __device__ __forceinline__ void epilogue_store(const Args& a, const float* s_sca
   }
   if (d.out_nchw_f32 == 0) {          // NHWC bf16 (optionally a channel slice of a concat buffer)
     __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(a.y) + (size_t)m * d.y_cstride + d.y_coffset + co0;
+    u32 o[8];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      if (co0 + 8 * h < d.Co) {
-        uint4 o;
-        o.x = pack_bf16x2(f[8 * h + 0], f[8 * h + 1]);
-        o.y = pack_bf16x2(f[8 * h + 2], f[8 * h + 3]);
-        o.z = pack_bf16x2(f[8 * h + 4], f[8 * h + 5]);
-        o.w = pack_bf16x2(f[8 * h + 6], f[8 * h + 7]);
-        *reinterpret_cast<uint4*>(yp + 8 * h) = o;
-      }
+    for (int j = 0; j < 8; ++j) o[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+    if (co0 + 8 < d.Co && ((d.y_cstride | d.y_coffset) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.y) & 31) == 0) {
+      // all 16 channels, 32-byte aligned: one 256-bit store = one whole sector per lane (two 128-bit stores put
+      // two half-sector writes on the crossbar)
+      asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(yp), "r"(o[0]), "r"(o[1]), "r"(o[2]),
+                   "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])
+                   : "memory");
+    } else {
+      *reinterpret_cast<uint4*>(yp) = make_uint4(o[0], o[1], o[2], o[3]);
+      if (co0 + 8 < d.Co) *reinterpret_cast<uint4*>(yp + 8) = make_uint4(o[4], o[5], o[6], o[7]);
     }
   } else if (d.out_nchw_f32 == 1) {   // NCHW fp32 (head maps for decode / losses): lanes = consecutive pixels
     float* yp = reinterpret_cast<float*>(a.y) + ((size_t)on * d.Co + co0) * HoWo + opix;
@@ -146,10 +160,19 @@ __device__ __forceinline__ void epilogue_store(const Args& a, const float* s_sca
     }
   } else {                            // NHWC fp32 (offset/mask maps feeding the DCN sampler)
     float* yp = reinterpret_cast<float*>(a.y) + (size_t)m * d.y_cstride + d.y_coffset + co0;
+    if (co0 + 16 <= d.y_cstride && (d.y_cstride & 7) == 0 && (reinterpret_cast<uintptr_t>(a.y) & 31) == 0) {
 #pragma unroll
-    for (int h = 0; h < 4; ++h)
-      if (co0 + 4 * h < d.y_cstride)
-        *reinterpret_cast<float4*>(yp + 4 * h) = make_float4(f[4 * h], f[4 * h + 1], f[4 * h + 2], f[4 * h + 3]);
+      for (int h = 0; h < 2; ++h)   // 256-bit stores: whole sectors
+        asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(yp + 8 * h), "f"(f[8 * h]),
+                     "f"(f[8 * h + 1]), "f"(f[8 * h + 2]), "f"(f[8 * h + 3]), "f"(f[8 * h + 4]), "f"(f[8 * h + 5]),
+                     "f"(f[8 * h + 6]), "f"(f[8 * h + 7])
+                     : "memory");
+    } else {
+#pragma unroll
+      for (int h = 0; h < 4; ++h)
+        if (co0 + 4 * h < d.y_cstride)
+          *reinterpret_cast<float4*>(yp + 4 * h) = make_float4(f[4 * h], f[4 * h + 1], f[4 * h + 2], f[4 * h + 3]);
+    }
   }
 }
 

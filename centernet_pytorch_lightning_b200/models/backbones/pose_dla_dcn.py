@@ -13,6 +13,8 @@ pre-allocated concat buffer.
 import math
 
 import numpy as np
+import os
+
 import torch
 from torch import nn
 
@@ -162,6 +164,15 @@ class _Compiled:
             self.cache[key] = (wpk, scale, shift, w_kw)
         return self.cache[key]
 
+    def stem_s2d(self, conv, bn):
+        """space-to-depth packing of the 7x7 stem (ops.pack_stem_s2d_weights): two output pixels per GEMM row"""
+        key = ("s2d", id(conv))
+        if key not in self.cache:
+            wpk, geom = ops.pack_stem_s2d_weights(conv.weight)
+            scale, shift = fold_bn(bn, conv.bias)
+            self.cache[key] = (wpk, geom, scale.repeat(2).contiguous(), shift.repeat(2).contiguous())
+        return self.cache[key]
+
     def deform(self, dc):
         key = id(dc)
         if key not in self.cache:
@@ -288,8 +299,14 @@ class DLASeg(nn.Module):              # pose_dla_dcn.py:532-570
         if self._cc is None:
             self._cc = _Compiled()
         cc, b = self._cc, self.base
-        h = View(ops.to_nhwc_bf16(x, c_pad=8), 8, 0)                       # 3 -> 8 channels for the 7x7 stem
-        h = _conv_bn_act(cc, h, b.base_layer[0], b.base_layer[1])
+        if x.shape[3] % 2 == 0 and os.environ.get("CNB_STEM_S2D", "1") != "0":
+            # 3 -> 4 channels; pixel pairs are the 8-channel super-pixels of the space-to-depth stem
+            wpk, geom, scale2, shift2 = cc.stem_s2d(b.base_layer[0], b.base_layer[1])
+            h = View(ops.stem_s2d(ops.to_nhwc_bf16(x, c_pad=4), wpk, geom, b.base_layer[0].out_channels, scale2,
+                                  shift2), b.base_layer[0].out_channels, 0)
+        else:
+            h = View(ops.to_nhwc_bf16(x, c_pad=8), 8, 0)                   # 3 -> 8 channels for the 7x7 stem
+            h = _conv_bn_act(cc, h, b.base_layer[0], b.base_layer[1])
         feats = []
         for lvl in (b.level0, b.level1):
             for i in range(0, len(lvl), 3):

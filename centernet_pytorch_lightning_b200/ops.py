@@ -123,16 +123,23 @@ def pack_conv_weights(w, kw_pad=None):
     return out
 
 
+def _pair(v):
+    return (v, v) if isinstance(v, int) else (int(v[0]), int(v[1]))
+
+
 def _out_geometry(H, W, k, stride, pad, dil=1):
-    return (H + 2 * pad - dil * (k - 1) - 1) // stride + 1, (W + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    (kh, kw), (ph, pw) = _pair(k), _pair(pad)
+    return (H + 2 * ph - dil * (kh - 1) - 1) // stride + 1, (W + 2 * pw - dil * (kw - 1) - 1) // stride + 1
 
 
 def _make_desc(x: View, Co, k, stride, pad, dil, Ho, Wo, out_mode, act, y_cstride, y_coffset, res: Optional[View],
                w_kw=0):
     d = ConvDesc()
     d.B, d.Hi, d.Wi, d.Ci = x.B, x.H, x.W, x.C
-    d.Co, d.KH, d.KW = Co, k, k
-    d.stride, d.pad, d.dil = stride, pad, dil
+    (kh, kw), (ph, pw) = _pair(k), _pair(pad)
+    d.Co, d.KH, d.KW = Co, kh, kw
+    d.stride, d.pad, d.dil = stride, ph, dil
+    d.pad_w1 = pw + 1 if pw != ph else 0
     d.Ho, d.Wo = Ho, Wo
     d.x_cstride, d.x_coffset = x.cstride, x.coffset
     d.y_cstride, d.y_coffset = y_cstride, y_coffset
@@ -155,9 +162,11 @@ def _alloc_out(x: View, Co, Ho, Wo, out_mode, out):
     return torch.empty((x.B, Ho, Wo, cs), dtype=torch.float32, device=dev)
 
 
-def conv2d(x, wpk, Co, k, stride, pad, scale, shift, res=None, act=0, out_mode=0, out=None, dil=1, w_kw=0):
+def conv2d(x, wpk, Co, k, stride, pad, scale, shift, res=None, act=0, out_mode=0, out=None, dil=1, w_kw=0,
+           flops=None):
     """y = act(conv(x, w) * scale + shift (+ res)).  out_mode 0: NHWC bf16 (returns the tensor, or writes the
-    `out` View), 1: NCHW fp32, 2: NHWC fp32 (channel stride rounded up to 16)."""
+    `out` View), 1: NCHW fp32, 2: NHWC fp32 (channel stride rounded up to 16).  `k` / `pad` may be (h, w) pairs
+    (rectangular filter: the space-to-depth stem)."""
     x = as_view(x)
     res = as_view(res) if res is not None else None
     Ho, Wo = _out_geometry(x.H, x.W, k, stride, pad, dil)
@@ -176,12 +185,54 @@ def conv2d(x, wpk, Co, k, stride, pad, scale, shift, res=None, act=0, out_mode=0
                                                 _lib.ptr(res.buf) if res is not None else None, y_ptr,
                                                 _stream(x.buf)), "cnb_conv2d_fprop")
         if prof:   # algorithmic FLOPs: 2*MACs with the true input channels (the 7x7 stem pads 3 -> 8)
-            ci = 3 if (k == 7 and x.C == 8) else x.C
-            prof.end(t0, "conv", 2.0 * x.B * Ho * Wo * Co * k * k * ci)
+            kh, kw = _pair(k)
+            ci = 3 if (kh == 7 and x.C == 8) else x.C
+            prof.end(t0, "conv", flops if flops is not None else 2.0 * x.B * Ho * Wo * Co * kh * kw * ci)
     if out_mode == 0:
         return o.buf if (out is None) else o
     return o
 
+
+
+def stem_s2d_filter(w):
+    """[Co,Ci<=4,K,K] -> ([2*Co, 8, K, KX] fp32, (K, KX, D)): the rectangular filter of the space-to-depth stem (see
+    pack_stem_s2d_weights); plain tensor arithmetic, runs on any device."""
+    Co, Ci, K, K2 = w.shape
+    assert K == K2 and K % 2 == 1 and Ci <= 4
+    p = K // 2
+    D = (p + 1) // 2
+    KX = 2 * D + 1
+    w = w.detach().float()
+    ws = torch.zeros((2, Co, 2, 4, K, KX), dtype=torch.float32, device=w.device)   # [par, co, h, ci, kh, ds+D]
+    for par in range(2):
+        for kw in range(K):
+            t = par + kw - p
+            ds, h = t // 2, t % 2          # floor division: t = 2*ds + h
+            ws[par, :, h, :Ci, :, ds + D] = w[:, :, :, kw]
+    return ws.reshape(2 * Co, 8, K, KX), (K, KX, D)
+
+
+def pack_stem_s2d_weights(w):
+    """Space-to-depth packing of a stride-1 KxK filter over <= 4 input channels (the DLA 7x7 stem,
+    pose_dla_dcn.py:281-285).  The input [B,H,W,4] bf16 is read as [B,H,W/2,8]: one 16-byte "super-pixel" holds
+    two neighbouring pixels.  Output pixel x = 2X + par reads input pixel 2X + par + (kw - K//2), i.e. super-pixel
+    X + ds, half h with 2*ds + h = par + kw - K//2.  The returned filter is [2*Co, 8, K, KX] (KX = 2*ceil(K//2 / 2) + 1
+    taps over super-pixels, output channel par*Co + co, input channel h*4 + ci) packed for `stem_s2d`: per filter row
+    3 tensor-core steps produce 256 output pixels x Co channels instead of 4 steps per 128 pixels."""
+    ws, (K, KX, D) = stem_s2d_filter(w)
+    kxp = KX + 1                           # even tap count: pairs of super-pixel taps form one K=16 step
+    return pack_conv_weights(ws, kw_pad=kxp), (K, KX, D, kxp)
+
+
+def stem_s2d(x4, wpk, geom, Co, scale2, shift2, act=1):
+    """x4 [B,H,W,4] bf16 (to_nhwc_bf16(x, c_pad=4), W even) -> [B,H,W,Co] bf16 = act(conv_KxK(x) * scale + shift).
+    `scale2` / `shift2` are the per-channel vectors repeated twice (one copy per output-pixel parity)."""
+    K, KX, D, kxp = geom
+    B, H, W, _ = x4.shape
+    xs = View(x4.view(B, H, W // 2, 8), 8, 0)
+    y = conv2d(xs, wpk, 2 * Co, (K, KX), 1, (K // 2, D), scale2, shift2, act=act, w_kw=kxp,
+               flops=2.0 * B * H * W * Co * K * K * 3)
+    return y.view(B, H, W, Co)
 
 def dcnv2(x, om, wpk, Co, scale, shift, act=0, out=None):
     """Modulated deformable 3x3 conv: x NHWC bf16, om [B,H,W,>=27] fp32 NHWC raw offset/mask channels."""

@@ -132,6 +132,9 @@ typedef struct cnb_conv_desc {
   int out_nchw_f32;       /* output format: 0 NHWC bf16, 1 NCHW fp32 (head maps), 2 NHWC fp32 (DCN offsets) */
   int w_kw;               /* filter width the weights were PACKED with (0 = KW).  The 8-channel stem packs its 7x7
                              filter as 7x8 (zero column) so that pairs of taps form one K=16 tensor-core step. */
+  int pad_w1;             /* horizontal padding + 1 when it differs from `pad` (0 = same as pad).  With KH != KW this
+                             describes the rectangular 7x5 filter of the space-to-depth stem (cnb_stem_s2d_pack_weights);
+                             rectangular filters run on the row-window kernel only (stride 1, Wo % 128 == 0). */
 } cnb_conv_desc;
 
 size_t cnb_conv_packed_weight_bytes(int Co, int Ci, int KH, int KW);

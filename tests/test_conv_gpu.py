@@ -78,6 +78,27 @@ def test_conv_matches_torch(cuda_dev, B, Ci, Co, H, W, k, stride, relu, residual
     _check(got, ref, 2e-3 if fp32_out else 2e-2)
 
 
+@pytest.mark.parametrize("B,H,W,k", [(2, 20, 256, 7), (1, 9, 512, 7), (2, 12, 64, 7), (1, 16, 256, 3),
+                                     (1, 8, 256, 5), (1, 7, 30, 7)])
+def test_stem_space_to_depth(cuda_dev, B, H, W, k):
+    """The 7x7 stem on pixel pairs (ops.pack_stem_s2d_weights / stem_s2d: 7x5 filter over [B,H,W/2,8], two output
+    pixels per GEMM row) against F.conv2d; W/2 % 128 == 0 runs on the row-window kernel, other widths on v1."""
+    g = torch.Generator(device="cpu").manual_seed(W + k)
+    Co = 16
+    x = _bf(torch.randn(B, 3, H, W, generator=g)).to(cuda_dev)
+    w = _bf(torch.randn(Co, 3, k, k, generator=g) / (3 * k * k) ** 0.5).to(cuda_dev)
+    scale = (0.5 + torch.rand(Co, generator=g)).to(cuda_dev)
+    shift = torch.randn(Co, generator=g).to(cuda_dev)
+    ref = (F.conv2d(x, w, padding=k // 2) * scale[None, :, None, None] + shift[None, :, None, None]).relu()
+    wpk, geom = ops.pack_stem_s2d_weights(w)
+    x4 = ops.to_nhwc_bf16(x, c_pad=4)
+    assert x4.shape == (B, H, W, 4)
+    assert torch.equal(x4[..., :3].float(), x.permute(0, 2, 3, 1)) and not x4[..., 3].any()
+    y = ops.stem_s2d(x4, wpk, geom, Co, scale.repeat(2), shift.repeat(2), act=1)
+    assert y.shape == (B, H, W, Co)
+    _check(y.permute(0, 3, 1, 2), ref, 2e-2)
+
+
 def test_conv_concat_slices(cuda_dev):
     """Reading / writing channel slices of wider NHWC buffers (Root's torch.cat without the copy)."""
     g = torch.Generator().manual_seed(7)

@@ -13,7 +13,28 @@ CASES = {  # name: (Ci, Co, H, k, stride)
 }
 dev = torch.device("cuda:0")
 B = 32
-for name in (sys.argv[1:] or list(CASES)):
+def s2d_case():
+    x = torch.randn(B, 3, 512, 512, device=dev)
+    wpk, geom = ops.pack_stem_s2d_weights(torch.randn(16, 3, 7, 7, device=dev) * 0.05)
+    sc, sh = torch.ones(32, device=dev), torch.zeros(32, device=dev)
+    x4 = ops.to_nhwc_bf16(x, c_pad=4)
+    for fn, label in ((lambda: ops.stem_s2d(x4, wpk, geom, 16, sc, sh), "stem_s2d"),
+                      (lambda: ops.to_nhwc_bf16(x, c_pad=4), "to_nhwc4"), (lambda: ops.to_nhwc_bf16(x, c_pad=8), "to_nhwc8")):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"{label:9s} {e0.elapsed_time(e1) / 5 * 1e3:8.1f} us")
+
+
+for name in (sys.argv[1:] or list(CASES) + ["s2d"]):
+    if name == "s2d":
+        s2d_case()
+        continue
     ci, co, hw, k, s = CASES[name]
     x = torch.randn(B, hw, hw, ci, device=dev).to(torch.bfloat16)
     w_kw = 8 if (ci == 8 and k == 7) else 0

@@ -32,6 +32,12 @@ elif what == "head1x1":
     bias = torch.zeros(80, device=dev)
     for _ in range(4):
         ops.conv2d(ops.View(mid, 256, 0), w, 80, 1, 1, 0, None, bias, act=2, out_mode=1)
+elif what == "s2d":
+    x4 = ops.to_nhwc_bf16(torch.randn(B, 3, 512, 512, device=dev), c_pad=4)
+    wpk, geom = ops.pack_stem_s2d_weights(torch.randn(16, 3, 7, 7, device=dev) * 0.05)
+    sc, sh = torch.ones(32, device=dev), torch.zeros(32, device=dev)
+    for _ in range(4):
+        ops.stem_s2d(x4, wpk, geom, 16, sc, sh)
 else:
     ci, co, hw, k = {"conv64": (64, 64, 128, 3), "dcn64": (64, 64, 128, 3), "head": (64, 768, 128, 3),
                      "conv256": (256, 256, 32, 3), "conv128": (128, 128, 64, 3), "conv16": (16, 16, 512, 3), "stem": (8, 16, 512, 7)}[what]
