@@ -111,6 +111,25 @@ __device__ __forceinline__ void mbar_wait_parked(void* bar, u32 parity) {
     if (t1 - t0 > 4000000000ull) __trap();   // 4 s: a lost arrival becomes a CUDA error, not a hang
   }
 }
+// Non-blocking poll (mbarrier.test_wait never suspends the thread): for single-thread roles whose wake-up latency
+// after a suspended try_wait would sit on the critical path.
+__device__ __forceinline__ bool mbar_test_wait(void* bar, u32 parity) {
+  u32 ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_spin(void* bar, u32 parity) {
+  u32 spins = 0;
+  while (!mbar_test_wait(bar, parity)) {
+    if (++spins > (1u << 28)) __trap();
+  }
+}
 // 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP); bytes % 16 == 0, 16B-aligned.
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u32 bytes, void* bar) {
   asm volatile(
@@ -118,6 +137,21 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
           smem_u32(dst_smem)),
       "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
+}
+
+// One elected lane of a converged warp.  The single-thread instructions of the tensor-core kernels (tcgen05.mma,
+// tcgen05.commit, TMA loads, expect_tx) are issued as `if (elect_one()) ...` from loops that ALL lanes of the role's
+// warp execute: operands computed in warp-uniform control flow live in uniform registers, which is what UTCHMMA /
+// UTMALDG take.  Inside an `if (lane == 0)` region the compiler cannot prove uniformity and wraps every such
+// instruction in a R2UR.BROADCAST waterfall loop (~150 clocks per tcgen05.mma, measured).
+__device__ __forceinline__ bool elect_one() {
+  u32 pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "@p mov.u32 %0, 1;\n\t}"
+      : "+r"(pred));
+  return pred != 0;
 }
 
 __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }

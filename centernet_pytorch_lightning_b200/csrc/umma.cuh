@@ -35,6 +35,14 @@ __device__ __forceinline__ void umma_commit(void* bar) {
                    smem_u32(bar))
                : "memory");
 }
+// the same, arriving on the barrier at this shared-memory offset in EVERY CTA of the cluster named by cta_mask
+__device__ __forceinline__ void umma_commit_mc(void* bar, unsigned short cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
 // 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread (lane = TMEM lane = tile row)
 __device__ __forceinline__ void tmem_ld16_nowait(u32 taddr, u32 (&v)[16]) {
   asm volatile(
@@ -69,6 +77,34 @@ __device__ __forceinline__ void tma_load_2d(u32 dst_smem, const void* tmap, int 
           "r"(dst_smem),
       "l"(reinterpret_cast<u64>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+// multicast: the tile lands at the same shared-memory offset of every CTA in cta_mask and completes tx bytes on
+// the barrier at the same offset there
+__device__ __forceinline__ void tma_load_2d_mc(u32 dst_smem, const void* tmap, int c0, int c1, void* bar,
+                                               unsigned short cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst_smem),
+      "l"(reinterpret_cast<u64>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ u32 cluster_ctarank() {
+  u32 r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ u32 cluster_id_x() {
+  u32 r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ u32 cluster_count_x() {
+  u32 r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {   // every thread of every CTA in the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // im2col mode over an NHWC tensor {C, W, H, N}: (c, w, h, n) = first channel and the base pixel of the first
 // row of the column tile (already shifted by the lower corner), (off_w, off_h) = filter tap offset.

@@ -36,6 +36,8 @@ CONV_CASES = [
     (2, 256, 128, 16, 16, 1, 1, True, False),    # 1x1 (Root)
     (1, 448, 128, 8, 8, 1, 1, True, True),       # Root with odd concat width
     (3, 64, 80, 20, 28, 3, 1, False, False),     # ragged M (tail tile) and Co=80
+    (1, 64, 64, 24, 24, 3, 1, True, True),       # 5 M tiles: the last cluster (2 or 4 CTAs) runs past the end
+    (1, 128, 256, 40, 40, 3, 1, True, False),    # 13 M tiles x N=256: multicast weight tile, several tiles per cluster
     (1, 8, 16, 40, 40, 7, 1, True, False),       # stem geometry: 7x7 on a channel-padded input
     (1, 32, 27, 24, 24, 3, 1, False, False),     # Co=27 (offset/mask conv) -> NHWC fp32
     # row-window kernel (conv_rows.cu): W_out % 128 == 0, Ci <= 64
