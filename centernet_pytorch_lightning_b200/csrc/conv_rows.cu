@@ -279,13 +279,14 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
     // two tcgen05.mma.
     const int ncp = a.nch >= 2 ? a.nch / 2 : 0;
     const int steps_per_kh = a.spk;
-    if (lane == 0) {
+    {   // all lanes walk the loop (warp-uniform operands -> uniform registers); one elected lane issues
       const int j = warp - W_MMA;
-      if (j == 0) {   // resident weights
+      if (j == 0 && elect_one()) {   // resident weights
         mbar_expect_tx(&s_bfull, a.b_bytes);
         for (int sl = 0; sl < a.nslab; ++sl)
           tma_load_2d(smem_base + (u32)sl * a.b_slab_bytes, &tmB, sl * 64, 0, &s_bfull);
       }
+      __syncwarp();
       mbar_wait_parked(&s_bfull, 0);
       RowWalk w;
       w.start(u_begin, d.Ho, a.s, d.KH, a.R, a.upr, a.nslots);
@@ -305,30 +306,33 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
         const u32 buf = t & (u32)(a.nbuf - 1), buf_ph = (t >> a.nbuf_sh) & 1u;
         mbar_wait_parked(&s_tempty[buf], buf_ph ^ 1u);
         tc_fence_after();
-        if (j < w.nr && !(a.debug & 4)) {
-          const u32 tmem_d = tmem_base + (buf * (u32)a.R + (u32)j) * a.acc_stride;
-          int sl = w.sb + j * a.s;            // slot of this output row's first input row
-          if (sl >= a.nslots) sl -= a.nslots;
-          u32 rowoff = (u32)sl * slot16;
-          const u32 wrap16 = (u32)a.nslots * slot16;
-          u32 accumulate = 0;
-          u32 ks = 0;
-          for (int kh = 0; kh < d.KH; ++kh) {
-            const u64 dbase = dslot0 + (u64)rowoff;
-            for (int r = 0; r < steps_per_kh; ++r, ++ks) {
-              const u64 da = dbase + (u64)a.aoff16[r];
-              const u64 db = db0 + (u64)((ks >> 2) * bslab16 + 2u * (ks & 3u));
-              umma_bf16(tmem_d, da, db, a.idesc, accumulate);
-              accumulate = 1;
+        if (elect_one()) {
+          if (j < w.nr && !(a.debug & 4)) {
+            const u32 tmem_d = tmem_base + (buf * (u32)a.R + (u32)j) * a.acc_stride;
+            int sl = w.sb + j * a.s;            // slot of this output row's first input row
+            if (sl >= a.nslots) sl -= a.nslots;
+            u32 rowoff = (u32)sl * slot16;
+            const u32 wrap16 = (u32)a.nslots * slot16;
+            u32 accumulate = 0;
+            u32 ks = 0;
+            for (int kh = 0; kh < d.KH; ++kh) {
+              const u64 dbase = dslot0 + (u64)rowoff;
+              for (int r = 0; r < steps_per_kh; ++r, ++ks) {
+                const u64 da = dbase + (u64)a.aoff16[r];
+                const u64 db = db0 + (u64)((ks >> 2) * bslab16 + 2u * (ks & 3u));
+                umma_bf16(tmem_d, da, db, a.idesc, accumulate);
+                accumulate = 1;
+              }
+              rowoff += slot16;                 // next filter row: one slot further
+              if (rowoff >= wrap16) rowoff -= wrap16;
             }
-            rowoff += slot16;                 // next filter row: one slot further
-            if (rowoff >= wrap16) rowoff -= wrap16;
           }
+          // one commit per MMA warp and unit: s_tfull[buf] completes when every row's chain has retired.  The input
+          // rows the unit frees are released by the epilogue (plain arrives) -- committing every freed slot from
+          // every MMA warp cost ~50 clocks per tcgen05.commit, 72 of them per unit
+          umma_commit(&s_tfull[buf]);
         }
-        // one commit per MMA warp and unit: s_tfull[buf] completes when every row's chain has retired.  The input
-        // rows the unit frees are released by the epilogue (plain arrives) -- committing every freed slot from every
-        // MMA warp cost ~50 clocks per tcgen05.commit, 72 of them per unit
-        umma_commit(&s_tfull[buf]);
+        __syncwarp();
         w.next();
       }
     }

@@ -152,7 +152,7 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
       for (int kb = 0; kb < a.nkb; ++kb) {
         mbar_wait_parked(&s_empty[s], ph ^ 1u);
         const u32 sa = smem_base + s * a.stage_bytes;
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {   // (elected, not `tid == 0`: uniform operands, no broadcast loop)
           mbar_expect_tx(&s_full[s], a.b_bytes);
           tma_load_2d(sa + A_BYTES, &tmB, tap * d.Ci + slab * 64, 0, &s_full[s]);
         }
@@ -295,8 +295,12 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
     }
   } else if (warp == W_MMA) {
     // =============================== MMA issuer ==============================================================
-    if (lane == 0) {
+    {   // all lanes walk the loop (warp-uniform operands -> uniform registers); one elected lane issues
       u32 s = 0, ph = 0, t = 0;
+      const u64 da0 = make_sdesc(smem_base, 16, 1024, 2);
+      const u64 db0 = make_sdesc(smem_base + A_BYTES, 16, 1024, 2);
+      const u32 stage16 = a.stage_bytes >> 4;
+      u32 soff16 = 0;
       for (int tile = tile_begin; tile < tile_end; ++tile, ++t) {
         const u32 acc = t & 1u, acc_ph = (t >> 1) & 1u;
         mbar_wait_parked(&s_tempty[acc], acc_ph ^ 1u);
@@ -306,21 +310,24 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
         for (int kb = 0; kb < a.nkb; ++kb) {
           mbar_wait_parked(&s_full[s], ph);
           tc_fence_after();
-          const u32 sa = smem_base + s * a.stage_bytes;
-          const u64 da = make_sdesc(sa, 16, 1024, 2);
-          const u64 db = make_sdesc(sa + A_BYTES, 16, 1024, 2);
+          if (elect_one()) {
+            const u64 da = da0 + (u64)soff16, db = db0 + (u64)soff16;
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {   // +32 bytes of K inside the swizzle atom
-            umma_bf16(tmem_d, da + (u64)(2 * kk), db + (u64)(2 * kk), a.idesc, accumulate);
-            accumulate = 1;
+            for (int kk = 0; kk < 4; ++kk)   // +32 bytes of K inside the swizzle atom
+              umma_bf16(tmem_d, da + (u64)(2 * kk), db + (u64)(2 * kk), a.idesc, kk == 0 ? accumulate : 1u);
+            umma_commit(&s_empty[s]);
           }
-          umma_commit(&s_empty[s]);
+          __syncwarp();
+          accumulate = 1;
+          soff16 += stage16;
           if (++s == (u32)a.stages) {
             s = 0;
             ph ^= 1u;
+            soff16 = 0;
           }
         }
-        umma_commit(&s_tfull[acc]);
+        if (elect_one()) umma_commit(&s_tfull[acc]);
+        __syncwarp();
       }
     }
   } else {
