@@ -259,6 +259,93 @@ dw_deconv_phase_kernel(const __nv_bfloat16* __restrict__ x, const float* __restr
   }
 }
 
+// f == 2 (every large up-sampling of the DLA-34 / ResNet nets): a thread owns (8-channel group, input column qx, output
+// row phase py) and walks down the rows.  Its 2 x 4 x 8 taps sit in registers, the two input rows of a cell roll
+// through registers, and each cell yields the two horizontally adjacent outputs: 2 input loads + 2 (add) loads +
+// 2 stores per 2 outputs (the phase kernel: 5 loads + 1 store per output, plus 64-bit index arithmetic per output;
+// block / grid indices replace all of that here).  Same tap order as above -> bit-identical results.
+__global__ void __launch_bounds__(128, 4)
+dw_deconv_f2_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wt,
+                    const __nv_bfloat16* __restrict__ add, __nv_bfloat16* __restrict__ y, int B, int H, int W, int C,
+                    int rows_per_block) {
+  constexpr int F = 2, KS = 4;
+  const int Ho = H * F, Wo = W * F, groups = C / 8;
+  const int t = blockIdx.x * 128 + threadIdx.x;
+  const int qx = t / groups, g = t - qx * groups;
+  if (qx > W) return;
+  const int b = blockIdx.z >> 1, py = blockIdx.z & 1;
+  float w[2][KS][8];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int kx = 0; kx < KS; ++kx) {
+      const float* wp = wt + (size_t)((py + a * F) * KS + kx) * C + g * 8;
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
+      w[a][kx][0] = w0.x; w[a][kx][1] = w0.y; w[a][kx][2] = w0.z; w[a][kx][3] = w0.w;
+      w[a][kx][4] = w1.x; w[a][kx][5] = w1.y; w[a][kx][6] = w1.z; w[a][kx][7] = w1.w;
+    }
+  // raw 16-byte loads (zero outside the image); converted to fp32 only where they are used, so that the loads of
+  // the NEXT row and of this row's `add` values are in flight while the current row is blended
+  auto load_q = [&](int iy, int ix) -> uint4 {
+    if (iy < 0 || iy >= H || ix < 0 || ix >= W) return make_uint4(0u, 0u, 0u, 0u);
+    return __ldg(reinterpret_cast<const uint4*>(x + ((size_t)(b * H + iy) * W + ix) * C + g * 8));
+  };
+  auto unpack8 = [](const uint4& q, float (&v)[8]) {
+    const float2 a0 = bf2_to_f2(q.x), a1 = bf2_to_f2(q.y), a2 = bf2_to_f2(q.z), a3 = bf2_to_f2(q.w);
+    v[0] = a0.x; v[1] = a0.y; v[2] = a1.x; v[3] = a1.y; v[4] = a2.x; v[5] = a2.y; v[6] = a3.x; v[7] = a3.y;
+  };
+  const int qy0 = blockIdx.y * rows_per_block;
+  const int qy1 = min(qy0 + rows_per_block, H + 1);
+  uint4 up0 = load_q(qy0 - 1, qx), up1 = load_q(qy0 - 1, qx - 1);      // input row qy-1 at columns qx / qx-1
+  uint4 cur0 = load_q(qy0, qx), cur1 = load_q(qy0, qx - 1);            // input row qy
+  for (int qy = qy0; qy < qy1; ++qy) {
+    const int oy = qy * F + py - 1;
+    const bool row_ok = oy >= 0 && oy < Ho;
+    const int ox0 = qx * F - 1;
+    const bool ok0 = row_ok && ox0 >= 0, ok1 = row_ok && ox0 + 1 < Wo;
+    const size_t o0 = ((size_t)(b * Ho + (row_ok ? oy : 0)) * Wo + (ox0 >= 0 ? ox0 : 0)) * C + g * 8;
+    const size_t o1 = ((size_t)(b * Ho + (row_ok ? oy : 0)) * Wo + (ox0 + 1 < Wo ? ox0 + 1 : 0)) * C + g * 8;
+    uint4 ad0 = make_uint4(0u, 0u, 0u, 0u), ad1 = ad0;
+    if (add && ok0) ad0 = __ldg(reinterpret_cast<const uint4*>(add + o0));
+    if (add && ok1) ad1 = __ldg(reinterpret_cast<const uint4*>(add + o1));
+    const uint4 nxt0 = qy + 1 < qy1 ? load_q(qy + 1, qx) : make_uint4(0u, 0u, 0u, 0u);
+    const uint4 nxt1 = qy + 1 < qy1 ? load_q(qy + 1, qx - 1) : make_uint4(0u, 0u, 0u, 0u);
+    if (row_ok) {
+      float c0[8], c1[8], u0[8], u1[8];
+      unpack8(cur0, c0);
+      unpack8(cur1, c1);
+      unpack8(up0, u0);
+      unpack8(up1, u1);
+#pragma unroll
+      for (int px = 0; px < F; ++px) {
+        if (!(px ? ok1 : ok0)) continue;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {   // taps (ky, kx) = (py, px), (py, px+2), (py+2, px), (py+2, px+2)
+          acc[j] = w[0][px][j] * c0[j];
+          acc[j] += w[0][px + F][j] * c1[j];
+          acc[j] += w[1][px][j] * u0[j];
+          acc[j] += w[1][px + F][j] * u1[j];
+        }
+        if (add) {
+          float av[8];
+          unpack8(px ? ad1 : ad0, av);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += av[j];
+        }
+        *reinterpret_cast<uint4*>(y + (px ? o1 : o0)) =
+            make_uint4(f2_to_bf2(acc[0], acc[1]), f2_to_bf2(acc[2], acc[3]), f2_to_bf2(acc[4], acc[5]),
+                       f2_to_bf2(acc[6], acc[7]));
+      }
+    }
+    up0 = cur0;
+    up1 = cur1;
+    cur0 = nxt0;
+    cur1 = nxt1;
+  }
+}
+
 // [C,1,ks,ks] fp32 -> [ks*ks][C] fp32
 __global__ void dw_weight_relayout_kernel(const float* __restrict__ w, float* __restrict__ wt, int C, int kk) {
   const int total = C * kk;
@@ -331,6 +418,16 @@ extern "C" int cnb_dw_deconv_up(const void* x, const float* wt, const void* add,
   CNB_CHECK_ARG(x && wt && y && B >= 1 && H >= 1 && W >= 1, "dw_deconv_up: bad argument");
   CNB_CHECK_ARG(C % 8 == 0 && f >= 1 && f % 2 == 0, "dw_deconv_up: C %% 8 == 0 and even upsampling factor required");
   const int groups = C / 8;
+  static const bool no_f2 = [] { const char* e = getenv("CNB_DW_DECONV_F2"); return e && e[0] == '0'; }();
+  if (f == 2 && !no_f2 && B <= 32767 && H >= 64) {   // measured: 71 vs 78 us at 64x64 -> 128x128, no gain on small maps
+    const int rows_per_block = 8;
+    dim3 grid((unsigned)(((long long)(W + 1) * groups + 127) / 128), (unsigned)((H + 1 + rows_per_block - 1) / rows_per_block),
+              (unsigned)(B * 2));
+    dw_deconv_f2_kernel<<<grid, 128, 0, (cudaStream_t)s>>>((const __nv_bfloat16*)x, wt, (const __nv_bfloat16*)add,
+                                                            (__nv_bfloat16*)y, B, H, W, C, rows_per_block);
+    CNB_LAUNCH_CHECK();
+    return CNB_OK;
+  }
   if (256 % groups == 0 && f <= 8) {   // phase kernel: taps in registers (every geometry of the DLA-34 / ResNet nets)
     const long long per_phase = (long long)B * (H + 1) * (W + 1) * groups;
     long long gx = (per_phase + 255) / 256;

@@ -32,6 +32,12 @@ elif what == "head1x1":
     bias = torch.zeros(80, device=dev)
     for _ in range(4):
         ops.conv2d(ops.View(mid, 256, 0), w, 80, 1, 1, 0, None, bias, act=2, out_mode=1)
+elif what == "up":
+    x = torch.randn(B, 64, 64, 64, device=dev).to(torch.bfloat16)
+    add = torch.randn(B, 128, 128, 64, device=dev).to(torch.bfloat16)
+    wt = ops.relayout_dw_weights(torch.randn(64, 1, 4, 4, device=dev), 2)
+    for _ in range(4):
+        ops.dw_deconv_up(x, wt, 2, add=add)
 elif what == "s2d":
     x4 = ops.to_nhwc_bf16(torch.randn(B, 3, 512, 512, device=dev), c_pad=4)
     wpk, geom = ops.pack_stem_s2d_weights(torch.randn(16, 3, 7, 7, device=dev) * 0.05)
