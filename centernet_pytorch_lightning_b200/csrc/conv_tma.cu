@@ -380,8 +380,9 @@ int conv_tma_run(const cnb_conv_desc* d, const void* x, const void* wpk, const f
     for (int km = env_km > 0 ? env_km : 4; km >= 1; --km) {
       const size_t sb = (size_t)km * g1 * (a.a_slab_bytes + a.b_slab_bytes);
       const int nst = (a.nslabs + km * g1 - 1) / (km * g1);
-      // three stages in flight, or two when the K loop is long enough to amortise the exposed load latency
-      if (km == 1 || sb * 3 <= budget || (sb * 2 <= budget && nst >= 6)) {
+      // at least three stages: with two, the ~1600-clock load latency of a refilled stage is exposed behind a
+      // single stage's worth of MMAs (measured with CNB_TMA_TRACE)
+      if (km == 1 || (sb * 3 <= budget && nst >= 2)) {
         a.g = km * g1;
         break;
       }

@@ -14,9 +14,10 @@ cat gpurun_out/configs_$tag.txt | tail -5
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv \
    --log-file gpurun_out/launches_$tag.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/ncu_bench_$tag.log 2>&1
 echo "ncu launches exit $?"
-for k in "decode:decode_:decode" "dcn64:dcn_ws:dcn64" "conv16:conv_rows:rows16" "conv64:conv_rows:rows64" "conv256:conv_tma:tma256" "head:conv_tma:head3x3"; do
+for k in "decode:decode_:decode" "dcn64:dcn_ws:dcn64" "conv16:conv_rows:rows16" "s2d:conv_rows:stem_s2d" "conv256:conv_tma:tma256" "head:conv_tma:head3x3"; do
   what=${k%%:*}; rest=${k#*:}; pat=${rest%%:*}; name=${rest#*:}
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$pat -s 2 -c 1 \
+  cnt=1; [ "$what" = decode ] && cnt=2     # decode = stream kernel + merge kernel
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$pat -s 2 -c $cnt \
      -o gpurun_out/prof_${name}_$tag -f python tools/run_one.py $what > gpurun_out/ncu_${name}_$tag.log 2>&1
   echo "ncu $name exit $?"
 done
