@@ -55,6 +55,7 @@ struct DArgs {
   int nkb;         // 9 * Ci/64
   int stages;
   u32 b_bytes, stage_bytes, tmem_cols, acc_stride, idesc;
+  int debug;       // CNB_DCN_DEBUG (timing experiments): 1 no corner loads, 2 no blend/store, 4 no MMAs, 8 no proxy fence, 16 no table math
 };
 
 // packed fp32x2 helpers (Blackwell FFMA2): a 64-bit register holds (low, high) floats
@@ -176,13 +177,18 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
             const u32 o00 = b & 0x3FFFFFFFu;                       // element offset of the clamped (y0, x0) pixel
             const u32 o01 = o00 + (((b >> 30) & 1u) ? cs : 0u);
             const u32 ddy = (b >> 31) ? row_step : 0u;
+            if (a.debug & 1) {
+              q[i][0] = q[i][1] = q[i][2] = q[i][3] = make_uint4(o00, o01, ddy, b);
+            } else {
             q[i][0] = __ldg(reinterpret_cast<const uint4*>(xs + o00));
             q[i][1] = __ldg(reinterpret_cast<const uint4*>(xs + o01));
             q[i][2] = __ldg(reinterpret_cast<const uint4*>(xs + (o00 + ddy)));
             q[i][3] = __ldg(reinterpret_cast<const uint4*>(xs + (o01 + ddy)));
+            }
           }
 #pragma unroll
           for (int i = 0; i < ROWS_PT; ++i) {
+            if (a.debug & 2) continue;
             const int row = r0 + (NPROD / 8) * i;
             u32 o[4];
 #pragma unroll
@@ -213,7 +219,7 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
                          : "memory");
           }
         }
-        fence_proxy_async_smem();       // generic-proxy stores -> visible to the tensor core (async proxy)
+        if (!(a.debug & 8)) fence_proxy_async_smem();       // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_full[s]);
         if (++tap == 9) {
@@ -258,7 +264,9 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
         const int m = m0 + r;
         float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
         u32 b = 0;
-        if (m < a.M) {
+        if (a.debug & 16) {
+          w = make_float4(0.25f, 0.25f, 0.25f, 0.25f);
+        } else if (m < a.M) {
           const int n = m / HW;
           const int rem = m - n * HW;
           const int oy = rem / d.Wi, ox = rem - oy * d.Wi;
@@ -312,9 +320,11 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
           tc_fence_after();
           if (elect_one()) {
             const u64 da = da0 + (u64)soff16, db = db0 + (u64)soff16;
+            if (!(a.debug & 4)) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)   // +32 bytes of K inside the swizzle atom
-              umma_bf16(tmem_d, da + (u64)(2 * kk), db + (u64)(2 * kk), a.idesc, kk == 0 ? accumulate : 1u);
+              for (int kk = 0; kk < 4; ++kk)   // +32 bytes of K inside the swizzle atom
+                umma_bf16(tmem_d, da + (u64)(2 * kk), db + (u64)(2 * kk), a.idesc, kk == 0 ? accumulate : 1u);
+            }
             umma_commit(&s_empty[s]);
           }
           __syncwarp();
@@ -418,6 +428,8 @@ int dcn_ws_run(const cnb_conv_desc* d, const void* x, const float* om, int om_cs
       return CNB_ERR_CUDA;
     }
   }
+  static const int env_dbg = [] { const char* e = getenv("CNB_DCN_DEBUG"); return e ? atoi(e) : 0; }();
+  a.debug = env_dbg;
   static const bool blend_bf16 = [] { const char* e = getenv("CNB_DCN_BLEND"); return e && e[0] == 'b'; }();
   static bool configured = false;
   if (!configured) {

@@ -1,0 +1,30 @@
+"""Times single DCNv2 layers of the DLA-34 schedule (B=32): python tools/dcn_bench.py [case ...]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from centernet_pytorch_lightning_b200 import ops  # noqa: E402
+
+CASES = {"d64": (64, 64, 128), "d128_64": (128, 64, 64), "d128": (128, 128, 64), "d256": (256, 256, 32)}
+dev = torch.device("cuda:0")
+B = 32
+for name in (sys.argv[1:] or list(CASES)):
+    ci, co, hw = CASES[name]
+    x = torch.randn(B, hw, hw, ci, device=dev).to(torch.bfloat16)
+    w = ops.pack_conv_weights(torch.randn(co, ci, 3, 3, device=dev) * 0.05)
+    sc, sh = torch.ones(co, device=dev), torch.zeros(co, device=dev)
+    om = torch.randn(B, hw, hw, 32, device=dev) * 0.5
+    run = lambda: ops.dcnv2(x, om, w, co, sc, sh, act=1)
+    for _ in range(3):
+        run()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / 10 * 1e3
+    kblocks = (B * hw * hw / 128) * (ci * 9 / 64) / 148
+    print(f"{name:8s} {us:8.1f} us  {us * 1e-6 * 1.965e9 / kblocks:7.0f} clk per K block per SM")
