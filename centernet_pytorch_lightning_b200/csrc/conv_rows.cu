@@ -28,6 +28,14 @@
 namespace cnb {
 namespace {
 
+// CNB_ROWS_DEBUG stage-skipping experiments: compiled in only with -DCNB_ROWS_EXPERIMENTS (their predicates sit in
+// the role loops)
+#ifdef CNB_ROWS_EXPERIMENTS
+#define ROWS_DBG(a) ((a).debug)
+#else
+#define ROWS_DBG(a) 0
+#endif
+
 constexpr int BM = 128;
 constexpr int NPW = 8;                       // producer warps
 constexpr int NPT = NPW * 32;
@@ -245,7 +253,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
         const u32 dst0 = ring_base + (u32)slot * a.slot_bytes;
         const bool row_ok = iy >= 0 && iy < d.Hi;
         const __nv_bfloat16* rowp = a.x + ((size_t)(n * d.Hi + (row_ok ? iy : 0)) * d.Wi) * d.x_cstride + d.x_coffset;
-        for (int it = lane; it < ((a.debug & 1) ? 0 : items); it += 32) {
+        for (int it = lane; it < ((ROWS_DBG(a) & 1) ? 0 : items); it += 32) {
           const int p = it >= per_phase ? 1 : 0;       // stride <= 2: at most two phases
           const int r = it - p * per_phase;
           const int c = r & (a.nch - 1);
@@ -307,7 +315,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
         mbar_wait_parked(&s_tempty[buf], buf_ph ^ 1u);
         tc_fence_after();
         if (elect_one()) {
-          if (j < w.nr && !(a.debug & 4)) {
+          if (j < w.nr && !(ROWS_DBG(a) & 4)) {
             const u32 tmem_d = tmem_base + (buf * (u32)a.R + (u32)j) * a.acc_stride;
             int sl = w.sb + j * a.s;            // slot of this output row's first input row
             if (sl >= a.nslots) sl -= a.nslots;
@@ -377,7 +385,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
         tmem_ld16_nowait(taddr + (u32)(g * 16), v);
         tmem_ld_wait();
         const int co0 = g * 16;
-        if (co0 < d.Co && !(a.debug & 2)) epilogue_store(a, s_scale, s_shift, v, m, co0, co0, HoWo, n, opix);
+        if (co0 < d.Co && !(ROWS_DBG(a) & 2)) epilogue_store(a, s_scale, s_shift, v, m, co0, co0, HoWo, n, opix);
         g += 2;
         while (g >= ngroups) {
           g -= ngroups;

@@ -27,7 +27,7 @@ namespace cnb {
 namespace {
 
 constexpr int BM = 128;
-constexpr int NPROD_WARPS = 16;                      // sampler warps: 512 threads, 2 pixel rows x one 8-ch chunk each
+constexpr int NPROD_WARPS = 16;                      // sampler warps: 512 threads = 128 pixel rows x 4 pairs of 8-channel chunks
 constexpr int NPROD = NPROD_WARPS * 32;
 constexpr int NSETUP_WARPS = 4;
 constexpr int NSETUP = NSETUP_WARPS * 32;
@@ -35,7 +35,7 @@ constexpr int W_SETUP0 = NPROD_WARPS;                // warps 16..19
 constexpr int W_MMA = W_SETUP0 + NSETUP_WARPS;       // warp 20
 constexpr int W_EPI0 = W_MMA + 1;                    // warps 21..24 (TMEM lane quarters 1,2,3,0)
 constexpr int NTHREADS = (W_EPI0 + 4) * 32;          // 800
-constexpr int ROWS_PT = BM * 8 / NPROD;              // pixel rows per sampler thread and K block
+static_assert(NPROD == BM * 4, "one sampler thread per (pixel row, 16-channel chunk pair)");
 constexpr int MAX_STAGES = 6;
 constexpr int NTAB = BM * 9;                         // (pixel, tap) entries per tile
 constexpr int OM_CS = 32;                            // channel stride of the offset/mask map this kernel takes
@@ -55,6 +55,7 @@ struct DArgs {
   int nkb;         // 9 * Ci/64
   int stages;
   u32 b_bytes, stage_bytes, tmem_cols, acc_stride, idesc;
+  long long* trace;  // CNB_DCN_TRACE: clock stamps of CTA 0 (see dcn_ws_run)
   int debug;       // CNB_DCN_DEBUG (timing experiments): 1 no corner loads, 2 no blend/store, 4 no MMAs, 8 no proxy fence, 16 no table math
 };
 
@@ -83,6 +84,17 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
 // BLEND_BF16: the 4-corner blend runs as packed bf16x2 FMAs straight on the loaded pairs (weights rounded to
 // bf16, three more bf16 roundings than the fp32 blend) -- about half the sampler's instructions.  Off unless
 // CNB_DCN_BLEND=bf16; the default blends in fp32 and rounds once.
+// The timing experiments (CNB_DCN_DEBUG stage skipping, CNB_DCN_TRACE clock stamps) are compiled in only with
+// -DCNB_DCN_EXPERIMENTS: their predicates sit in the latency-bound role loops.
+#ifdef CNB_DCN_EXPERIMENTS
+#define DCN_DBG(a) ((a).debug)
+#define DCN_STAMP(slot, idx) \
+  do { if (a.trace && blockIdx.x == 0 && (idx) < 512) a.trace[(slot) * 512 + (idx)] = clock64(); } while (0)
+#else
+#define DCN_DBG(a) 0
+#define DCN_STAMP(slot, idx) do { } while (0)
+#endif
+
 template <bool BLEND_BF16>
 __global__ void __launch_bounds__(NTHREADS, 1)
 dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
@@ -139,89 +151,103 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
 
   if (warp < NPROD_WARPS) {
     // =============================== samplers ===============================================================
-    const int chunk = tid & 7;          // 16-byte channel chunk inside the 64-channel slab
-    const int r0 = tid >> 3;            // rows r0 + (NPROD/8)*i
+    // A thread owns ONE pixel row of the tile and a PAIR of 16-byte channel chunks (16 channels): the table entry
+    // and the corner addresses are worked out once per 32 bytes sampled, and each corner is one 256-bit load when the
+    // tensor allows it (32-byte aligned pixels), two 128-bit loads otherwise.
+    const int cp = tid & 3;             // chunk pair inside the 64-channel slab: chunks 2cp, 2cp+1
+    const int row = tid >> 2;           // 0..127
     const u32 cs = (u32)d.x_cstride;
     const u32 row_step = (u32)d.Wi * cs;
+    const bool wide_ld = ((d.x_cstride | d.x_coffset) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.x) & 31) == 0;
+    const u32 dst_lo = (u32)row * 128u + ((u32)((2 * cp) ^ (row & 7)) << 4);
+    const u32 dst_hi = (u32)row * 128u + ((u32)((2 * cp + 1) ^ (row & 7)) << 4);
     u32 s = 0, ph = 0, t = 0;
     for (int tile = tile_begin; tile < tile_end; ++tile, ++t) {
       const u32 tb = t & 1u;
       mbar_wait_parked(&s_tabfull[tb], (t >> 1) & 1u);
-      const float4* tw = s_tabw + tb * NTAB;
-      const u32* tbs = s_tabb + tb * NTAB;
+      const float4* tw = s_tabw + tb * NTAB + row * 9;
+      const u32* tbs = s_tabb + tb * NTAB + row * 9;
       int slab = 0, tap = 0;
       for (int kb = 0; kb < a.nkb; ++kb) {
         mbar_wait_parked(&s_empty[s], ph ^ 1u);
+        if (tid == 0) DCN_STAMP(0, (int)(t * a.nkb) + kb);
         const u32 sa = smem_base + s * a.stage_bytes;
-        if (warp == 0 && elect_one()) {   // (elected, not `tid == 0`: uniform operands, no broadcast loop)
+        if (warp == 0 && elect_one()) {   // (elected, not `tid == 0`: uniform operands, no broadcast loop; a separate
+                                          // warp for this was measured slower: 26 warps contend more than this costs)
           mbar_expect_tx(&s_full[s], a.b_bytes);
           tma_load_2d(sa + A_BYTES, &tmB, tap * d.Ci + slab * 64, 0, &s_full[s]);
         }
-        const __nv_bfloat16* xs = a.x + d.x_coffset + slab * 64 + chunk * 8;
+        const __nv_bfloat16* xs = a.x + d.x_coffset + slab * 64 + cp * 16;
         {
-          uint4 q[ROWS_PT][4];
-          float4 w[ROWS_PT];
-          u64 ww[ROWS_PT][4];
-          u32 wh[ROWS_PT][4];
+          u32 q[4][8];
+          const float4 w = tw[tap];
+          const u32 b = tbs[tap];
+          const u32 o00 = b & 0x3FFFFFFFu;                       // element offset of the clamped (y0, x0) pixel
+          const u32 o01 = o00 + (((b >> 30) & 1u) ? cs : 0u);
+          const u32 ddy = (b >> 31) ? row_step : 0u;
+          const u32 off[4] = {o00, o01, o00 + ddy, o01 + ddy};
+          if (DCN_DBG(a) & 1) {
 #pragma unroll
-          for (int i = 0; i < ROWS_PT; ++i) {
-            const int item = (r0 + (NPROD / 8) * i) * 9 + tap;
-            w[i] = tw[item];
-            if constexpr (BLEND_BF16) {
-              wh[i][0] = pack_bf16x2(w[i].x, w[i].x); wh[i][1] = pack_bf16x2(w[i].y, w[i].y);
-              wh[i][2] = pack_bf16x2(w[i].z, w[i].z); wh[i][3] = pack_bf16x2(w[i].w, w[i].w);
-            } else {
-              ww[i][0] = dup2(w[i].x); ww[i][1] = dup2(w[i].y); ww[i][2] = dup2(w[i].z); ww[i][3] = dup2(w[i].w);
-            }
-            const u32 b = tbs[item];
-            const u32 o00 = b & 0x3FFFFFFFu;                       // element offset of the clamped (y0, x0) pixel
-            const u32 o01 = o00 + (((b >> 30) & 1u) ? cs : 0u);
-            const u32 ddy = (b >> 31) ? row_step : 0u;
-            if (a.debug & 1) {
-              q[i][0] = q[i][1] = q[i][2] = q[i][3] = make_uint4(o00, o01, ddy, b);
-            } else {
-            q[i][0] = __ldg(reinterpret_cast<const uint4*>(xs + o00));
-            q[i][1] = __ldg(reinterpret_cast<const uint4*>(xs + o01));
-            q[i][2] = __ldg(reinterpret_cast<const uint4*>(xs + (o00 + ddy)));
-            q[i][3] = __ldg(reinterpret_cast<const uint4*>(xs + (o01 + ddy)));
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+              for (int e = 0; e < 8; ++e) q[c][e] = off[c] + e;
+          } else if (wide_ld) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                           : "=r"(q[c][0]), "=r"(q[c][1]), "=r"(q[c][2]), "=r"(q[c][3]), "=r"(q[c][4]), "=r"(q[c][5]),
+                             "=r"(q[c][6]), "=r"(q[c][7])
+                           : "l"(xs + off[c]));
+          } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint4 lo = __ldg(reinterpret_cast<const uint4*>(xs + off[c]));
+              const uint4 hi = __ldg(reinterpret_cast<const uint4*>(xs + off[c] + 8));
+              q[c][0] = lo.x; q[c][1] = lo.y; q[c][2] = lo.z; q[c][3] = lo.w;
+              q[c][4] = hi.x; q[c][5] = hi.y; q[c][6] = hi.z; q[c][7] = hi.w;
             }
           }
+          if (!(DCN_DBG(a) & 2)) {
+            u32 o[8];
+            if constexpr (BLEND_BF16) {
+              const u32 wh0 = pack_bf16x2(w.x, w.x), wh1 = pack_bf16x2(w.y, w.y), wh2 = pack_bf16x2(w.z, w.z),
+                        wh3 = pack_bf16x2(w.w, w.w);
 #pragma unroll
-          for (int i = 0; i < ROWS_PT; ++i) {
-            if (a.debug & 2) continue;
-            const int row = r0 + (NPROD / 8) * i;
-            u32 o[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const u32 v0 = (&q[i][0].x)[e], v1 = (&q[i][1].x)[e], v2 = (&q[i][2].x)[e], v3 = (&q[i][3].x)[e];
-              // bf16 -> fp32 is a 16-bit shift: low element = v << 16, high element = v & 0xffff0000;
-              // the (low, high) pair is blended with one packed fp32x2 FMA per corner
-              if constexpr (BLEND_BF16) {
+              for (int e = 0; e < 8; ++e) {
                 u32 acc;
-                asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(acc) : "r"(wh[i][0]), "r"(v0));
-                asm("fma.rn.bf16x2 %0, %1, %2, %0;" : "+r"(acc) : "r"(wh[i][1]), "r"(v1));
-                asm("fma.rn.bf16x2 %0, %1, %2, %0;" : "+r"(acc) : "r"(wh[i][2]), "r"(v2));
-                asm("fma.rn.bf16x2 %0, %1, %2, %0;" : "+r"(acc) : "r"(wh[i][3]), "r"(v3));
+                asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(acc) : "r"(wh0), "r"(q[0][e]));
+                asm("fma.rn.bf16x2 %0, %1, %2, %0;" : "+r"(acc) : "r"(wh1), "r"(q[1][e]));
+                asm("fma.rn.bf16x2 %0, %1, %2, %0;" : "+r"(acc) : "r"(wh2), "r"(q[2][e]));
+                asm("fma.rn.bf16x2 %0, %1, %2, %0;" : "+r"(acc) : "r"(wh3), "r"(q[3][e]));
                 o[e] = acc;
-              } else {
-                u64 acc = mul2(ww[i][0], pair_from_bf16x2(v0));
-                acc = fma2(ww[i][1], pair_from_bf16x2(v1), acc);
-                acc = fma2(ww[i][2], pair_from_bf16x2(v2), acc);
-                acc = fma2(ww[i][3], pair_from_bf16x2(v3), acc);
+              }
+            } else {
+              const u64 w0 = dup2(w.x), w1 = dup2(w.y), w2 = dup2(w.z), w3 = dup2(w.w);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                // bf16 -> fp32 is a 16-bit shift: low element = v << 16, high element = v & 0xffff0000;
+                // the (low, high) pair is blended with one packed fp32x2 FMA per corner
+                u64 acc = mul2(w0, pair_from_bf16x2(q[0][e]));
+                acc = fma2(w1, pair_from_bf16x2(q[1][e]), acc);
+                acc = fma2(w2, pair_from_bf16x2(q[2][e]), acc);
+                acc = fma2(w3, pair_from_bf16x2(q[3][e]), acc);
                 float lo, hi;
                 asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc));
                 o[e] = pack_bf16x2(lo, hi);
               }
             }
-            const u32 dst = sa + row * 128 + ((chunk ^ (row & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(o[0]), "r"(o[1]), "r"(o[2]),
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sa + dst_lo), "r"(o[0]), "r"(o[1]), "r"(o[2]),
                          "r"(o[3])
+                         : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sa + dst_hi), "r"(o[4]), "r"(o[5]), "r"(o[6]),
+                         "r"(o[7])
                          : "memory");
           }
         }
-        if (!(a.debug & 8)) fence_proxy_async_smem();       // generic-proxy stores -> visible to the tensor core (async proxy)
+        if (!(DCN_DBG(a) & 8)) fence_proxy_async_smem();       // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_full[s]);
+        if (tid == 0) DCN_STAMP(1, (int)(t * a.nkb) + kb);
         if (++tap == 9) {
           tap = 0;
           ++slab;
@@ -256,6 +282,7 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
       const u32 tb = t & 1u;
       mbar_wait_parked(&s_tabempty[tb], ((t >> 1) & 1u) ^ 1u);
       mbar_wait_parked(&s_omfull[tb], (t >> 1) & 1u);
+      if (stid == 0) DCN_STAMP(4, (int)t);
       const float* oms = s_om + tb * (BM * OM_CS);
       const int m0 = tile * BM;
 #pragma unroll 3
@@ -264,7 +291,7 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
         const int m = m0 + r;
         float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
         u32 b = 0;
-        if (a.debug & 16) {
+        if (DCN_DBG(a) & 16) {
           w = make_float4(0.25f, 0.25f, 0.25f, 0.25f);
         } else if (m < a.M) {
           const int n = m / HW;
@@ -297,6 +324,7 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_tabfull[tb]);
+      if (stid == 0) DCN_STAMP(5, (int)t);
       // all setup warps are done with this om buffer: refill it for tile + 2
       asm volatile("bar.sync 1, %0;" ::"n"(NSETUP) : "memory");
       if (stid == 0 && tile + 2 < tile_end) issue_om(tile + 2, tb);
@@ -318,9 +346,10 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
         for (int kb = 0; kb < a.nkb; ++kb) {
           mbar_wait_parked(&s_full[s], ph);
           tc_fence_after();
+          if (lane == 0) DCN_STAMP(2, (int)(t * a.nkb) + kb);
           if (elect_one()) {
             const u64 da = da0 + (u64)soff16, db = db0 + (u64)soff16;
-            if (!(a.debug & 4)) {
+            if (!(DCN_DBG(a) & 4)) {
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)   // +32 bytes of K inside the swizzle atom
                 umma_bf16(tmem_d, da + (u64)(2 * kk), db + (u64)(2 * kk), a.idesc, kk == 0 ? accumulate : 1u);
@@ -328,6 +357,7 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
             umma_commit(&s_empty[s]);
           }
           __syncwarp();
+          if (lane == 0) DCN_STAMP(3, (int)(t * a.nkb) + kb);
           accumulate = 1;
           soff16 += stage16;
           if (++s == (u32)a.stages) {
@@ -349,6 +379,7 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
       const int m = tile * BM + 32 * q + lane;
       mbar_wait_parked(&s_tfull[acc], acc_ph);
       tc_fence_after();
+      if (warp == W_EPI0 && lane == 0) DCN_STAMP(6, (int)t);
       const u32 taddr = tmem_base + acc * a.acc_stride + ((u32)(32 * q) << 16);
       const int ngroups = a.BN / 16;
       for (int g = 0; g < ngroups; ++g) {
@@ -361,6 +392,7 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_tempty[acc]);
+      if (warp == W_EPI0 && lane == 0) DCN_STAMP(7, (int)t);
     }
   }
   tc_fence_before();
@@ -430,6 +462,14 @@ int dcn_ws_run(const cnb_conv_desc* d, const void* x, const float* om, int om_cs
   }
   static const int env_dbg = [] { const char* e = getenv("CNB_DCN_DEBUG"); return e ? atoi(e) : 0; }();
   a.debug = env_dbg;
+  static const bool env_trace = getenv("CNB_DCN_TRACE") != nullptr;
+  static long long* trace_buf = nullptr;
+  a.trace = nullptr;
+  if (env_trace) {
+    if (!trace_buf) cudaMalloc(&trace_buf, 8 * 512 * sizeof(long long));
+    cudaMemset(trace_buf, 0, 8 * 512 * sizeof(long long));
+    a.trace = trace_buf;
+  }
   static const bool blend_bf16 = [] { const char* e = getenv("CNB_DCN_BLEND"); return e && e[0] == 'b'; }();
   static bool configured = false;
   if (!configured) {
@@ -443,6 +483,23 @@ int dcn_ws_run(const cnb_conv_desc* d, const void* x, const float* om, int om_cs
   else
     dcn_ws_kernel<false><<<grid, NTHREADS, smem, st>>>(tmB, a);
   CNB_LAUNCH_CHECK();
+  if (env_trace) {   // debugging aid: clock stamps of CTA 0, printed relative to the first sampler stamp
+    static int printed = 0;
+    cudaStreamSynchronize(st);
+    if (printed++ == 3) {
+      static long long h[8 * 512];
+      cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
+      const long long t0 = h[0];
+      fprintf(stderr, "dcn_ws trace Ci=%d Co=%d nkb=%d stages=%d (clocks since the first K block)\n", d->Ci, d->Co, a.nkb,
+              a.stages);
+      for (int k = 0; k < 45 && h[k]; ++k)
+        fprintf(stderr, "k=%3d sampler0 got_stage %7lld arrived %7lld | mma got_data %7lld committed %7lld\n", k, h[k] - t0,
+                h[512 + k] - t0, h[1024 + k] - t0, h[1536 + k] - t0);
+      for (int t = 0; t < 6 && h[2048 + t]; ++t)
+        fprintf(stderr, "tile %d setup start %7lld table_done %7lld | epilogue start %7lld done %7lld\n", t, h[2048 + t] - t0,
+                h[2560 + t] - t0, h[3072 + t] - t0, h[3584 + t] - t0);
+    }
+  }
   return CNB_OK;
 }
 
