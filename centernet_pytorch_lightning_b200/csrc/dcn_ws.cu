@@ -53,6 +53,9 @@ struct DArgs {
   int M, m_tiles;
   int BN;          // = Co rounded up to 16, <= 256
   int nkb;         // 9 * Ci/64
+  int kper;        // K blocks (taps) per pipeline stage: 2 when two such stages fit (stage handshake amortised)
+  int nsteps;      // ceil(nkb / kper)
+  u32 bstage;      // bytes of one K block's weight tile inside a stage (b_bytes rounded up to 1 KB)
   int stages;
   u32 b_bytes, stage_bytes, tmem_cols, acc_stride, idesc;
   long long* trace;  // CNB_DCN_TRACE: clock stamps of CTA 0 (see dcn_ws_run)
@@ -168,15 +171,25 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
       const float4* tw = s_tabw + tb * NTAB + row * 9;
       const u32* tbs = s_tabb + tb * NTAB + row * 9;
       int slab = 0, tap = 0;
-      for (int kb = 0; kb < a.nkb; ++kb) {
+      for (int st = 0; st < a.nsteps; ++st) {
+        const int kc = min(a.kper, a.nkb - st * a.kper);   // K blocks (taps) in this stage
         mbar_wait_parked(&s_empty[s], ph ^ 1u);
-        if (tid == 0) DCN_STAMP(0, (int)(t * a.nkb) + kb);
-        const u32 sa = smem_base + s * a.stage_bytes;
+        if (tid == 0) DCN_STAMP(0, (int)(t * a.nsteps) + st);
+        const u32 sa0 = smem_base + s * a.stage_bytes;
         if (warp == 0 && elect_one()) {   // (elected, not `tid == 0`: uniform operands, no broadcast loop; a separate
                                           // warp for this was measured slower: 26 warps contend more than this costs)
-          mbar_expect_tx(&s_full[s], a.b_bytes);
-          tma_load_2d(sa + A_BYTES, &tmB, tap * d.Ci + slab * 64, 0, &s_full[s]);
+          mbar_expect_tx(&s_full[s], (u32)kc * a.b_bytes);
+          int tp = tap, sl = slab;
+          for (int j = 0; j < kc; ++j) {
+            tma_load_2d(sa0 + (u32)a.kper * A_BYTES + (u32)j * a.bstage, &tmB, tp * d.Ci + sl * 64, 0, &s_full[s]);
+            if (++tp == 9) {
+              tp = 0;
+              ++sl;
+            }
+          }
         }
+        for (int j = 0; j < kc; ++j) {
+        const u32 sa = sa0 + (u32)j * A_BYTES;
         const __nv_bfloat16* xs = a.x + d.x_coffset + slab * 64 + cp * 16;
         {
           u32 q[4][8];
@@ -244,14 +257,15 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
                          : "memory");
           }
         }
-        if (!(DCN_DBG(a) & 8)) fence_proxy_async_smem();       // generic-proxy stores -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_full[s]);
-        if (tid == 0) DCN_STAMP(1, (int)(t * a.nkb) + kb);
         if (++tap == 9) {
           tap = 0;
           ++slab;
         }
+        }   // K blocks of the stage
+        if (!(DCN_DBG(a) & 8)) fence_proxy_async_smem();       // generic-proxy stores -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_full[s]);
+        if (tid == 0) DCN_STAMP(1, (int)(t * a.nsteps) + st);
         if (++s == (u32)a.stages) {
           s = 0;
           ph ^= 1u;
@@ -334,8 +348,9 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
     {   // all lanes walk the loop (warp-uniform operands -> uniform registers); one elected lane issues
       u32 s = 0, ph = 0, t = 0;
       const u64 da0 = make_sdesc(smem_base, 16, 1024, 2);
-      const u64 db0 = make_sdesc(smem_base + A_BYTES, 16, 1024, 2);
+      const u64 db0 = make_sdesc(smem_base + (u32)a.kper * A_BYTES, 16, 1024, 2);
       const u32 stage16 = a.stage_bytes >> 4;
+      const u32 bstage16 = a.bstage >> 4;
       u32 soff16 = 0;
       for (int tile = tile_begin; tile < tile_end; ++tile, ++t) {
         const u32 acc = t & 1u, acc_ph = (t >> 1) & 1u;
@@ -343,21 +358,26 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
         tc_fence_after();
         const u32 tmem_d = tmem_base + acc * a.acc_stride;
         u32 accumulate = 0;
-        for (int kb = 0; kb < a.nkb; ++kb) {
+        for (int st = 0; st < a.nsteps; ++st) {
+          const int kc = min(a.kper, a.nkb - st * a.kper);
           mbar_wait_parked(&s_full[s], ph);
           tc_fence_after();
-          if (lane == 0) DCN_STAMP(2, (int)(t * a.nkb) + kb);
+          if (lane == 0) DCN_STAMP(2, (int)(t * a.nsteps) + st);
           if (elect_one()) {
-            const u64 da = da0 + (u64)soff16, db = db0 + (u64)soff16;
+            u64 da = da0 + (u64)soff16, db = db0 + (u64)soff16;
             if (!(DCN_DBG(a) & 4)) {
+              for (int j = 0; j < kc; ++j) {
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk)   // +32 bytes of K inside the swizzle atom
-                umma_bf16(tmem_d, da + (u64)(2 * kk), db + (u64)(2 * kk), a.idesc, kk == 0 ? accumulate : 1u);
+                for (int kk = 0; kk < 4; ++kk)   // +32 bytes of K inside the swizzle atom
+                  umma_bf16(tmem_d, da + (u64)(2 * kk), db + (u64)(2 * kk), a.idesc, (kk | j) == 0 ? accumulate : 1u);
+                da += (u64)(A_BYTES >> 4);
+                db += (u64)bstage16;
+              }
             }
             umma_commit(&s_empty[s]);
           }
           __syncwarp();
-          if (lane == 0) DCN_STAMP(3, (int)(t * a.nkb) + kb);
+          if (lane == 0) DCN_STAMP(3, (int)(t * a.nsteps) + st);
           accumulate = 1;
           soff16 += stage16;
           if (++s == (u32)a.stages) {
@@ -432,10 +452,19 @@ int dcn_ws_run(const cnb_conv_desc* d, const void* x, const float* om, int om_cs
   a.BN = round_up(d->Co, 16);
   a.nkb = 9 * (d->Ci / 64);
   a.b_bytes = (u32)a.BN * 128u;
-  a.stage_bytes = A_BYTES + ((a.b_bytes + 1023u) & ~1023u);
+  a.bstage = (a.b_bytes + 1023u) & ~1023u;
   const size_t fixed = (size_t)2 * NTAB * (sizeof(float4) + sizeof(u32)) + (size_t)2 * BM * OM_CS * 4 +
                        (size_t)a.BN * 8 + 1024;
+  // Every sampler warp takes part in every stage, so a stage costs one warp's dependent chain plus a ~400-clock
+  // handshake (fence, arrive, wait); the ring depth does not matter (2..6 stages measured equal).  Two taps per stage
+  // halve the handshakes when two such stages fit (CNB_DCN_KPER / CNB_DCN_STAGES override).
+  static const int env_kper = [] { const char* e = getenv("CNB_DCN_KPER"); return e ? atoi(e) : 0; }();
   static const int env_stages = [] { const char* e = getenv("CNB_DCN_STAGES"); return e ? atoi(e) : 0; }();
+  a.kper = env_kper > 0 ? env_kper : 2;
+  if (a.kper > 3) a.kper = 3;
+  while (a.kper > 1 && (size_t)2 * a.kper * (A_BYTES + a.bstage) + fixed > 220 * 1024) --a.kper;
+  a.stage_bytes = (u32)a.kper * (A_BYTES + a.bstage);
+  a.nsteps = (a.nkb + a.kper - 1) / a.kper;
   a.stages = env_stages > 0 ? env_stages : 3;
   if (a.stages > MAX_STAGES) a.stages = MAX_STAGES;
   while (a.stages > 2 && (size_t)a.stages * a.stage_bytes + fixed > 220 * 1024) --a.stages;
