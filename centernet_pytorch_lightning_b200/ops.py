@@ -212,6 +212,18 @@ def stem_s2d_filter(w):
     return ws.reshape(2 * Co, 8, K, KX), (K, KX, D)
 
 
+def pack_conv_weights_dgrad(w):
+    """Packed weights of the DATA-GRADIENT convolution of a stride-1 conv: dX = conv(dY, W') with
+    W'[ci, co, kh, kw] = W[co, ci, KH-1-kh, KW-1-kw] and padding K-1-pad -- the same tcgen05 kernel as the forward.
+    (First piece of the training path, SURVEY 8b `conv2d_dgrad`; stride-2 dgrad and wgrad are not built.)"""
+    return pack_conv_weights(w.detach().float().flip(2, 3).transpose(0, 1).contiguous())
+
+
+def conv2d_dgrad(dy, wpk_dgrad, Ci, k, pad, out=None):
+    """dX [B,H,W,Ci] bf16 = d(conv2d stride 1)/dX applied to dY [B,H,W,Co] bf16 (NHWC), fp32 accumulation."""
+    return conv2d(dy, wpk_dgrad, Ci, k, 1, k - 1 - pad, None, None, act=0, out=out)
+
+
 def pack_stem_s2d_weights(w):
     """Space-to-depth packing of a stride-1 KxK filter over <= 4 input channels (the DLA 7x7 stem,
     pose_dla_dcn.py:281-285).  The input [B,H,W,4] bf16 is read as [B,H,W/2,8]: one 16-byte "super-pixel" holds

@@ -137,6 +137,10 @@ typedef struct cnb_conv_desc {
                              rectangular filters run on the row-window kernel only (stride 1, Wo % 128 == 0). */
 } cnb_conv_desc;
 
+/* Data gradient of a stride-1 convolution (first piece of the training path): dX = cnb_conv2d_fprop(dY, W') with
+ * W'[ci][co][kh][kw] = W[co][ci][KH-1-kh][KW-1-kw] packed by cnb_conv_pack_weights(Co'=Ci, Ci'=Co) and pad' = K-1-pad
+ * (host mirror: ops.pack_conv_weights_dgrad / ops.conv2d_dgrad; parity: tests/test_conv_gpu.py::test_conv_dgrad_*).
+ * Stride-2 dgrad and wgrad have no entry point yet. */
 size_t cnb_conv_packed_weight_bytes(int Co, int Ci, int KH, int KW);
 /* w: [Co,Ci,KH,KW] fp32 (PyTorch layout, device) -> wpk bf16 device */
 int cnb_conv_pack_weights(const float* w, void* wpk, int Co, int Ci, int KH, int KW,

@@ -101,6 +101,20 @@ def test_stem_space_to_depth(cuda_dev, B, H, W, k):
     _check(y.permute(0, 3, 1, 2), ref, 2e-2)
 
 
+@pytest.mark.parametrize("B,Ci,Co,H,W,k", [(2, 64, 128, 24, 24, 3), (1, 16, 32, 8, 128, 3), (1, 256, 64, 16, 16, 1)])
+def test_conv_dgrad_matches_autograd(cuda_dev, B, Ci, Co, H, W, k):
+    """Data gradient of a stride-1 convolution = the forward kernel on the flipped / transposed filter
+    (ops.pack_conv_weights_dgrad) against torch.autograd on the same bf16-rounded operands."""
+    g = torch.Generator(device="cpu").manual_seed(Ci + Co + k)
+    x = _bf(torch.randn(B, Ci, H, W, generator=g)).to(cuda_dev).requires_grad_(True)
+    w = _bf(torch.randn(Co, Ci, k, k, generator=g) / (Co * k * k) ** 0.5).to(cuda_dev)
+    dy = _bf(torch.randn(B, Co, H, W, generator=g)).to(cuda_dev)
+    (ref,) = torch.autograd.grad(F.conv2d(x, w, padding=k // 2), x, dy)
+    dx = ops.conv2d_dgrad(ops.to_nhwc_bf16(dy), ops.pack_conv_weights_dgrad(w), Ci, k, k // 2)
+    assert dx.shape == (B, H, W, Ci)
+    _check(dx.permute(0, 3, 1, 2), ref, 2e-2)
+
+
 def test_conv_concat_slices(cuda_dev):
     """Reading / writing channel slices of wider NHWC buffers (Root's torch.cat without the copy)."""
     g = torch.Generator().manual_seed(7)
@@ -132,8 +146,13 @@ def test_conv_nchw_f32_head_output(cuda_dev):
     _check(ys, torch.sigmoid(F.conv2d(x, w, bias)), 2e-3)
 
 
-@pytest.mark.parametrize("B,Ci,Co,H,W", [(2, 64, 64, 24, 24), (1, 128, 64, 16, 20), (1, 256, 256, 8, 8)])
-def test_dcnv2_matches_torchvision(cuda_dev, B, Ci, Co, H, W):
+@pytest.mark.parametrize("B,Ci,Co,H,W,sliced", [(2, 64, 64, 24, 24, False), (1, 128, 64, 16, 20, False),
+                                                 (1, 256, 256, 8, 8, False),
+                                                 (1, 128, 128, 20, 24, False),   # BN=128: two taps per stage, 18 K blocks
+                                                 (2, 64, 24, 12, 40, False),     # Co not a multiple of 16
+                                                 (1, 64, 64, 16, 24, True)])     # 16-byte-aligned channel slice of a
+                                                                                 # wider tensor: 128-bit corner loads
+def test_dcnv2_matches_torchvision(cuda_dev, B, Ci, Co, H, W, sliced):
     """DCN numerics are 'parity unpinned' by the reference (external extension); the pin is
     torchvision.ops.deform_conv2d on CPU fp32 with the same bf16-rounded operands."""
     from torchvision.ops import deform_conv2d
@@ -147,7 +166,12 @@ def test_dcnv2_matches_torchvision(cuda_dev, B, Ci, Co, H, W):
     ref = deform_conv2d(x, torch.cat((o1, o2), 1), w, bias, padding=1, mask=torch.sigmoid(m))
     om_nhwc = torch.zeros(B, H, W, 32)
     om_nhwc[..., :27] = om.permute(0, 2, 3, 1)
-    y = ops.dcnv2(ops.to_nhwc_bf16(x.to(cuda_dev)), om_nhwc.to(cuda_dev).contiguous(),
+    xn = ops.to_nhwc_bf16(x.to(cuda_dev))
+    if sliced:   # x lives at channel offset 8 of a [B,H,W,Ci+24] buffer
+        wide = torch.randn(B, H, W, Ci + 24, device=cuda_dev).to(torch.bfloat16)
+        wide[..., 8:8 + Ci] = xn
+        xn = ops.View(wide, Ci, 8)
+    y = ops.dcnv2(xn, om_nhwc.to(cuda_dev).contiguous(),
                   ops.pack_conv_weights(w.to(cuda_dev)), Co, None, bias.to(cuda_dev), act=0)
     torch.cuda.synchronize()
     _check(y.permute(0, 3, 1, 2).cpu(), ref, 2e-2)
