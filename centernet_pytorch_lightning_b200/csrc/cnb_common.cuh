@@ -6,6 +6,8 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include <atomic>
+#include <utility>
+#include <stdlib.h>
 #include "../../include/centernet_b200.h"
 
 namespace cnb {
@@ -43,6 +45,23 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n
     }                                                                                      \
     ::cnb::count_launch();                                                                 \
   } while (0)
+
+// kernel launch with the programmatic-stream-serialization attribute (CNB_PDL=0: plain launch)
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  static const bool on = [] { const char* e = getenv("CNB_PDL"); return !(e && e[0] == '0'); }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = on ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // ---- device helpers ----------------------------------------------------------------------------
 typedef unsigned long long u64;
@@ -153,6 +172,13 @@ __device__ __forceinline__ bool elect_one() {
       : "+r"(pred));
   return pred != 0;
 }
+
+// Programmatic dependent launch: a kernel launched with launch_pdl() may start (prologue: barrier init, TMEM
+// allocation, constants) while the previous kernel in the stream drains; pdl_wait() blocks until that kernel has
+// completed and its writes are visible -- it must precede every access to activations.  Both are no-ops for a
+// normally launched kernel.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }
 __device__ __forceinline__ float warp_sum_f(float v) {

@@ -199,6 +199,8 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
   }
   tc_fence_before();
   __syncthreads();
+  pdl_launch_dependents();
+  pdl_wait();   // activations (input rows, residual) are touched only after the previous kernel has completed
   tc_fence_after();
   const u32 tmem_base = s_tmem;
 
@@ -564,7 +566,7 @@ int conv_rows_run(const cnb_conv_desc* d, const void* x, const void* wpk, const 
     configured = true;
   }
   const int grid = a.units < drv.num_sms ? a.units : drv.num_sms;
-  conv_rows_kernel<<<grid, NTHREADS, p.smem, st>>>(tmB, a);
+  CNB_CUDA(launch_pdl(conv_rows_kernel, dim3(grid), dim3(NTHREADS), p.smem, st, tmB, a));
   CNB_LAUNCH_CHECK();
   return CNB_OK;
 }

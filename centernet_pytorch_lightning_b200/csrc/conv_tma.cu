@@ -102,6 +102,8 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (CL) cluster_sync_all();   // peers' barriers are initialised before anything is multicast to them
   else __syncthreads();
   tc_fence_after();
+  pdl_launch_dependents();      // the next kernel may start its prologue as soon as SMs free up ...
+  pdl_wait();                   // ... and this one touches activations only after its predecessor has completed
   const u32 tmem_base = s_tmem;
   const int HoWo = d.Ho * d.Wo;
   // tile walk: cluster `cid` of `ncl` takes (M group, N tile) pairs; CTA `crank` of the cluster owns M tile
@@ -488,7 +490,7 @@ int conv_tma_run(const cnb_conv_desc* d, const void* x, const void* wpk, const f
   if (a.csize == 1) {
     const int grid = a.total_tiles < drv.num_sms ? a.total_tiles : drv.num_sms;
     if (a.debug || a.trace) conv_tma_kernel<false, true><<<grid, NTHREADS, smem, st>>>(tmA, tmB, a);
-    else conv_tma_kernel<false, false><<<grid, NTHREADS, smem, st>>>(tmA, tmB, a);
+    else CNB_CUDA(launch_pdl(conv_tma_kernel<false, false>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, a));
   } else {
     const int ncl = a.total_tiles < nclusters ? a.total_tiles : nclusters;
     cudaLaunchConfig_t cfg = {};

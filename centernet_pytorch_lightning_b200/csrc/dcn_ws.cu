@@ -144,6 +144,8 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
   }
   tc_fence_before();
   __syncthreads();
+  pdl_launch_dependents();
+  pdl_wait();   // x / offsets are touched only after the previous kernel has completed
   tc_fence_after();
   const u32 tmem_base = s_tmem;
   const int HW = d.Hi * d.Wi;
@@ -508,9 +510,9 @@ int dcn_ws_run(const cnb_conv_desc* d, const void* x, const float* om, int om_cs
   }
   const int grid = a.m_tiles < drv.num_sms ? a.m_tiles : drv.num_sms;
   if (blend_bf16)
-    dcn_ws_kernel<true><<<grid, NTHREADS, smem, st>>>(tmB, a);
+    CNB_CUDA(launch_pdl(dcn_ws_kernel<true>, dim3(grid), dim3(NTHREADS), smem, st, tmB, a));
   else
-    dcn_ws_kernel<false><<<grid, NTHREADS, smem, st>>>(tmB, a);
+    CNB_CUDA(launch_pdl(dcn_ws_kernel<false>, dim3(grid), dim3(NTHREADS), smem, st, tmB, a));
   CNB_LAUNCH_CHECK();
   if (env_trace) {   // debugging aid: clock stamps of CTA 0, printed relative to the first sampler stamp
     static int printed = 0;
