@@ -261,7 +261,21 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tc_fence_after();
       const u32 taddr = tmem_base + acc * a.acc_stride + ((u32)(32 * q) << 16);
       const int ngroups = a.BN / 16;
-      for (int g = half; g < ngroups; g += 2) {
+      // wide part: the quarter's two warps alternate over 64-column blocks, one tcgen05.ld each (see umma.cuh)
+      const int nwide = a.BN / 64;
+      for (int b = half; b < nwide; b += 2) {
+        if (dbg & 16) continue;
+        u32 v[64];
+        tmem_ld64_nowait(taddr + (u32)(b * 64), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int co0 = n0 + b * 64 + j * 16;
+          u32(&vj)[16] = *reinterpret_cast<u32(*)[16]>(&v[16 * j]);
+          if (m < a.M && co0 < d.Co && !(dbg & 8)) epilogue_store(a, s_scale, s_shift, vj, m, co0, co0, HoWo, on, opix);
+        }
+      }
+      for (int g = nwide * 4 + half; g < ngroups; g += 2) {   // the last BN % 64 columns, 16 at a time
         u32 v[16];
         if (dbg & 16) continue;
         tmem_ld16_nowait(taddr + (u32)(g * 16), v);
