@@ -1,0 +1,34 @@
+"""-m gpu: the opt-in / fallback code paths of the convolution and DCN kernels, each in a fresh interpreter (the
+switches are read once per process): cluster multicast of the weight tile, the v1 gather kernel, the bf16 sampler
+blend, one tap per DCN stage, plain launches instead of programmatic dependent launch.  Same parity tests, same
+tolerances as tests/test_conv_gpu.py."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+VARIANTS = [
+    ({"CNB_CONV_CLUSTER": "2"}, "test_conv_matches_torch or test_conv_concat_slices"),
+    ({"CNB_CONV_CLUSTER": "4"}, "test_conv_matches_torch"),
+    ({"CNB_CONV_IMPL": "v1"}, "test_conv_matches_torch or test_stem_space_to_depth"),
+    ({"CNB_CONV_ROWS": "0"}, "test_conv_matches_torch"),
+    ({"CNB_DCN_BLEND": "bf16"}, "dcn"),
+    ({"CNB_DCN_KPER": "1"}, "dcn"),
+    ({"CNB_DCN_IMPL": "v1"}, "dcn"),
+    ({"CNB_PDL": "0"}, "test_conv_matches_torch or dcn"),
+]
+
+
+@pytest.mark.parametrize("env,select", VARIANTS, ids=[",".join(f"{k}={v}" for k, v in e.items()) for e, _ in VARIANTS])
+def test_kernel_variant(cuda_dev, env, select):
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_conv_gpu.py"), "-x", "-q",
+                        "-m", "gpu", "-k", select, "-p", "no:cacheprovider"],
+                       cwd=ROOT, env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
