@@ -259,6 +259,90 @@ dw_deconv_phase_kernel(const __nv_bfloat16* __restrict__ x, const float* __restr
   }
 }
 
+// The phase kernel without per-element index division and with the taps amortised: 3-D grid (x: input column x
+// channel group, y: block of RPT cell rows, z: image x phase); a thread keeps its phase's 4 x 8 taps in registers,
+// walks RPT rows down its column and rolls the two input pixels of the previous row through registers: per output
+// 2 input loads + 1 (add) load + 1 store.  (The grid-stride version above spends more issue slots on 64-bit div/mod
+// than on the blend, and reloading the 8 tap vectors per output made the L1 wavefront count the bound.)
+constexpr int UP_RPT = 8;
+__global__ void __launch_bounds__(256)
+dw_deconv_phase3d_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wt,
+                         const __nv_bfloat16* __restrict__ add, __nv_bfloat16* __restrict__ y, int B, int H, int W,
+                         int C, int f, int gshift) {
+  const int Ho = H * f, Wo = W * f, groups = C / 8, ks = 2 * f, pad = f / 2;
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  const int qx = t >> gshift, g = t & (groups - 1);
+  const int ff = f * f;
+  const int b = blockIdx.z / ff, phase = blockIdx.z - b * ff;
+  const int py = phase / f, px = phase - py * f;
+  const int ox = qx * f + px - pad;
+  // taps of this block's phase in shared memory ([4 taps][C] fp32, <= 4 KB): registers go to loads in flight instead
+  __shared__ __align__(16) float s_w[4 * 256];
+  const bool active = qx <= W && ox >= 0 && ox < Wo;
+  for (int i = threadIdx.x; i < 4 * C; i += 256) {
+    const int tp = i / C, c = i - tp * C;
+    const int ky = py + (tp >> 1) * f, kx = px + (tp & 1) * f;     // tap (ky, kx) reads input (qy - a, qx - c)
+    s_w[i] = __ldg(wt + (size_t)(ky * ks + kx) * C + c);
+  }
+  __syncthreads();
+  if (!active) return;
+  auto load_q = [&](int iy, int ix) -> uint4 {
+    if (iy < 0 || iy >= H || ix < 0 || ix >= W) return make_uint4(0u, 0u, 0u, 0u);
+    return __ldg(reinterpret_cast<const uint4*>(x + ((size_t)(b * H + iy) * W + ix) * C + g * 8));
+  };
+  auto out_off = [&](int qy, bool* ok) -> size_t {
+    const int oy = qy * f + py - pad;
+    *ok = oy >= 0 && oy < Ho;
+    return ((size_t)(b * Ho + (*ok ? oy : 0)) * Wo + ox) * C + g * 8;
+  };
+  const int qy0 = blockIdx.y * UP_RPT;
+  const int qy1 = min(qy0 + UP_RPT, H + 1);
+  uint4 v[4];                                          // v[tp]: input (qy - (tp>>1), qx - (tp&1))
+  v[2] = load_q(qy0 - 1, qx);
+  v[3] = load_q(qy0 - 1, qx - 1);
+  v[0] = load_q(qy0, qx);
+  v[1] = load_q(qy0, qx - 1);
+  bool ok;
+  size_t o = out_off(qy0, &ok);
+  uint4 av = (add && ok) ? __ldg(reinterpret_cast<const uint4*>(add + o)) : make_uint4(0u, 0u, 0u, 0u);
+  for (int qy = qy0; qy < qy1; ++qy) {
+    // next row's loads first: they are in flight while this row is blended
+    const bool more = qy + 1 < qy1;
+    const uint4 n0 = more ? load_q(qy + 1, qx) : make_uint4(0u, 0u, 0u, 0u);
+    const uint4 n1 = more ? load_q(qy + 1, qx - 1) : make_uint4(0u, 0u, 0u, 0u);
+    bool nok = false;
+    const size_t no = more ? out_off(qy + 1, &nok) : 0;
+    const uint4 nav = (add && nok) ? __ldg(reinterpret_cast<const uint4*>(add + no)) : make_uint4(0u, 0u, 0u, 0u);
+    if (ok) {
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int tp = 0; tp < 4; ++tp) {
+        const float4 w0 = *reinterpret_cast<const float4*>(&s_w[tp * C + g * 8]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&s_w[tp * C + g * 8 + 4]);
+        const float2 a0 = bf2_to_f2(v[tp].x), a1 = bf2_to_f2(v[tp].y), a2 = bf2_to_f2(v[tp].z), a3 = bf2_to_f2(v[tp].w);
+        acc[0] += w0.x * a0.x; acc[1] += w0.y * a0.y; acc[2] += w0.z * a1.x; acc[3] += w0.w * a1.y;
+        acc[4] += w1.x * a2.x; acc[5] += w1.y * a2.y; acc[6] += w1.z * a3.x; acc[7] += w1.w * a3.y;
+      }
+      if (add) {
+        const float2 a0 = bf2_to_f2(av.x), a1 = bf2_to_f2(av.y), a2 = bf2_to_f2(av.z), a3 = bf2_to_f2(av.w);
+        acc[0] += a0.x; acc[1] += a0.y; acc[2] += a1.x; acc[3] += a1.y;
+        acc[4] += a2.x; acc[5] += a2.y; acc[6] += a3.x; acc[7] += a3.y;
+      }
+      *reinterpret_cast<uint4*>(y + o) = make_uint4(f2_to_bf2(acc[0], acc[1]), f2_to_bf2(acc[2], acc[3]),
+                                                    f2_to_bf2(acc[4], acc[5]), f2_to_bf2(acc[6], acc[7]));
+    }
+    v[2] = v[0];
+    v[3] = v[1];
+    v[0] = n0;
+    v[1] = n1;
+    av = nav;
+    o = no;
+    ok = nok;
+  }
+}
+
 // f == 2 (every large up-sampling of the DLA-34 / ResNet nets): a thread owns (8-channel group, input column qx, output
 // row phase py) and walks down the rows.  Its 2 x 4 x 8 taps sit in registers, the two input rows of a cell roll
 // through registers, and each cell yields the two horizontally adjacent outputs: 2 input loads + 2 (add) loads +
@@ -419,12 +503,23 @@ extern "C" int cnb_dw_deconv_up(const void* x, const float* wt, const void* add,
   CNB_CHECK_ARG(C % 8 == 0 && f >= 1 && f % 2 == 0, "dw_deconv_up: C %% 8 == 0 and even upsampling factor required");
   const int groups = C / 8;
   static const bool no_f2 = [] { const char* e = getenv("CNB_DW_DECONV_F2"); return e && e[0] == '0'; }();
-  if (f == 2 && !no_f2 && B <= 32767 && H >= 64) {   // measured: 71 vs 78 us at 64x64 -> 128x128, no gain on small maps
+  static const int up_impl0 = [] { const char* e = getenv("CNB_DW_DECONV_IMPL"); return e ? atoi(e) : 3; }();
+  if (f == 2 && !no_f2 && B <= 32767 && H >= 64 && up_impl0 == 2) {   // measured: 71 vs 78 us at 64x64 -> 128x128, no gain on small maps
     const int rows_per_block = 8;
     dim3 grid((unsigned)(((long long)(W + 1) * groups + 127) / 128), (unsigned)((H + 1 + rows_per_block - 1) / rows_per_block),
               (unsigned)(B * 2));
     dw_deconv_f2_kernel<<<grid, 128, 0, (cudaStream_t)s>>>((const __nv_bfloat16*)x, wt, (const __nv_bfloat16*)add,
                                                             (__nv_bfloat16*)y, B, H, W, C, rows_per_block);
+    CNB_LAUNCH_CHECK();
+    return CNB_OK;
+  }
+  static const int up_impl = [] { const char* e = getenv("CNB_DW_DECONV_IMPL"); return e ? atoi(e) : 3; }();
+  if (up_impl == 3 && (groups & (groups - 1)) == 0 && f <= 8 && C <= 256 && (long long)B * f * f <= 65535 && H + 1 <= 65535) {
+    int gshift = 0;
+    while ((1 << gshift) < groups) ++gshift;
+    dim3 grid((unsigned)(((long long)(W + 1) * groups + 255) / 256), (unsigned)((H + UP_RPT) / UP_RPT), (unsigned)(B * f * f));
+    dw_deconv_phase3d_kernel<<<grid, 256, 0, (cudaStream_t)s>>>((const __nv_bfloat16*)x, wt, (const __nv_bfloat16*)add,
+                                                                 (__nv_bfloat16*)y, B, H, W, C, f, gshift);
     CNB_LAUNCH_CHECK();
     return CNB_OK;
   }
