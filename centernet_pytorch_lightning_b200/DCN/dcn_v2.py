@@ -5,7 +5,7 @@
     om  = conv3x3(x; conv_offset_mask)                 -> cnb_conv2d_fprop (tcgen05, NHWC fp32 out)
     y   = sum_k W_k * sigmoid(m_k) * bilinear(x, p+k+d_k) -> cnb_dcnv2_fprop (sampler feeds tcgen05 A tile)
 
-Forward only for now (inference path, configs 2/4/5); `requires_grad` training raises.
+Training: `autograd_ops.dcn` (cnb_dcnv2_im2col + 1x1 GEMMs + cnb_dcnv2_col2im + cnb_conv2d_wgrad).
 """
 import math
 
@@ -29,7 +29,7 @@ class DCN(nn.Module):
         self.conv_offset_mask = nn.Conv2d(in_channels, deformable_groups * 3 * kh * kw, kernel_size=(kh, kw),
                                           stride=stride, padding=padding, bias=True)
         self.reset_parameters()
-        self._packed = None
+        self._packed = ops.PackCache()
 
     def reset_parameters(self):
         stdv = 1.0 / math.sqrt(self.in_channels * 9)
@@ -39,22 +39,25 @@ class DCN(nn.Module):
         self.conv_offset_mask.bias.data.zero_()
 
     def packed(self):
-        """(w_main, w_offset) packed bf16, re-packed when the parameters change."""
-        key = (self.weight._version, self.conv_offset_mask.weight._version, self.weight.data_ptr())
-        if self._packed is None or self._packed[0] != key:
-            self._packed = (key, ops.pack_conv_weights(self.weight), ops.pack_conv_weights(self.conv_offset_mask.weight))
-        return self._packed[1], self._packed[2]
+        """(w_main, w_offset, b_offset) packed bf16 / fp32, rebuilt (in place) when the parameters change."""
+        com = self.conv_offset_mask
+        return self._packed.get("w", (self.weight, com.weight, com.bias),
+                                lambda: (ops.pack_conv_weights(self.weight), ops.pack_conv_weights(com.weight),
+                                         com.bias.detach().float().contiguous()))
 
     def forward_nhwc(self, x, scale=None, shift=None, act=0, out=None):
         """x: NHWC bf16 tensor or ops.View.  scale/shift default to (1, bias); pass folded BN to fuse it."""
-        w_main, w_off = self.packed()
-        om = ops.conv2d(x, w_off, 27, 3, 1, 1, None, self.conv_offset_mask.bias.detach().float(), act=0, out_mode=2)
+        w_main, w_off, b_off = self.packed()
+        om = ops.conv2d(x, w_off, 27, 3, 1, 1, None, b_off, act=0, out_mode=2)
         if shift is None:
             shift = self.bias.detach().float()
         return ops.dcnv2(x, om, w_main, self.out_channels, scale, shift, act=act, out=out)
 
     def forward(self, x):
-        if torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad) and self.training:
-            raise NotImplementedError("DCN backward is not implemented yet in centernet_b200 (inference only)")
+        """[B,C,H,W] fp32 -> [B,Co,H,W] fp32, the stand-alone module call of the DCNv2 API.  In training mode the op
+        runs on the autograd tape (autograd_ops.dcn: sampled columns + tensor-core GEMMs, backward included)."""
+        if self.training and torch.is_grad_enabled():
+            from .. import autograd_ops as ag
+            return ag.to_nchw_f32(ag.dcn(ag.to_nhwc_bf16(x), self))
         y = self.forward_nhwc(ops.to_nhwc_bf16(x))
         return ops.to_nchw_f32(y)

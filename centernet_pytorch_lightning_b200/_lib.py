@@ -53,6 +53,32 @@ def _declare(lib):
         "cnb_dw_deconv_up": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
         "cnb_nchw_f32_to_nhwc_bf16": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
         "cnb_nhwc_bf16_to_nchw_f32": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+        # training path
+        "cnb_conv_wgrad_acc_elems": (c_size_t, [c_int] * 4),
+        "cnb_conv2d_wgrad": (c_int, [POINTER(ConvDesc), P, P, c_int, c_int, P, P]),
+        "cnb_conv_unpack_wgrad": (c_int, [P, P] + [c_int] * 7 + [c_float, P]),
+        "cnb_bn_train_fwd": (c_int, [P, P, P, P, P, c_float, c_float, P, c_int, P, P, P, c_longlong, c_int, P]),
+        "cnb_scale_shift_act": (c_int, [P, P, P, P, c_int, P, c_longlong, c_int, P]),
+        "cnb_bn_train_bwd": (c_int, [P, P, P, P, P, P, P, P, c_int, P, c_longlong, c_int, P]),
+        "cnb_channel_sum": (c_int, [P, c_int, c_int, P, P, c_int, c_longlong, c_int, P]),
+        "cnb_relu_bwd": (c_int, [P, P, P, c_longlong, P]),
+        "cnb_add_bf16": (c_int, [P, P, P, c_longlong, P]),
+        "cnb_f32_to_bf16": (c_int, [P, P, P, c_longlong, c_int, c_int, P]),
+        "cnb_maxpool2x2_bwd": (c_int, [P, P, P] + [c_int] * 4 + [P]),
+        "cnb_dw_deconv_bwd": (c_int, [P, P, P, P, P] + [c_int] * 5 + [P]),
+        "cnb_dw_deconv_unpack_wgrad": (c_int, [P, P, c_int, c_int, c_int, P]),
+        "cnb_dcnv2_im2col": (c_int, [P, P, c_int, P] + [c_int] * 4 + [P]),
+        "cnb_dcnv2_col2im": (c_int, [P, P, c_int, P, P, P] + [c_int] * 4 + [P]),
+        "cnb_adam_step": (c_int, [P, P, P, P, c_longlong, c_float, c_float, c_float, c_float, c_int, c_float, P]),
+        # fp32-strict mode
+        "cnb_strict_conv2d_f32": (c_int, [P] * 6 + [c_int] * 10 + [P]),
+        "cnb_strict_dcn_im2col_f32": (c_int, [P, P, P] + [c_int] * 4 + [P]),
+        "cnb_strict_conv_transpose2d_f32": (c_int, [P] * 6 + [c_int] * 10 + [P]),
+        "cnb_strict_maxpool2d_f32": (c_int, [P, P] + [c_int] * 6 + [P]),
+        # decode primitives by name
+        "cnb_nms3x3": (c_int, [P, P, c_longlong, c_int, c_int, P]),
+        "cnb_topk_rows": (c_int, [P, c_int, c_int, c_int, P, P, P]),
+        "cnb_gather_feat": (c_int, [P, P, P] + [c_int] * 5 + [P]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
@@ -86,16 +112,23 @@ def launch_count():
 
 # ---- torch glue ------------------------------------------------------------------------------------
 _workspaces = {}
+_retired = []      # outgrown buffers stay alive: a captured CUDA graph may still hold their address
 
 
 def workspace(device, nbytes):
-    """A cached per-device scratch tensor of at least nbytes (grown geometrically)."""
+    """Scratch tensor of at least nbytes for the CURRENT stream of `device` (one buffer per (device, stream): two
+    streams never share scratch, so the entry points stay re-entrant per stream as include/centernet_b200.h says).
+    Buffers grow geometrically; an outgrown buffer is retired, never freed, because an engine's captured graph
+    (engine.py) may replay kernels that were recorded with its address."""
     import torch
 
-    key = (device.type, device.index)
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        if ws is not None:
+            _retired.append(ws)
+        ws = torch.empty(max(int(nbytes), 1 << 20, 2 * ws.numel() if ws is not None else 0), dtype=torch.uint8,
+                         device=device)
         _workspaces[key] = ws
     return ws
 

@@ -15,12 +15,24 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-// Device staging arena for the *_host entry points (grown on demand, one per process).
+// Device staging arena for the *_host entry points (grown on demand; belongs to the device that was current when it
+// was allocated and is re-allocated when the caller has switched devices).
 struct Arena {
   void* dev = nullptr;
   size_t bytes = 0;
+  int device = -1;
   std::mutex mu;
   int ensure(size_t need) {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cur != device && dev) {
+      cudaSetDevice(device);
+      cudaFree(dev);
+      cudaSetDevice(cur);
+      dev = nullptr;
+      bytes = 0;
+    }
+    device = cur;
     if (need <= bytes) return CNB_OK;
     if (dev) cudaFree(dev);
     dev = nullptr;

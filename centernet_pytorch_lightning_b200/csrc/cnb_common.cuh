@@ -46,6 +46,27 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n
     ::cnb::count_launch();                                                                 \
   } while (0)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE attribute: `static PerDeviceOnce once;
+// if (once.need()) { ...set attributes...; once.mark(); }` configures each kernel once on every device a process uses
+// (setting it twice from two racing threads is harmless).
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> done{0};
+  static int dev() { int d = 0; cudaGetDevice(&d); return d & 63; }
+  bool need() const { return !((done.load(std::memory_order_acquire) >> dev()) & 1ull); }
+  void mark() { done.fetch_or(1ull << dev(), std::memory_order_release); }
+};
+// SM count of the current device (cached per device)
+inline int sm_count() {
+  static std::atomic<int> cache[64];
+  const int d = PerDeviceOnce::dev();
+  int n = cache[d].load(std::memory_order_relaxed);
+  if (n <= 0) {
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d);
+    cache[d].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+
 // kernel launch with the programmatic-stream-serialization attribute (CNB_PDL=0: plain launch)
 template <class... KArgs, class... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

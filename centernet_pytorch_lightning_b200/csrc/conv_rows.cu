@@ -193,14 +193,14 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmB, const RArgs a) {
     fence_mbar_init();
   }
   if (warp == W_MMA) tmem_alloc(&s_tmem, a.tmem_cols);
+  pdl_launch_dependents();
+  pdl_wait();   // global memory (input rows, residual, scale/shift) is read only after the previous kernel has completed
   for (int i = tid; i < a.BN; i += NTHREADS) {
     s_scale[i] = (i < d.Co && a.scale) ? a.scale[i] : 1.f;
     s_shift[i] = (i < d.Co && a.shift) ? a.shift[i] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
-  pdl_launch_dependents();
-  pdl_wait();   // activations (input rows, residual) are touched only after the previous kernel has completed
   tc_fence_after();
   const u32 tmem_base = s_tmem;
 
@@ -560,10 +560,10 @@ int conv_rows_run(const cnb_conv_desc* d, const void* x, const void* wpk, const 
       return CNB_ERR_CUDA;
     }
   }
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.need()) {
     CNB_CUDA(cudaFuncSetAttribute(conv_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    configured = true;
+    once.mark();
   }
   const int grid = a.units < drv.num_sms ? a.units : drv.num_sms;
   CNB_CUDA(launch_pdl(conv_rows_kernel, dim3(grid), dim3(NTHREADS), p.smem, st, tmB, a));

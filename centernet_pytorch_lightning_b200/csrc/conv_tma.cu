@@ -94,6 +94,9 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1) tmem_alloc(&s_tmem, a.tmem_cols);
+  pdl_launch_dependents();      // the next kernel may start its prologue as soon as SMs free up ...
+  pdl_wait();                   // ... and this one reads global memory (scale/shift included: they may have been
+                                // produced in-stream) only after its predecessor has completed
   for (int i = tid; i < a.nscale; i += NTHREADS) {
     s_scale[i] = (i < d.Co && a.scale) ? a.scale[i] : 1.f;
     s_shift[i] = (i < d.Co && a.shift) ? a.shift[i] : 0.f;
@@ -102,8 +105,6 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (CL) cluster_sync_all();   // peers' barriers are initialised before anything is multicast to them
   else __syncthreads();
   tc_fence_after();
-  pdl_launch_dependents();      // the next kernel may start its prologue as soon as SMs free up ...
-  pdl_wait();                   // ... and this one touches activations only after its predecessor has completed
   const u32 tmem_base = s_tmem;
   const int HoWo = d.Ho * d.Wo;
   // tile walk: cluster `cid` of `ncl` takes (M group, N tile) pairs; CTA `crank` of the cluster owns M tile
@@ -424,12 +425,12 @@ int conv_tma_run(const cnb_conv_desc* d, const void* x, const void* wpk, const f
   while (a.tmem_cols < 2 * a.acc_stride) a.tmem_cols <<= 1;
   a.idesc = make_idesc_bf16(BM, a.BN);
   const size_t smem = (size_t)a.stages * a.stage_bytes + (size_t)a.nscale * 8 + 1024;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.need()) {
     CNB_CUDA(cudaFuncSetAttribute(conv_tma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     CNB_CUDA(cudaFuncSetAttribute(conv_tma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     CNB_CUDA(cudaFuncSetAttribute(conv_tma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    configured = true;
+    once.mark();
   }
 
   // ---- clusters (opt-in: CNB_CONV_CLUSTER=2|4).  Multicasting the weight tile cuts the L2 -> SM bytes of a K block

@@ -399,12 +399,12 @@ static Plan make_plan(const cnb_conv_desc& d) {
 
 template <int STAGES, bool DCN>
 static cudaError_t launch_conv(const ConvArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.need()) {
     cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<STAGES, DCN>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    configured = true;
+    once.mark();
   }
   conv_umma_kernel<STAGES, DCN><<<grid, CT, smem, st>>>(a);
   return cudaGetLastError();

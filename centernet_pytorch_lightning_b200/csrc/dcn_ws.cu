@@ -138,14 +138,14 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
   }
   if (warp == 0 && lane == 0) tma_prefetch_desc(&tmB);
   if (warp == W_MMA) tmem_alloc(&s_tmem, a.tmem_cols);
+  pdl_launch_dependents();
+  pdl_wait();   // global memory (x, offsets, scale/shift) is read only after the previous kernel has completed
   for (int i = tid; i < a.BN; i += NTHREADS) {
     s_scale[i] = (i < d.Co && a.scale) ? a.scale[i] : 1.f;
     s_shift[i] = (i < d.Co && a.shift) ? a.shift[i] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
-  pdl_launch_dependents();
-  pdl_wait();   // x / offsets are touched only after the previous kernel has completed
   tc_fence_after();
   const u32 tmem_base = s_tmem;
   const int HW = d.Hi * d.Wi;
@@ -502,11 +502,11 @@ int dcn_ws_run(const cnb_conv_desc* d, const void* x, const float* om, int om_cs
     a.trace = trace_buf;
   }
   static const bool blend_bf16 = [] { const char* e = getenv("CNB_DCN_BLEND"); return e && e[0] == 'b'; }();
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.need()) {
     CNB_CUDA(cudaFuncSetAttribute(dcn_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
     CNB_CUDA(cudaFuncSetAttribute(dcn_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-    configured = true;
+    once.mark();
   }
   const int grid = a.m_tiles < drv.num_sms ? a.m_tiles : drv.num_sms;
   if (blend_bf16)

@@ -1387,12 +1387,12 @@ static bool stream_ok(const ScanGeom& g, int K) {
 }
 
 static cudaError_t launch_stream(const ScanArgs& a, cudaStream_t st) {
-  static bool configured = false;
+  static PerDeviceOnce once;
   const size_t smem = (size_t)NST * a.tile_bytes + (size_t)SW * WLC * sizeof(u64);
-  if (!configured) {
+  if (once.need()) {
     cudaError_t e = cudaFuncSetAttribute(decode_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
     if (e != cudaSuccess) return e;
-    configured = true;
+    once.mark();
   }
   int grid = env_int("CNB_DECODE_CTAS", 2 * num_sms());
   if (grid > a.total_chunks) grid = a.total_chunks;
@@ -1406,12 +1406,12 @@ static cudaError_t launch_stream(const ScanArgs& a, cudaStream_t st) {
 
 template <int VEC>
 static cudaError_t launch_scan(const ScanArgs& a, size_t smem, cudaStream_t st) {
-  static bool configured = false;  // per template instantiation
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.need()) {
     cudaError_t e = cudaFuncSetAttribute(decode_scan_kernel<VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          112 * 1024);
     if (e != cudaSuccess) return e;
-    configured = true;
+    once.mark();
   }
   int grid = env_int("CNB_DECODE_CTAS", 2 * num_sms());
   if (grid > a.total_chunks) grid = a.total_chunks;

@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(1024) reg_l1_kernel(const RegArgs a) {
     const float m = a.mask_per_channel ? ((const float*)a.mask)[i]
                                        : (((const unsigned char*)a.mask)[bm] ? 1.f : 0.f);
     const long long idx = a.ind[bm];
+    if (idx < 0 || idx >= HW) continue;   // out-of-range index: the entry is dropped (the reference's gather asserts)
     const float pred = a.output[((size_t)b * a.C + c) * HW + idx];
     num += fabsf(pred * m - a.target[i] * m);
     den += m;
@@ -222,6 +223,7 @@ __global__ void __launch_bounds__(1024) reg_l1_kernel(const RegArgs a) {
     const float m = a.mask_per_channel ? ((const float*)a.mask)[i]
                                        : (((const unsigned char*)a.mask)[bm] ? 1.f : 0.f);
     const long long idx = a.ind[bm];
+    if (idx < 0 || idx >= HW) continue;
     const size_t o = ((size_t)b * a.C + c) * HW + idx;
     const float d = a.output[o] * m - a.target[i] * m;
     const float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);

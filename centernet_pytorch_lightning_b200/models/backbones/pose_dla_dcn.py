@@ -19,6 +19,7 @@ import torch
 from torch import nn
 
 from ... import ops
+from ..._lib import require_cuda as _lib_require_cuda
 from ...DCN.dcn_v2 import DCN
 from ...ops import View
 
@@ -89,12 +90,15 @@ class DLA(nn.Module):                 # pose_dla_dcn.py:268-396
         return nn.Sequential(*mods)
 
 
-def _fill_bilinear(up):               # pose_dla_dcn.py:424-432 (bilinear kernel, identical for every channel)
+def _fill_bilinear(up):
+    """Separable bilinear kernel into weight[:, 0] (pose_dla_dcn.py:424-432, resnet_dcn.py:109-118).  For the
+    depthwise DLA up-samplers that is the whole weight; a dense ConvTranspose2d keeps its default init elsewhere."""
     k = up.weight.shape[2]
     f = math.ceil(k / 2)
     c = (2 * f - 1 - f % 2) / (2.0 * f)
     g = torch.tensor([1 - abs(i / f - c) for i in range(k)], dtype=torch.float32)
-    up.weight.data.copy_((g[:, None] * g[None, :]).expand_as(up.weight.data))
+    with torch.no_grad():
+        up.weight[:, 0].copy_((g[:, None] * g[None, :]).expand_as(up.weight[:, 0]))
 
 
 class DeformConv(nn.Module):          # pose_dla_dcn.py:435-454
@@ -143,15 +147,17 @@ def fold_bn(bn, conv_bias=None):
     return scale.contiguous(), shift.contiguous()
 
 
-class _Compiled:
-    """Packed weights + folded BN per conv, built once per parameter version."""
+def _bn_params(bn):
+    return (bn.weight, bn.bias, bn.running_mean, bn.running_var)
 
-    def __init__(self):
-        self.cache = {}
+
+class _Compiled(ops.PackCache):
+    """Packed weights + folded BN per conv.  Every entry is stamped with (version, data_ptr) of the parameters and
+    BN buffers it was built from (ops.param_key) and rebuilt when they change -- an optimizer step, a
+    `load_state_dict` through ANY parent module, `nn.init.*_` -- like `DCN.packed()`."""
 
     def conv(self, conv, bn=None):
-        key = id(conv)
-        if key not in self.cache:
+        def build():
             # the 3-channel 7x7 stem runs on an 8-channel padded input: packed 7x8 (zero column) so that the taps
             # (kw, kw+1) of one row form one K=16 tensor-core step (cnb_conv_desc.w_kw)
             w_kw = conv.kernel_size[1] + 1 if (conv.in_channels <= 8 and conv.kernel_size[1] % 2 == 1
@@ -161,30 +167,22 @@ class _Compiled:
                 scale, shift = fold_bn(bn, conv.bias)
             else:
                 scale, shift = None, (conv.bias.detach().float().contiguous() if conv.bias is not None else None)
-            self.cache[key] = (wpk, scale, shift, w_kw)
-        return self.cache[key]
+            return (wpk, scale, shift, w_kw)
+        return self.get(id(conv), (conv.weight, conv.bias) + (_bn_params(bn) if bn is not None else ()), build)
 
     def stem_s2d(self, conv, bn):
         """space-to-depth packing of the 7x7 stem (ops.pack_stem_s2d_weights): two output pixels per GEMM row"""
-        key = ("s2d", id(conv))
-        if key not in self.cache:
+        def build():
             wpk, geom = ops.pack_stem_s2d_weights(conv.weight)
             scale, shift = fold_bn(bn, conv.bias)
-            self.cache[key] = (wpk, geom, scale.repeat(2).contiguous(), shift.repeat(2).contiguous())
-        return self.cache[key]
+            return (wpk, geom, scale.repeat(2).contiguous(), shift.repeat(2).contiguous())
+        return self.get(("s2d", id(conv)), (conv.weight, conv.bias) + _bn_params(bn), build)
 
     def deform(self, dc):
-        key = id(dc)
-        if key not in self.cache:
-            scale, shift = fold_bn(dc.actf[0], dc.conv.bias)
-            self.cache[key] = (scale, shift)
-        return self.cache[key]
+        return self.get(id(dc), (dc.conv.bias,) + _bn_params(dc.actf[0]), lambda: fold_bn(dc.actf[0], dc.conv.bias))
 
     def up(self, up, f):
-        key = id(up)
-        if key not in self.cache:
-            self.cache[key] = ops.relayout_dw_weights(up.weight, f)
-        return self.cache[key]
+        return self.get(id(up), (up.weight,), lambda: (ops.relayout_dw_weights(up.weight, f),))[0]
 
 
 def _new(x, H, W, C):
@@ -272,30 +270,20 @@ class DLASeg(nn.Module):              # pose_dla_dcn.py:532-570
             raise RuntimeError("ImageNet weights for dla34 need a network fetch (pose_dla_dcn.py:380-396); "
                                "load a checkpoint with load_state_dict instead")
 
-    # any change of parameters invalidates the packed/folded copies
-    def _invalidate(self):
+    # Packed / folded copies are stamped with the parameters' versions (ops.PackCache) and rebuild themselves; only
+    # a device / dtype move (`_apply`) or a write through `.data` needs the explicit reset below.
+    def invalidate_caches(self):
         self._cc = None
         for m in self.modules():
             if isinstance(m, DCN):
-                m._packed = None
-
-    def train(self, mode=True):
-        self._invalidate()
-        return super().train(mode)
+                m._packed.clear()
 
     def _apply(self, fn, *a, **k):
-        self._invalidate()
+        self.invalidate_caches()
         return super()._apply(fn, *a, **k)
-
-    def load_state_dict(self, *a, **k):
-        self._invalidate()
-        return super().load_state_dict(*a, **k)
 
     def forward_nhwc(self, x):
         """x [B,3,H,W] fp32 (CUDA) -> View of the [B,H/4,W/4,64] bf16 NHWC feature map."""
-        if self.training:
-            raise NotImplementedError("centernet_b200 DLASeg: training-mode forward/backward is not built yet "
-                                      "(inference engine only); call .eval()")
         if self._cc is None:
             self._cc = _Compiled()
         cc, b = self._cc, self.base
@@ -327,6 +315,17 @@ class DLASeg(nn.Module):              # pose_dla_dcn.py:532-570
         return y[-1]
 
     def forward(self, x):
+        """[B,3,H,W] fp32 -> [Tensor[B,64,H/4,W/4] fp32] (the plugin contract, pose_dla_dcn.py:561-570).
+        eval: the fused NHWC bf16 inference schedule above; train: the same operators on the autograd tape with
+        batch-statistics BatchNorm (exec_modes.TrainBackend); precision "fp32-strict": fp32 CUDA-core kernels."""
+        from .. import exec_modes
+        _lib_require_cuda(x)
+        if exec_modes.precision() == "fp32-strict":
+            if self.training:
+                raise RuntimeError("fp32-strict is an evaluation mode (parity checks); call .eval()")
+            return [exec_modes.run_dla_seg(self, x, exec_modes.StrictBackend())]
+        if self.training:
+            return [exec_modes.run_dla_seg(self, x, exec_modes.TrainBackend())]
         v = self.forward_nhwc(x)
         out = ops.to_nchw_f32(v)
         out._cnb_nhwc = v            # lets CenterHead skip the NCHW fp32 -> NHWC bf16 round trip

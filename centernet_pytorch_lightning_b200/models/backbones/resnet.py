@@ -14,15 +14,13 @@ buffers: tcgen05 implicit-GEMM convolutions with the folded BatchNorm / residual
 sampler kernel, a padded 3x3/2 max-pool, and every dense ConvTranspose2d(4, 2, 1) as ONE 3x3 convolution that
 produces the four output phases as channel blocks followed by a pixel shuffle (ops.deconv4x4s2).
 """
-import math
-
 import torch
 from torch import nn
 
 from ... import ops
 from ...DCN.dcn_v2 import DCN
 from ...ops import View
-from .pose_dla_dcn import BN_MOMENTUM, fold_bn
+from .pose_dla_dcn import BN_MOMENTUM, _bn_params, _fill_bilinear, fold_bn
 
 
 def _bn(c):
@@ -55,17 +53,6 @@ class Bottleneck(nn.Module):          # resnet_dcn.py:68-106, msra_resnet.py:64-
         self.bn3 = _bn(planes * 4)
         self.relu = nn.ReLU(inplace=True)
         self.downsample, self.stride = downsample, stride
-
-
-def fill_up_weights(up):              # resnet_dcn.py:109-118 (bilinear kernel in channel 0, copied to [c, 0])
-    w = up.weight.data
-    f = math.ceil(w.size(2) / 2)
-    c = (2 * f - 1 - f % 2) / (2.0 * f)
-    for i in range(w.size(2)):
-        for j in range(w.size(3)):
-            w[0, 0, i, j] = (1 - math.fabs(i / f - c)) * (1 - math.fabs(j / f - c))
-    for ch in range(1, w.size(0)):
-        w[ch, 0, :, :] = w[0, 0, :, :]
 
 
 resnet_spec = {18: (BasicBlock, [2, 2, 2, 2]), 34: (BasicBlock, [3, 4, 6, 3]), 50: (Bottleneck, [3, 4, 6, 3]),
@@ -107,7 +94,7 @@ class PoseResNet(nn.Module):
                 fc = DCN(self.inplanes, planes, kernel_size=(3, 3), stride=1, padding=1, dilation=1, deformable_groups=1)
                 up = nn.ConvTranspose2d(planes, planes, 4, stride=2, padding=1, output_padding=0,
                                         bias=self.deconv_with_bias)
-                fill_up_weights(up)
+                _fill_bilinear(up)     # resnet_dcn.py:109-118: the same separable bilinear kernel in every channel
                 layers += [fc, _bn(planes), nn.ReLU(inplace=True), up, _bn(planes), nn.ReLU(inplace=True)]
             else:          # msra_resnet.py:161-181
                 layers += [nn.ConvTranspose2d(self.inplanes, planes, 4, stride=2, padding=1, output_padding=0,
@@ -115,29 +102,23 @@ class PoseResNet(nn.Module):
             self.inplanes = planes
         return nn.Sequential(*layers)
 
-    # ---- cache invalidation (packed weights / folded BN) ---------------------------------------------------
-    def _invalidate(self):
+    # ---- packed weights / folded BN: version-stamped entries (ops.PackCache) ------------------------------
+    def invalidate_caches(self):
         self._cache = None
-
-    def train(self, mode=True):
-        self._invalidate()
-        return super().train(mode)
+        for m in self.modules():
+            if isinstance(m, DCN):
+                m._packed.clear()
 
     def _apply(self, fn, *a, **k):
-        self._invalidate()
+        self.invalidate_caches()
         return super()._apply(fn, *a, **k)
-
-    def load_state_dict(self, *a, **k):
-        self._invalidate()
-        return super().load_state_dict(*a, **k)
 
     # ---- engine ------------------------------------------------------------------------------------------------
     def _conv(self, conv, bn):
-        key = id(conv)
-        if key not in self._cache:
+        def build():
             w_kw = conv.kernel_size[1] + 1 if (conv.in_channels <= 8 and conv.kernel_size[1] > 1) else 0
-            self._cache[key] = (ops.pack_conv_weights(conv.weight, kw_pad=w_kw or None), *fold_bn(bn, conv.bias), w_kw)
-        return self._cache[key]
+            return (ops.pack_conv_weights(conv.weight, kw_pad=w_kw or None), *fold_bn(bn, conv.bias), w_kw)
+        return self._cache.get(id(conv), (conv.weight, conv.bias) + _bn_params(bn), build)
 
     def _cba(self, x, conv, bn, act=1, res=None):
         wpk, scale, shift, w_kw = self._conv(conv, bn)
@@ -155,11 +136,11 @@ class PoseResNet(nn.Module):
         return self._cba(h, blk.conv2, blk.bn2, act=1, res=residual)
 
     def _up(self, x, up, bn):
-        key = id(up)
-        if key not in self._cache:
-            self._cache[key] = (ops.pack_deconv4x4s2_weights(up.weight), *fold_bn(bn, up.bias))
-        wpk, scale, shift = self._cache[key]
-        return View(ops.deconv4x4s2(x, wpk, up.out_channels, scale, shift, act=1), up.out_channels, 0)
+        def build():   # scale/shift repeated once per output phase here, not per call
+            scale, shift = fold_bn(bn, up.bias)
+            return (ops.pack_deconv4x4s2_weights(up.weight), scale.repeat(4).contiguous(), shift.repeat(4).contiguous())
+        wpk, scale4, shift4 = self._cache.get(id(up), (up.weight, up.bias) + _bn_params(bn), build)
+        return View(ops.deconv4x4s2(x, wpk, up.out_channels, scale4, shift4, act=1), up.out_channels, 0)
 
     def forward_nhwc(self, x):
         """x [B,3,H,W] fp32 (CUDA) -> View of the [B,H/4,W/4,out_channels] bf16 NHWC feature map."""
@@ -167,7 +148,7 @@ class PoseResNet(nn.Module):
             raise NotImplementedError("centernet_b200 PoseResNet: training-mode forward/backward is not built yet "
                                       "(inference engine only); call .eval()")
         if self._cache is None:
-            self._cache = {}
+            self._cache = ops.PackCache()
         h = View(ops.to_nhwc_bf16(x, c_pad=8), 8, 0)
         h = self._cba(h, self.conv1, self.bn1)
         h = View(ops.maxpool2d_pad(h, 3, 2, 1), 64, 0)
@@ -179,10 +160,8 @@ class PoseResNet(nn.Module):
         for i in range(0, len(mods), step):
             if self.dcn:
                 fc, bn_fc, _, up, bn_up, _ = mods[i:i + 6]
-                key = id(fc)
-                if key not in self._cache:
-                    self._cache[key] = fold_bn(bn_fc, fc.bias)
-                scale, shift = self._cache[key]
+                scale, shift = self._cache.get(id(fc), (fc.bias,) + _bn_params(bn_fc),
+                                               lambda: fold_bn(bn_fc, fc.bias))
                 h = View(fc.forward_nhwc(h, scale=scale, shift=shift, act=1), fc.out_channels, 0)
                 h = self._up(h, up, bn_up)
             else:

@@ -14,21 +14,21 @@ from ..ops import View
 
 
 class HeadConv(nn.Module):
+    """3x3 conv (bias) -> ReLU -> 1x1 conv, parameters under `fc.0` / `fc.2` (heads.py:4-25)."""
+
     def __init__(self, out_channels: int, intermediate_channel: int, head_conv: int):
         super().__init__()
         self.out_channels = out_channels
-        self.fc = nn.Sequential(
-            nn.Conv2d(intermediate_channel, head_conv, kernel_size=3, padding=1, bias=True),
-            nn.ReLU(inplace=True),
-            nn.Conv2d(head_conv, out_channels, kernel_size=1, stride=1, padding=0),
-        )
+        self.fc = nn.Sequential(nn.Conv2d(intermediate_channel, head_conv, 3, padding=1),
+                                nn.ReLU(inplace=True),
+                                nn.Conv2d(head_conv, out_channels, 1))
 
     def fill_fc_weights(self):
-        for m in self.modules():
-            if isinstance(m, nn.Conv2d):
-                nn.init.normal_(m.weight, std=0.001)
-                if m.bias is not None:
-                    nn.init.constant_(m.bias, 0)
+        """N(0, 0.001) weights, zero biases (heads.py:17-22)."""
+        with torch.no_grad():
+            for conv in (self.fc[0], self.fc[2]):
+                conv.weight.normal_(std=0.001)
+                conv.bias.zero_()
 
     def forward(self, x):
         return CenterHead.run_heads({"_": self}, x)["_"]
@@ -39,40 +39,36 @@ class CenterHead(nn.Module):
         super().__init__()
         self.heads = heads
         for name, out_channel in heads.items():
-            self.__setattr__(name, HeadConv(out_channel, intermediate_channel, head_conv))
+            setattr(self, name, HeadConv(out_channel, intermediate_channel, head_conv))
         self.init_weights()
-        self._packed = None
+        self._packed = ops.PackCache()
 
     def init_weights(self):
-        for name in self.heads.keys():
+        """Heat-map heads keep the default conv init with the last bias at -2.19 (focal-loss prior); every other
+        head is N(0, 0.001) / zero bias (heads.py:44-50)."""
+        for name in self.heads:
+            head = getattr(self, name)
             if name.startswith("heatmap"):
-                self.__getattr__(name).fc[-1].bias.data.fill_(-2.19)
+                with torch.no_grad():
+                    head.fc[2].bias.fill_(-2.19)
             else:
-                self.__getattr__(name).fill_fc_weights()
+                head.fill_fc_weights()
 
-    def _invalidate(self):
-        self._packed = None
-
-    def train(self, mode=True):
-        self._invalidate()
-        return super().train(mode)
+    def invalidate_caches(self):
+        self._packed.clear()
 
     def _apply(self, fn, *a, **k):
-        self._invalidate()
+        self.invalidate_caches()
         return super()._apply(fn, *a, **k)
-
-    def load_state_dict(self, *a, **k):
-        self._invalidate()
-        return super().load_state_dict(*a, **k)
 
     @staticmethod
     def _pack(mods):
         with torch.no_grad():
             w3 = torch.cat([m.fc[0].weight for m in mods.values()], 0)
             b3 = torch.cat([m.fc[0].bias for m in mods.values()], 0).float().contiguous()
-            one = [(ops.pack_conv_weights(m.fc[2].weight), m.fc[2].bias.detach().float().contiguous())
-                   for m in mods.values()]
-        return ops.pack_conv_weights(w3), b3, one
+            one = [t for m in mods.values()
+                   for t in (ops.pack_conv_weights(m.fc[2].weight), m.fc[2].bias.detach().float().contiguous())]
+        return (ops.pack_conv_weights(w3), b3, *one)     # flat tuple of tensors (ops.PackCache refreshes in place)
 
     @staticmethod
     def run_heads(mods, x, packed=None, sigmoid=()):
@@ -82,20 +78,25 @@ class CenterHead(nn.Module):
             v = getattr(x, "_cnb_nhwc", None)
             x = v if v is not None else ops.to_nhwc_bf16(x)
         x = ops.as_view(x)
-        w3, b3, one = packed if packed is not None else CenterHead._pack(mods)
+        w3, b3, *one = packed if packed is not None else CenterHead._pack(mods)
         hc = next(iter(mods.values())).fc[0].out_channels
         mid = ops.conv2d(x, w3, hc * len(mods), 3, 1, 1, None, b3, act=1)
         ret = {}
         for i, (name, m) in enumerate(mods.items()):
-            w1, b1 = one[i]
+            w1, b1 = one[2 * i], one[2 * i + 1]
             ret[name] = ops.conv2d(View(mid, hc, i * hc), w1, m.out_channels, 1, 1, 0, None, b1,
                                    act=2 if name in sigmoid else 0, out_mode=1)
         return ret
 
     def forward(self, x, sigmoid=()):
+        from . import exec_modes
+        if exec_modes.precision() == "fp32-strict":
+            out = exec_modes.run_heads(self, x, exec_modes.StrictBackend())
+            return {k: (v.sigmoid_() if k in sigmoid else v) for k, v in out.items()}
         if self.training:
-            raise NotImplementedError("centernet_b200 CenterHead: training-mode forward is not built yet; call .eval()")
-        mods = {name: self.__getattr__(name) for name in self.heads.keys()}
-        if self._packed is None:
-            self._packed = self._pack(mods)
-        return self.run_heads(mods, x, self._packed, sigmoid)
+            out = exec_modes.run_heads(self, x, exec_modes.TrainBackend())
+            return {k: (v.sigmoid() if k in sigmoid else v) for k, v in out.items()}
+        mods = {name: getattr(self, name) for name in self.heads}
+        params = [p for m in mods.values() for p in (m.fc[0].weight, m.fc[0].bias, m.fc[2].weight, m.fc[2].bias)]
+        packed = self._packed.get("heads", params, lambda: self._pack(mods))
+        return self.run_heads(mods, x, packed, sigmoid)

@@ -105,6 +105,46 @@ def to_nchw_f32(v):
     return y
 
 
+def param_key(*tensors):
+    """(version, data_ptr) of every parameter a packed / folded copy was built from.  `_version` is bumped by every
+    in-place update autograd can see (optimizer steps, `load_state_dict` -- also through a parent module --,
+    `nn.init.*_`); writes through `.data` are invisible to it: call the model's `invalidate_caches()` after those."""
+    return tuple((t._version, t.data_ptr()) for t in tensors if t is not None)
+
+
+class PackCache:
+    """Packed-weight / folded-BN copies keyed by the owning module, each entry stamped with `param_key` of the
+    parameters it was built from and rebuilt when that changes.  A rebuilt entry is written IN PLACE into the old
+    tensors when shapes allow, so CUDA graphs that captured their addresses (engine.py) see the new weights."""
+
+    def __init__(self):
+        self.entries = {}
+
+    def get(self, key, params, build):
+        stamp = param_key(*params)
+        hit = self.entries.get(key)
+        if hit is not None and hit[0] == stamp:
+            return hit[1]
+        new = build()
+        if hit is not None:
+            old = hit[1]
+            same = len(old) == len(new) and all(
+                (not isinstance(o, torch.Tensor) and o == n) or
+                (isinstance(o, torch.Tensor) and isinstance(n, torch.Tensor) and o.shape == n.shape and o.dtype == n.dtype)
+                for o, n in zip(old, new))
+            if same:
+                with torch.no_grad():
+                    for o, n in zip(old, new):
+                        if isinstance(o, torch.Tensor):
+                            o.copy_(n)
+                new = old
+        self.entries[key] = (stamp, new)
+        return new
+
+    def clear(self):
+        self.entries.clear()
+
+
 def pack_conv_weights(w, kw_pad=None):
     """[Co,Ci,KH,KW] fp32 -> packed bf16 [Co_pad][Kpad] (K order kh,kw,ci; Ci padded to 8).
     `kw_pad` > KW appends zero filter columns first (pass the same value as `w_kw` to conv2d)."""
@@ -304,13 +344,14 @@ def pack_deconv4x4s2_weights(w):
     return pack_conv_weights(w3.reshape(4 * Co, Ci, 3, 3))
 
 
-def deconv4x4s2(x, wpk, Co, scale, shift, act=1):
+def deconv4x4s2(x, wpk, Co, scale4, shift4, act=1):
     """Dense ConvTranspose2d(4, stride 2, pad 1) + per-channel scale/shift (+ReLU): one 3x3 conv producing the
-    four output phases as channel blocks, then a pixel shuffle.  scale/shift are per output channel [Co]."""
+    four output phases as channel blocks, then a pixel shuffle.  scale4/shift4 are the per-output-channel vectors
+    repeated once per phase ([4*Co], built once at pack time: nothing that feeds a kernel prologue is produced
+    in-stream)."""
     x = as_view(x)
-    s4 = scale.repeat(4).contiguous() if scale is not None else None
-    b4 = shift.repeat(4).contiguous() if shift is not None else None
-    y4 = conv2d(x, wpk, 4 * Co, 3, 1, 1, s4, b4, act=act)
+    assert scale4 is None or scale4.numel() == 4 * Co
+    y4 = conv2d(x, wpk, 4 * Co, 3, 1, 1, scale4, shift4, act=act)
     y = torch.empty((x.B, 2 * x.H, 2 * x.W, Co), dtype=torch.bfloat16, device=x.buf.device)
     with torch.cuda.device(x.buf.device):
         _lib.check(_lib.lib().cnb_depth_to_space2(_lib.ptr(y4), _lib.ptr(y), x.B, x.H, x.W, Co, _stream(x.buf)),

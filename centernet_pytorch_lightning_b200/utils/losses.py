@@ -66,14 +66,20 @@ class _FocalLogitsFn(torch.autograd.Function):
 
 def focal_loss_with_logits(logits, gt):
     """== FocalLoss()(sigmoid_clamped(logits), gt) in one HBM pass (12 B/element fwd+bwd)."""
-    return _FocalLogitsFn.apply(logits, gt)
+    return _FocalLogitsFn.apply(_f32(logits), gt)
+
+
+def _f32(t):
+    """The kernels read fp32: an fp16 / bf16 prediction (AMP) is cast here, outside the autograd Function, so the
+    gradient is cast back to the input dtype by autograd itself."""
+    return t if t.dtype == torch.float32 else t.float()
 
 
 class FocalLoss(nn.Module):
     """`FocalLoss()(pred, gt)`; pred is the sigmoid-clamped heat map (losses.py:42-50)."""
 
     def forward(self, out, target):
-        return _FocalFn.apply(out, target)
+        return _FocalFn.apply(_f32(out), target)
 
 
 class _RegL1Fn(torch.autograd.Function):
@@ -117,11 +123,11 @@ class RegL1Loss(nn.Module):
     """losses.py:53-63: mask [B,M] bool expanded over channels."""
 
     def forward(self, output, mask, ind, target):
-        return _RegL1Fn.apply(output, mask, ind, target, False)
+        return _RegL1Fn.apply(_f32(output), mask, ind, target, False)
 
 
 class RegWeightedL1Loss(nn.Module):
     """losses.py:81-91: mask [B,M,C] float weights."""
 
     def forward(self, output, mask, ind, target):
-        return _RegL1Fn.apply(output, mask, ind, target, True)
+        return _RegL1Fn.apply(_f32(output), mask, ind, target, True)

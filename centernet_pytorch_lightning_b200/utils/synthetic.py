@@ -98,3 +98,39 @@ def randomize_(sd, seed=0, offset_gain=0.05, offset_bias=0.3):
         elif k.endswith(".bias"):
             v.copy_(torch.randn(v.shape, generator=g) * 0.1)
     return sd
+
+
+def ctdet_targets(B, C=80, H=128, W=128, n_obj=32, max_objs=128, seed=1234):
+    """COCO-shaped training targets of SURVEY.md 8(d) config 3 as torch CPU tensors: `heatmap` [B,C,H,W] (Gaussian
+    bumps composed by max, exactly 1 at object centres), `indices` [B,max_objs] int64, `regression_mask` bool,
+    `width_height`, `regression` [B,max_objs,2] -- the dict `CenterNetDetection.loss` consumes
+    (centernet_detection.py:97-130; encoded on the CPU by sample/ctdet.py:39-90 in the reference)."""
+    import torch
+
+    rng = np.random.default_rng(seed)
+    heat = np.zeros((B, C, H, W), np.float32)
+    ind = np.zeros((B, max_objs), np.int64)
+    mask = np.zeros((B, max_objs), bool)
+    wh = np.zeros((B, max_objs, 2), np.float32)
+    reg = np.zeros((B, max_objs, 2), np.float32)
+    yy, xx = np.mgrid[0:H, 0:W]
+    for b in range(B):
+        used = set()
+        for k in range(min(n_obj, max_objs)):
+            c = int(rng.integers(0, C))
+            cx, cy = int(rng.integers(0, W)), int(rng.integers(0, H))
+            if (c, cy, cx) in used:
+                continue
+            used.add((c, cy, cx))
+            w, h = 2 + 28 * rng.random(), 2 + 28 * rng.random()
+            rad = max(1, int(min(w, h) / 3))
+            sigma = (2 * rad + 1) / 6.0
+            g = np.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / (2 * sigma * sigma)).astype(np.float32)
+            g[(np.abs(xx - cx) > rad) | (np.abs(yy - cy) > rad)] = 0
+            np.maximum(heat[b, c], g, out=heat[b, c])
+            heat[b, c, cy, cx] = 1.0
+            ind[b, k], mask[b, k] = cy * W + cx, True
+            wh[b, k] = (w, h)
+            reg[b, k] = rng.random(2)
+    return {"heatmap": torch.from_numpy(heat), "indices": torch.from_numpy(ind), "regression_mask": torch.from_numpy(mask),
+            "width_height": torch.from_numpy(wh), "regression": torch.from_numpy(reg)}

@@ -137,16 +137,33 @@ typedef struct cnb_conv_desc {
                              rectangular filters run on the row-window kernel only (stride 1, Wo % 128 == 0). */
 } cnb_conv_desc;
 
-/* Data gradient of a stride-1 convolution (first piece of the training path): dX = cnb_conv2d_fprop(dY, W') with
- * W'[ci][co][kh][kw] = W[co][ci][KH-1-kh][KW-1-kw] packed by cnb_conv_pack_weights(Co'=Ci, Ci'=Co) and pad' = K-1-pad
- * (host mirror: ops.pack_conv_weights_dgrad / ops.conv2d_dgrad; parity: tests/test_conv_gpu.py::test_conv_dgrad_*).
- * Stride-2 dgrad and wgrad have no entry point yet. */
+/* Data gradient of a convolution = cnb_conv2d_fprop on a transformed filter (no separate kernel):
+ *   stride 1: dX = conv(dY, W') with W'[ci][co][kh][kw] = W[co][ci][KH-1-kh][KW-1-kw], pad' = K-1-pad
+ *             (host mirror: ops.pack_conv_weights_dgrad / ops.conv2d_dgrad);
+ *   stride 2 (3x3, pad 1, even input): the four output phases (dX[2i+a, 2j+b]) are the channel blocks of ONE 3x3
+ *             stride-1 convolution over dY with 4*Ci output channels, followed by cnb_depth_to_space2
+ *             (ops.pack_conv_weights_dgrad_s2 / ops.conv2d_dgrad_s2).
+ * Weight gradient: cnb_conv2d_wgrad below. */
 size_t cnb_conv_packed_weight_bytes(int Co, int Ci, int KH, int KW);
 /* w: [Co,Ci,KH,KW] fp32 (PyTorch layout, device) -> wpk bf16 device */
 int cnb_conv_pack_weights(const float* w, void* wpk, int Co, int Ci, int KH, int KW,
                           cnb_stream_t stream);
 int cnb_conv2d_fprop(const cnb_conv_desc* d, const void* x, const void* wpk, const float* scale,
                      const float* shift, const void* res, void* y, cnb_stream_t stream);
+
+/* Weight gradient (training path; what autograd gives the reference in centernet.py:70-80):
+ *   dW[co][kh][kw][ci] += sum over output pixels of dY[.., co] * X[.., shifted by (kh,kw), ci]
+ * tcgen05 GEMM with the pixel index as the contraction (both operands MN-major, the forward kernel's TMA im2col
+ * tiles reused as they lie).  `d` is the FORWARD convolution's descriptor (x geometry, Co, filter, stride, pad, w_kw);
+ * dy [B,Ho,Wo,dy_cstride] bf16 NHWC, channels [dy_coffset, dy_coffset+Co);  dw_acc fp32 [Co][KH*KWp*Ci] (KWp = w_kw
+ * or KW; K order (kh,kw,ci) = the packed-weight order) is ACCUMULATED into with vector reductions: zero it first.
+ * cnb_conv_unpack_wgrad turns it into the PyTorch layout [Co][Ci][KH][KW] fp32 (dw = (accumulate ? dw : 0) +
+ * scale * unpacked). */
+size_t cnb_conv_wgrad_acc_elems(int Co, int Ci_pad, int KH, int KWp);
+int cnb_conv2d_wgrad(const cnb_conv_desc* d, const void* x, const void* dy, int dy_cstride, int dy_coffset,
+                     float* dw_acc, cnb_stream_t stream);
+int cnb_conv_unpack_wgrad(const float* dw_acc, float* dw, int Co, int Ci, int Ci_pad, int KH, int KW, int KWp,
+                          int accumulate, float scale, cnb_stream_t stream);
 
 /* Modulated deformable convolution v2 (DCN.dcn_v2.DCN forward; call sites pose_dla_dcn.py:441-449,
  * resnet_dcn.py:202-210): 3x3, stride 1, pad 1, dil 1, deformable_groups 1.
@@ -185,6 +202,74 @@ int cnb_nchw_f32_to_nhwc_bf16(const float* x, void* y, int B, int C, int H, int 
                               cnb_stream_t stream);
 int cnb_nhwc_bf16_to_nchw_f32(const void* x, float* y, int B, int C, int H, int W, int x_cstride,
                               int x_coffset, cnb_stream_t stream);
+
+/* ---------------------------------------------------------------- training path (bandwidth-bound pieces) ---- */
+/* Train-mode nn.BatchNorm2d (pose_dla_dcn.py:40, momentum 0.1) fused with the residual add and ReLU that follow it.
+ * z [M,C] bf16 NHWC = conv output; y = act(bn(z) (+ res)).  stats [4][C] fp32 receives (mean, invstd, scale, shift)
+ * for the backward; running_mean/var are updated like PyTorch (unbiased variance; pass NULL to skip);
+ * sums_ws: 2*C floats of scratch. */
+int cnb_bn_train_fwd(const void* z, const float* gamma, const float* beta, float* running_mean,
+                     float* running_var, float momentum, float eps, const void* res, int act, void* y,
+                     float* stats, float* sums_ws, long long M, int C, cnb_stream_t stream);
+/* y = act(z * scale + shift (+ res)), per-channel fp32 scale/shift, NHWC bf16 */
+int cnb_scale_shift_act(const void* z, const float* scale, const float* shift, const void* res, int act,
+                        void* y, long long M, int C, cnb_stream_t stream);
+/* backward of the above: g = dy * (y > 0) (y_or_null == NULL: no ReLU); dz = scale*(g - mean(g) - xhat*mean(g*xhat));
+ * dres_or_null receives g (gradient of the residual branch); dgamma/dbeta fp32 [C] (+= if accumulate). */
+int cnb_bn_train_bwd(const void* dy, const void* y_or_null, const void* z, const float* stats, void* dz,
+                     void* dres_or_null, float* dgamma, float* dbeta, int accumulate, float* sums_ws,
+                     long long M, int C, cnb_stream_t stream);
+/* out[c] (+)= sum over pixels of dy[m][coffset + c] (* (y > 0) when y_mask_or_null is given): conv bias gradients */
+int cnb_channel_sum(const void* dy, int cstride, int coffset, const void* y_mask_or_null, float* out,
+                    int accumulate, long long M, int C, cnb_stream_t stream);
+int cnb_relu_bwd(const void* y, const void* dy, void* dx, long long n, cnb_stream_t stream);
+int cnb_add_bf16(const void* a, const void* b, void* out, long long n, cnb_stream_t stream);
+/* out = bf16(acc (+ addend)); with 0 < cvalid < cstride: channels >= cvalid of every [.., cstride] pixel are zeroed */
+int cnb_f32_to_bf16(const float* acc, const void* addend_or_null, void* out, long long n, int cstride,
+                    int cvalid, cnb_stream_t stream);
+/* nn.MaxPool2d(2, 2) backward (pose_dla_dcn.py:243): gradient to the first maximum of each window */
+int cnb_maxpool2x2_bwd(const void* x, const void* dy, void* dx, int B, int H, int W, int C, cnb_stream_t stream);
+/* depthwise ConvTranspose2d(C,C,2f,stride f,pad f/2) backward (pose_dla_dcn.py:466-475): dx, and dW accumulated into
+ * dwt_acc [(2f)^2][C] fp32 (zero it first); cnb_dw_deconv_unpack_wgrad -> [C,1,2f,2f]. */
+int cnb_dw_deconv_bwd(const void* x, const float* wt, const void* dy, void* dx, float* dwt_acc, int B, int H,
+                      int W, int C, int f, cnb_stream_t stream);
+int cnb_dw_deconv_unpack_wgrad(const float* dwt_acc, float* dw, int C, int f, int accumulate, cnb_stream_t stream);
+/* DCNv2 for training (DCN.dcn_v2.DCN backward; pose_dla_dcn.py:441-449): the sampled, modulated column matrix
+ * col [B*H*W][9*C] bf16 (K order (tap, ci)) is materialised so that y = conv1x1(col; W), dW and dcol are tensor-core
+ * GEMMs (cnb_conv2d_fprop / cnb_conv2d_wgrad); cnb_dcnv2_col2im turns dcol into dX (fp32, zero-filled here,
+ * scatter-added), and the gradients of the 27 raw offset/mask channels dom [B,H,W,om_cstride] fp32. */
+int cnb_dcnv2_im2col(const void* x, const float* om, int om_cstride, void* col, int B, int H, int W, int C,
+                     cnb_stream_t stream);
+int cnb_dcnv2_col2im(const void* x, const float* om, int om_cstride, const void* dcol, float* dx_acc,
+                     float* dom, int B, int H, int W, int C, cnb_stream_t stream);
+/* torch.optim.Adam step (centernet.py:94-95 defaults) on flat fp32 buffers; g is multiplied by grad_scale first
+ * (1/world_size after a sum all-reduce). */
+int cnb_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                  float beta2, float eps, int step, float grad_scale, cnb_stream_t stream);
+
+/* ---------------------------------------------------------------- fp32-strict mode (NCHW fp32, CUDA cores) ---- */
+/* The same operators in the reference's own precision, for small-shape END-TO-END parity checks against the fp32
+ * CPU path (hard part 2).  Not the measured fast path. */
+int cnb_strict_conv2d_f32(const float* x, const float* w, const float* scale, const float* shift,
+                          const float* res, float* y, int B, int Ci, int Hi, int Wi, int Co, int KH, int KW,
+                          int stride, int pad, int act, cnb_stream_t stream);
+int cnb_strict_dcn_im2col_f32(const float* x, const float* om, float* col, int B, int C, int H, int W,
+                              cnb_stream_t stream);
+int cnb_strict_conv_transpose2d_f32(const float* x, const float* w, const float* scale, const float* shift,
+                                    const float* add, float* y, int B, int Ci, int Hi, int Wi, int Co, int K,
+                                    int stride, int pad, int depthwise, int act, cnb_stream_t stream);
+int cnb_strict_maxpool2d_f32(const float* x, float* y, int BC, int H, int W, int k, int stride, int pad,
+                             cnb_stream_t stream);
+
+/* ---------------------------------------------------------------- decode primitives by name ---- */
+/* utils/decode.py:5-10 `_nms`; :13-40 the torch.topk inside `_topk` / `_topk_channel` (exact, sorted, ties by
+ * ascending index); :48-63 `_gather_feat` / `_transpose_and_gather_feat`.  ctdet_decode / multi_pose_decode fuse all
+ * of these and do not call them. */
+int cnb_nms3x3(const float* heat, float* out, long long planes, int H, int W, cnb_stream_t stream);
+int cnb_topk_rows(const float* scores, int rows, int n, int K, float* out_scores, long long* out_idx,
+                  cnb_stream_t stream);
+int cnb_gather_feat(const float* feat, const long long* ind, float* out, int B, int C, int N, int K,
+                    int feat_is_nchw, cnb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -17,9 +17,29 @@ import torch.nn.functional as F
 from torchvision.ops import deform_conv2d
 
 
+_TRAINING = False   # train-mode BatchNorm (batch statistics, running-stat update in `sd`): see `training(...)` below
+
+
+class training:
+    """`with net_torch.training():` runs the restatement like `module.train()`: BatchNorm normalises with batch
+    statistics and updates the running ones in the state dict (pose_dla_dcn.py:40, momentum 0.1); gradients flow to
+    every tensor of `sd` that requires grad (centernet.py:70-80)."""
+
+    def __init__(self, on=True):
+        self.on = on
+
+    def __enter__(self):
+        global _TRAINING
+        self.prev, _TRAINING = _TRAINING, self.on
+
+    def __exit__(self, *exc):
+        global _TRAINING
+        _TRAINING = self.prev
+
+
 def _bn(sd, p, x):
     return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],
-                        False, 0.1, 1e-5)
+                        _TRAINING, 0.1, 1e-5)
 
 
 def _conv(sd, p, x, stride=1):
@@ -37,7 +57,8 @@ def _tree(sd, p, levels, x, stride, level_root, children=None):
     children = [] if children is None else children
     bottom = F.max_pool2d(x, stride, stride) if stride > 1 else x
     residual = bottom
-    if (p + ".project.0.weight") in sd:
+    if (p + ".project.0.weight") in sd:   # (levels == 2: computed and never used, as in Tree.forward :254-255; in
+        # train mode its BatchNorm still updates the running statistics)
         residual = _bn(sd, p + ".project.1", _conv(sd, p + ".project.0", bottom))
     if level_root:
         children.append(bottom)

@@ -103,3 +103,104 @@ def ref_msra_resnet(num_layers):
 
     block, layers = msra_resnet.resnet_spec[num_layers]
     return msra_resnet.PoseResNet(block, layers)
+
+
+# ---- the LightningModule classes themselves (centernet.py, centernet_detection.py, centernet_multi_pose.py) --------
+def install_task_stubs():
+    """Stand-ins for what `CenterNet/centernet_detection.py:1-26` imports besides torch and the hot-path modules:
+    pytorch_lightning (a 30-line LightningModule: nn.Module + save_hyperparameters / hparams / log), imgaug,
+    pycocotools, and the augmentation package `CenterNet.transforms` (imgaug-based, CPU dataloader side, not on the hot
+    path; `transforms/sample.py:5` also fails to import on Python >= 3.10).  None of this touches the reference's
+    task classes, whose source runs unmodified."""
+    import collections
+    import collections.abc
+    import inspect
+
+    import torch
+
+    if not hasattr(collections, "Callable"):
+        collections.Callable = collections.abc.Callable
+
+    class _HParams(dict):
+        __getattr__ = dict.__getitem__
+
+    class LightningModule(torch.nn.Module):
+        def save_hyperparameters(self):
+            frame = inspect.currentframe().f_back
+            args = inspect.getargvalues(frame)
+            self.hparams = _HParams({k: args.locals[k] for k in args.args if k != "self"})
+
+        def log(self, *a, **k):
+            self.__dict__.setdefault("logged", []).append((a, k))
+
+    def fake(name, **attrs):
+        if name in sys.modules and not getattr(sys.modules[name], "_cnb_stub", False):
+            return sys.modules[name]
+        m = types.ModuleType(name)
+        m._cnb_stub = True
+        m.__path__ = []
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[name] = m
+        return m
+
+    class _Any:
+        def __init__(self, *a, **k):
+            pass
+
+        def __call__(self, *a, **k):
+            return a[0] if a else None
+
+    pl = fake("pytorch_lightning", LightningModule=LightningModule, Trainer=_Any, seed_everything=lambda *a, **k: None)
+    pl.callbacks = fake("pytorch_lightning.callbacks", ModelCheckpoint=_Any, LearningRateMonitor=_Any)
+    pl.loggers = fake("pytorch_lightning.loggers", TensorBoardLogger=_Any)
+    ia = fake("imgaug", seed=lambda *a, **k: None)
+    ia.augmenters = fake("imgaug.augmenters", Augmenter=_Any, Identity=_Any, Sequential=_Any)
+    ia.augmentables = fake("imgaug.augmentables", Keypoint=_Any, KeypointsOnImage=_Any, BoundingBox=_Any,
+                           BoundingBoxesOnImage=_Any)
+    pc = fake("pycocotools")
+    pc.cocoeval = fake("pycocotools.cocoeval", COCOeval=_Any)
+    pc.coco = fake("pycocotools.coco", COCO=_Any)
+    tr = fake("CenterNet.transforms", CategoryIdToClass=_Any, ImageAugmentation=_Any)
+    tr.sample = fake("CenterNet.transforms.sample", ComposeSample=_Any, MultiSampleTransform=_Any, PoseFlip=_Any)
+    fake("CenterNet.sample.multi_pose", MultiPoseSample=_Any)   # sample/multi_pose.py:74 breaks on numpy 2 (SURVEY 8c)
+
+
+def ref_tasks():
+    """(CenterNet, CenterNetDetection, CenterNetMultiPose) -- the reference's task classes, source unmodified, importing
+    whatever `CenterNet.models`, `CenterNet.utils.losses`, ... currently resolve to in sys.modules (the reference's own
+    modules after `install()`, or this repo's after `install_b200_swap()`)."""
+    install()
+    install_task_stubs()
+    import importlib
+
+    stub = sys.modules["CenterNet"]
+    for name in ("CenterNet.centernet", "CenterNet.centernet_detection", "CenterNet.centernet_multi_pose"):
+        sys.modules.pop(name, None)
+    base = importlib.import_module("CenterNet.centernet")
+    stub.CenterNet = base.CenterNet
+    det = importlib.import_module("CenterNet.centernet_detection")
+    pose = importlib.import_module("CenterNet.centernet_multi_pose")
+    return base.CenterNet, det.CenterNetDetection, pose.CenterNetMultiPose
+
+
+_SWAPPED = ("DCN", "DCN.dcn_v2", "CenterNet.models", "CenterNet.models.heads", "CenterNet.decode.ctdet",
+            "CenterNet.decode.multi_pose", "CenterNet.utils.losses", "CenterNet.utils.decode")
+
+
+def install_b200_swap():
+    """INTEGRATION.md section 1, executed: the hot-path modules of the reference resolve to this repo's package."""
+    install()
+    import centernet_pytorch_lightning_b200 as b
+
+    return b.install_swap()
+
+
+def remove_b200_swap(saved):
+    for k, v in saved.items():
+        if v is None:
+            sys.modules.pop(k, None)
+        else:
+            sys.modules[k] = v
+    for name in ("CenterNet.centernet", "CenterNet.centernet_detection", "CenterNet.centernet_multi_pose"):
+        sys.modules.pop(name, None)

@@ -212,3 +212,41 @@ def test_multi_pose_requires_hm_hp(cuda_dev):
         multi_pose_decode(_t(heat, dev), _t(wh, dev), _t(kps, dev), _t(reg, dev), None, None)
 
 
+
+
+def test_decode_primitives_by_name(cuda_dev):
+    """`_nms`, `_topk`, `_topk_channel`, `_gather_feat`, `_transpose_and_gather_feat` (utils/decode.py:5-63) as
+    stand-alone kernels vs the numpy oracle on tie-free maps: values, indices, classes bit-exact."""
+    from centernet_pytorch_lightning_b200.utils.decode import (_gather_feat, _nms, _topk, _topk_channel,
+                                                               _transpose_and_gather_feat)
+    heat, wh, _ = synthetic.ctdet_maps(2, 7, 24, 40, seed=31)
+    th = torch.from_numpy(heat).to(cuda_dev)
+    n = _nms(th)
+    assert np.array_equal(n.cpu().numpy(), decode_np.nms(heat))
+    for K in (1, 40, 100):
+        got = _topk(n, K=K)
+        want = decode_np.topk(decode_np.nms(heat), K)
+        for g, w, name in zip(got, want, ("score", "inds", "clses", "ys", "xs")):
+            assert np.array_equal(g.cpu().numpy().astype(np.float64), np.asarray(w).astype(np.float64)), (K, name)
+        assert got[1].dtype == torch.int64 and got[2].dtype == torch.int32
+    gc = _topk_channel(n, K=30)
+    wc = decode_np.topk_channel(decode_np.nms(heat), 30)
+    for g, w in zip(gc, wc):
+        assert np.array_equal(g.cpu().numpy().astype(np.float64), np.asarray(w).astype(np.float64))
+    ind = torch.from_numpy(np.random.default_rng(0).integers(0, 24 * 40, size=(2, 17))).to(cuda_dev)
+    tw = torch.from_numpy(wh).to(cuda_dev)
+    got = _transpose_and_gather_feat(tw, ind).cpu().numpy()
+    assert np.array_equal(got, decode_np.transpose_and_gather(wh, ind.cpu().numpy()))
+    feat = tw.permute(0, 2, 3, 1).reshape(2, -1, 2).contiguous()
+    assert np.array_equal(_gather_feat(feat, ind).cpu().numpy(), got)
+
+
+def test_ctdet_decode_host_entry(cuda_dev):
+    """`cnb_ctdet_decode_host`: host buffers in, host buffer out (H2D, decode, D2H inside the call)."""
+    import ctypes
+    from centernet_pytorch_lightning_b200 import _lib
+    heat, wh, reg = synthetic.ctdet_maps(3, 80, 32, 32, seed=41)
+    out = np.empty((3, 100, 6), np.float32)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)   # noqa: E731
+    _lib.check(_lib.lib().cnb_ctdet_decode_host(P(heat), P(wh), P(reg), P(out), 3, 80, 32, 32, 100), "cnb_ctdet_decode_host")
+    assert np.array_equal(out, decode_np.ctdet_decode(heat, wh, reg))

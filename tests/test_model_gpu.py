@@ -130,3 +130,30 @@ def test_resnet_backbones_match_oracle(cuda_dev, arch, B, H, W, head_conv):
         print(f"{arch} head {k} rel-L2 {l2:.4f} max-rel {mx:.4f}")
         assert l2 <= 3e-2 and mx <= 8e-2
     assert det.shape == (B, 100, 6) and torch.isfinite(det).all()
+
+
+def test_packed_weight_caches_follow_parameter_updates(cuda_dev):
+    """after one forward, (a) `parent.load_state_dict` (the reference's LightningModule owns `backbone` and
+    `heads`), (b) an in-place optimizer-style update, must both be visible to the next forward -- the packed / folded
+    copies are stamped with the parameters' versions (ops.PackCache)."""
+    m, h = _models(9)
+    parent = torch.nn.ModuleDict({"backbone": m, "heads": torch.nn.ModuleList([h])}).to(cuda_dev)
+    x = torch.rand(1, 3, 128, 128, generator=torch.Generator().manual_seed(1)).to(cuda_dev)
+
+    def run(p):
+        with torch.no_grad():
+            return p["heads"][0](p["backbone"](x)[-1])
+    first = run(parent)
+    m2, h2 = _models(10)
+    other = torch.nn.ModuleDict({"backbone": m2, "heads": torch.nn.ModuleList([h2])})
+    parent.load_state_dict(other.state_dict())
+    after = run(parent)
+    fresh = run(other.to(cuda_dev))
+    for k in HEADS:
+        assert torch.equal(after[k], fresh[k]), f"{k}: stale packed weights after parent.load_state_dict"
+        assert not torch.equal(after[k], first[k])
+    with torch.no_grad():                       # what an optimizer step does
+        for p in parent.parameters():
+            p.mul_(0.5)
+    halved = run(parent)
+    assert not torch.equal(halved["width_height"], after["width_height"])

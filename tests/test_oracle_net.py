@@ -7,6 +7,7 @@ import pytest
 import torch
 
 from oracle import net_torch, ref_shim
+from centernet_pytorch_lightning_b200.utils.synthetic import randomize_
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 HEADS = {"heatmap": 80, "width_height": 2, "regression": 2}
@@ -84,3 +85,36 @@ def test_resnet_schema_and_oracle_match_reference(arch, num_layers):
         want = ref(x)[-1]
         got = net_torch.pose_resnet_forward(sd, x, num_layers, arch == "resdcn")
     assert torch.equal(got, want)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="needs the reference checkout")
+def test_train_mode_oracle_equals_reference_dlaseg():
+    """`net_torch.training()` (batch-statistics BatchNorm, gradients to every tensor of the state dict) vs the
+    reference DLASeg in `.train()`: forward bit-equal, every parameter gradient within 1e-4, running statistics equal,
+    and the parameters the reference leaves without gradient (`level{3,4}.project`, dead in Tree.forward :254-255) get
+    none here either.  This pins the oracle tests/test_train_gpu.py compares the CUDA training path against."""
+    ref = ref_shim.ref_dlaseg().train()
+    randomize_(ref.state_dict(), 3)
+    sd = {k: v.clone() for k, v in ref.state_dict().items()}
+    for k, v in sd.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+    x = torch.rand(2, 3, 64, 64, generator=torch.Generator().manual_seed(0))
+    y_ref = ref(x)[-1]
+    (y_ref ** 2).sum().backward()
+    with net_torch.training():
+        y = net_torch.dla34_seg_forward(sd, x)
+    (y ** 2).sum().backward()
+    assert torch.equal(y, y_ref)
+    dead = []
+    for k, p in ref.named_parameters():
+        g = sd[k].grad
+        if p.grad is None:
+            dead.append(k)
+            assert g is None or float(g.abs().max()) == 0.0, k
+        else:
+            assert torch.allclose(g, p.grad, rtol=1e-4, atol=1e-6), k
+    assert sorted(dead) == sorted(f"base.level{l}.project.{s}" for l in (3, 4) for s in ("0.weight", "1.weight", "1.bias"))
+    for k, b in ref.named_buffers():
+        if not k.endswith("num_batches_tracked"):
+            assert torch.allclose(sd[k], b), k

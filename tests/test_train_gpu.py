@@ -1,0 +1,311 @@
+"""-m gpu parity of the TRAINING path (centernet.py:70-80: forward -> loss -> backward) against PyTorch fp32 autograd
+on the CPU, operator by operator and through the whole DLA-34 + heads + losses step.
+
+Operands are rounded to bf16 first so that both sides multiply the same numbers; what remains is fp32 accumulation
+order (GEMMs: <= 2e-3 of the largest gradient entry) and the bf16 rounding of stored activations / data gradients
+(<= 2^-8 relative).  Tolerances are written at each assert.  DCNv2 is pinned to torchvision's CPU `deform_conv2d`
+autograd (the reference's own extension, tteepe/DCNv2, is not vendored: "parity unpinned").
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from centernet_pytorch_lightning_b200 import autograd_ops as ag
+from centernet_pytorch_lightning_b200 import ops
+from centernet_pytorch_lightning_b200.DCN.dcn_v2 import DCN
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+def _r(t):                      # round to bf16, keep fp32
+    return t.to(BF).float()
+
+
+def _nhwc(t, dev):              # [B,C,H,W] fp32 (bf16-representable) -> NHWC bf16 on the device
+    return t.permute(0, 2, 3, 1).contiguous().to(BF).to(dev)
+
+
+def _nchw(t):                   # NHWC (any dtype, device) -> [B,C,H,W] fp32 on the CPU
+    return t.float().cpu().permute(0, 3, 1, 2).contiguous()
+
+
+def _close(got, ref, tol, what):
+    got, ref = got.float().cpu(), ref.float()
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-12
+    print(f"{what}: max err {err:.3e} / max |ref| {scale:.3e} = {err / scale:.2e}")
+    assert err <= tol * scale, f"{what}: {err / scale:.3e} > {tol}"
+
+
+@pytest.mark.parametrize("Ci,Co,k,s,H,W,B", [
+    (64, 64, 3, 1, 32, 32, 2), (128, 256, 3, 1, 16, 16, 2), (64, 128, 3, 2, 32, 32, 2), (256, 64, 1, 1, 16, 16, 2),
+    (16, 16, 3, 1, 64, 64, 1), (16, 32, 3, 2, 64, 64, 1), (32, 64, 3, 2, 64, 64, 1), (64, 64, 3, 1, 128, 128, 3),
+    (512, 512, 3, 1, 8, 8, 2), (1280, 512, 1, 1, 8, 8, 2), (64, 64, 3, 1, 24, 40, 1)])
+def test_conv_forward_backward(cuda_dev, Ci, Co, k, s, H, W, B):
+    g = torch.Generator().manual_seed(Ci * 7 + Co)
+    conv = nn.Conv2d(Ci, Co, k, s, k // 2, bias=False)
+    with torch.no_grad():
+        conv.weight.copy_(_r(torch.randn(conv.weight.shape, generator=g) / (Ci * k * k) ** 0.5))
+    x = _r(torch.randn(B, Ci, H, W, generator=g)).requires_grad_(True)
+    y = conv(x)
+    dy = _r(torch.randn(y.shape, generator=g))
+    y.backward(dy)
+    gconv = nn.Conv2d(Ci, Co, k, s, k // 2, bias=False)
+    gconv.load_state_dict(conv.state_dict())
+    gconv = gconv.to(cuda_dev)
+    xg = _nhwc(x.detach(), cuda_dev).requires_grad_(True)
+    yg = ag.conv(xg, gconv)
+    yg.backward(_nhwc(dy, cuda_dev))
+    torch.cuda.synchronize()
+    _close(_nchw(yg), y.detach(), 1e-2, "y")                 # bf16 store
+    _close(gconv.weight.grad, conv.weight.grad, 2e-3, "dW")    # fp32 accumulate, fp32 out
+    _close(_nchw(xg.grad), x.grad, 1e-2, "dX")               # bf16 store
+
+
+def test_stem_conv_wgrad(cuda_dev):
+    """3 -> 16, 7x7 on the 8-channel padded image (packed 7x8): weight gradient only (the image needs none)."""
+    g = torch.Generator().manual_seed(5)
+    conv = nn.Conv2d(3, 16, 7, 1, 3, bias=False)
+    with torch.no_grad():
+        conv.weight.copy_(_r(conv.weight))
+    x = _r(torch.rand(2, 3, 64, 96, generator=g))
+    y = conv(x)
+    dy = _r(torch.randn(y.shape, generator=g))
+    y.backward(dy)
+    gconv = nn.Conv2d(3, 16, 7, 1, 3, bias=False)
+    gconv.load_state_dict(conv.state_dict())
+    gconv = gconv.to(cuda_dev)
+    xg = ops.to_nhwc_bf16(x.to(cuda_dev), c_pad=8)
+    yg = ag.conv(xg, gconv)
+    yg.backward(_nhwc(dy, cuda_dev))
+    _close(_nchw(yg), y.detach(), 1e-2, "y")
+    _close(gconv.weight.grad, conv.weight.grad, 2e-3, "dW stem")
+
+
+@pytest.mark.parametrize("Co,out_mode", [(80, 1), (2, 1), (27, 2)])
+def test_conv_bias_fp32_outputs(cuda_dev, Co, out_mode):
+    """Head 1x1 convs (NCHW fp32 out) and the DCN offset/mask conv (NHWC fp32 out, 27 of 32 channels): y, dX, dW, db."""
+    g = torch.Generator().manual_seed(Co)
+    k = 1 if out_mode == 1 else 3
+    Ci = 256 if out_mode == 1 else 64
+    conv = nn.Conv2d(Ci, Co, k, 1, k // 2, bias=True)
+    with torch.no_grad():
+        conv.weight.copy_(_r(torch.randn(conv.weight.shape, generator=g) / (Ci * k * k) ** 0.5))
+        conv.bias.copy_(torch.randn(Co, generator=g))
+    x = _r(torch.randn(2, Ci, 16, 24, generator=g)).requires_grad_(True)
+    y = conv(x)
+    dy = _r(torch.randn(y.shape, generator=g))
+    y.backward(dy)
+    gconv = nn.Conv2d(Ci, Co, k, 1, k // 2, bias=True)
+    gconv.load_state_dict(conv.state_dict())
+    gconv = gconv.to(cuda_dev)
+    xg = _nhwc(x.detach(), cuda_dev).requires_grad_(True)
+    yg = ag.conv(xg, gconv, out_mode=out_mode)
+    if out_mode == 1:
+        assert yg.shape == y.shape and yg.dtype == torch.float32
+        _close(yg, y.detach(), 2e-3, "y")
+        yg.backward(dy.to(cuda_dev))
+    else:
+        assert yg.shape == (2, 16, 24, 32) and yg.dtype == torch.float32
+        _close(_nchw(yg[..., :Co]), y.detach(), 2e-3, "y")
+        dyg = torch.zeros_like(yg)
+        dyg[..., :Co] = dy.permute(0, 2, 3, 1).to(cuda_dev)
+        dyg[..., Co:] = 7.0          # garbage in the padding channels must be ignored
+        yg.backward(dyg)
+    _close(gconv.weight.grad, conv.weight.grad, 2e-3, "dW")
+    _close(gconv.bias.grad, conv.bias.grad, 2e-3, "db")
+    _close(_nchw(xg.grad), x.grad, 1e-2, "dX")
+
+
+@pytest.mark.parametrize("C,H,W,B,act,with_res", [(64, 32, 32, 2, 1, True), (16, 64, 64, 2, 1, False),
+                                                   (512, 8, 8, 2, 0, False), (128, 16, 24, 3, 1, True)])
+def test_batchnorm_train(cuda_dev, C, H, W, B, act, with_res):
+    g = torch.Generator().manual_seed(C)
+    bn = nn.BatchNorm2d(C, momentum=0.1)
+    with torch.no_grad():
+        bn.weight.copy_(0.5 + torch.rand(C, generator=g))
+        bn.bias.copy_(torch.randn(C, generator=g) * 0.2)
+        bn.running_mean.copy_(torch.randn(C, generator=g) * 0.1)
+        bn.running_var.copy_(0.5 + torch.rand(C, generator=g))
+    gbn = nn.BatchNorm2d(C, momentum=0.1)
+    gbn.load_state_dict(bn.state_dict())
+    gbn = gbn.to(cuda_dev).train()
+    z = _r(torch.randn(B, C, H, W, generator=g) * 1.5 + 0.3).requires_grad_(True)
+    res = _r(torch.randn(B, C, H, W, generator=g)).requires_grad_(True) if with_res else None
+    y = bn.train()(z)
+    if with_res:
+        y = y + res
+    if act:
+        y = F.relu(y)
+    dy = _r(torch.randn(y.shape, generator=g))
+    y.backward(dy)
+    zg = _nhwc(z.detach(), cuda_dev).requires_grad_(True)
+    rg = _nhwc(res.detach(), cuda_dev).requires_grad_(True) if with_res else None
+    yg = ag.bn_act(zg, gbn, res=rg, act=act)
+    yg.backward(_nhwc(dy, cuda_dev))
+    _close(_nchw(yg), y.detach(), 1e-2, "y")
+    _close(gbn.running_mean, bn.running_mean, 1e-4, "running_mean")
+    _close(gbn.running_var, bn.running_var, 1e-4, "running_var")
+    assert int(gbn.num_batches_tracked) == 1
+    # the ReLU mask is taken from the bf16-rounded output: entries within rounding of 0 may flip -> compare in L2
+    ref_dz, got_dz = z.grad, _nchw(zg.grad)
+    rel = ((got_dz - ref_dz).norm() / ref_dz.norm()).item()
+    print(f"dz rel-L2 {rel:.3e}")
+    assert rel <= 2e-2
+    _close(gbn.weight.grad, bn.weight.grad, 1e-2, "dgamma")
+    _close(gbn.bias.grad, bn.bias.grad, 1e-2, "dbeta")
+    if with_res:
+        rel = ((_nchw(rg.grad) - res.grad).norm() / res.grad.norm()).item()
+        assert rel <= 2e-2
+
+
+def test_maxpool_backward(cuda_dev):
+    g = torch.Generator().manual_seed(1)
+    x = _r(torch.randn(2, 32, 16, 24, generator=g)).requires_grad_(True)
+    y = F.max_pool2d(x, 2, 2)
+    dy = _r(torch.randn(y.shape, generator=g))
+    y.backward(dy)
+    xg = _nhwc(x.detach(), cuda_dev).requires_grad_(True)
+    yg = ag.maxpool2(xg)
+    yg.backward(_nhwc(dy, cuda_dev))
+    assert torch.equal(_nchw(yg), y.detach())
+    assert torch.equal(_nchw(xg.grad), x.grad)
+
+
+@pytest.mark.parametrize("C,f,H,W", [(64, 2, 16, 16), (128, 2, 8, 12), (64, 4, 8, 8), (256, 2, 4, 4)])
+def test_depthwise_upsampling_backward(cuda_dev, C, f, H, W):
+    g = torch.Generator().manual_seed(C + f)
+    up = nn.ConvTranspose2d(C, C, 2 * f, stride=f, padding=f // 2, groups=C, bias=False)
+    with torch.no_grad():
+        up.weight.copy_(_r(torch.rand(up.weight.shape, generator=g)))
+    x = _r(torch.randn(2, C, H, W, generator=g)).requires_grad_(True)
+    add = _r(torch.randn(2, C, H * f, W * f, generator=g)).requires_grad_(True)
+    y = up(x) + add
+    dy = _r(torch.randn(y.shape, generator=g))
+    y.backward(dy)
+    gup = nn.ConvTranspose2d(C, C, 2 * f, stride=f, padding=f // 2, groups=C, bias=False)
+    gup.load_state_dict(up.state_dict())
+    gup = gup.to(cuda_dev)
+    xg = _nhwc(x.detach(), cuda_dev).requires_grad_(True)
+    ag_add = _nhwc(add.detach(), cuda_dev).requires_grad_(True)
+    yg = ag.dw_up(xg, gup, f, add=ag_add)
+    yg.backward(_nhwc(dy, cuda_dev))
+    _close(_nchw(yg), y.detach(), 1e-2, "y")
+    _close(_nchw(xg.grad), x.grad, 1e-2, "dX")
+    _close(gup.weight.grad, up.weight.grad, 2e-3, "dW")
+    assert torch.equal(_nchw(ag_add.grad), add.grad)
+
+
+@pytest.mark.parametrize("Ci,Co,H,W,B,gain", [(64, 64, 16, 16, 2, 0.5), (128, 64, 12, 20, 1, 1.0), (256, 128, 8, 8, 2, 2.0)])
+def test_dcn_forward_backward(cuda_dev, Ci, Co, H, W, B, gain):
+    """DCNv2 training op vs torchvision.ops.deform_conv2d autograd on the CPU (offsets of up to a few pixels, so
+    samples cross the image border): y, dX (both paths: sampling and offset conv), dW, db, d(conv_offset_mask)."""
+    from torchvision.ops import deform_conv2d
+    g = torch.Generator().manual_seed(Ci + Co)
+    m = DCN(Ci, Co, (3, 3), 1, 1)
+    with torch.no_grad():
+        m.weight.copy_(_r(m.weight))
+        m.bias.copy_(torch.randn(Co, generator=g) * 0.1)
+        m.conv_offset_mask.weight.copy_(_r(torch.randn(m.conv_offset_mask.weight.shape, generator=g) * gain / (Ci * 9) ** 0.5))
+        m.conv_offset_mask.bias.copy_(torch.randn(27, generator=g) * 0.3)
+    x = _r(torch.randn(B, Ci, H, W, generator=g)).requires_grad_(True)
+    om = F.conv2d(x, m.conv_offset_mask.weight, m.conv_offset_mask.bias, padding=1)
+    o1, o2, mk = torch.chunk(om, 3, dim=1)
+    y = deform_conv2d(x, torch.cat((o1, o2), 1), m.weight, m.bias, padding=1, mask=torch.sigmoid(mk))
+    dy = _r(torch.randn(y.shape, generator=g))
+    y.backward(dy)
+    ref = {n: p.grad.clone() for n, p in m.named_parameters()}
+    for p in m.parameters():
+        p.grad = None
+    gm = DCN(Ci, Co, (3, 3), 1, 1)
+    gm.load_state_dict(m.state_dict())
+    gm = gm.to(cuda_dev).train()
+    xg = _nhwc(x.detach(), cuda_dev).requires_grad_(True)
+    yg = ag.dcn(xg, gm)
+    yg.backward(_nhwc(dy, cuda_dev))
+    torch.cuda.synchronize()
+    # the offset/mask map is computed from bf16 operands in fp32 on both sides; columns are rounded to bf16 before the
+    # GEMM on the GPU side -> 2^-8 relative on y; gradients inherit it
+    _close(_nchw(yg), y.detach(), 2e-2, "y")
+    _close(gm.weight.grad, ref["weight"], 2e-2, "dW")
+    _close(gm.bias.grad, ref["bias"], 2e-3, "db")
+    rel = ((_nchw(xg.grad) - x.grad).norm() / x.grad.norm()).item()
+    print(f"dX rel-L2 {rel:.3e}")
+    assert rel <= 2e-2
+    for n in ("conv_offset_mask.weight", "conv_offset_mask.bias"):
+        got = dict(gm.named_parameters())[n].grad.float().cpu()
+        rel = ((got - ref[n]).norm() / (ref[n].norm() + 1e-12)).item()
+        print(f"d {n} rel-L2 {rel:.3e}")
+        assert rel <= 3e-2
+
+
+def test_dla34_training_step_matches_oracle(cuda_dev):
+    """Whole path: DLA-34 (train-mode BatchNorm) -> ctdet heads -> sigmoid_clamped -> FocalLoss + 2 x RegL1Loss ->
+    backward, against the fp32 CPU oracle (oracle/net_torch.py under `training()`, pinned bit-for-bit to the reference
+    module in tests/test_oracle_net.py).  bf16 activations through ~60 layers: loss within 2 %, parameter gradients
+    compared per tensor in relative L2 (median <= 6 %, every tensor with a non-negligible gradient <= 35 %), running
+    statistics within 2 %."""
+    from centernet_pytorch_lightning_b200.models import create_model
+    from centernet_pytorch_lightning_b200.models.heads import CenterHead
+    from centernet_pytorch_lightning_b200.utils.decode import sigmoid_clamped
+    from centernet_pytorch_lightning_b200.utils.losses import FocalLoss, RegL1Loss
+    from centernet_pytorch_lightning_b200.utils.synthetic import randomize_, ctdet_targets
+    from oracle import net_torch, task_torch
+    heads = {"heatmap": 80, "width_height": 2, "regression": 2}
+    torch.manual_seed(0)
+    model, head = create_model("dla_34"), CenterHead(heads, 64, 256)
+    randomize_(model.state_dict(), 7, offset_gain=0.02)
+    randomize_(head.state_dict(), 8)
+    B, H, W = 2, 128, 128
+    x = torch.rand(B, 3, H, W, generator=torch.Generator().manual_seed(3))
+    tgt = ctdet_targets(B, 80, H // 4, W // 4, n_obj=12, seed=4)
+    # ---- oracle (CPU fp32)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    hd = {k: v.clone() for k, v in head.state_dict().items()}
+    for d in (sd, hd):
+        for k, v in d.items():
+            if v.is_floating_point() and "running" not in k:
+                v.requires_grad_(True)
+    with net_torch.training():
+        o = net_torch.center_head_forward(hd, net_torch.dla34_seg_forward(sd, x), heads)
+    ref_loss = task_torch.ctdet_loss_torch(o, tgt)
+    ref_loss.backward()
+    # ---- engine
+    model, head = model.to(cuda_dev).train(), head.to(cuda_dev).train()
+    out = head(model(x.to(cuda_dev))[-1])
+    t = {k: v.to(cuda_dev) for k, v in tgt.items()}
+    hm = sigmoid_clamped(out["heatmap"])
+    loss = FocalLoss()(hm, t["heatmap"]) + 0.1 * RegL1Loss()(out["width_height"], t["regression_mask"], t["indices"],
+                                                             t["width_height"]) \
+        + RegL1Loss()(out["regression"], t["regression_mask"], t["indices"], t["regression"])
+    loss.backward()
+    torch.cuda.synchronize()
+    print(f"loss engine {loss.item():.5f} oracle {ref_loss.item():.5f}")
+    assert abs(loss.item() - ref_loss.item()) <= 2e-2 * abs(ref_loss.item())
+    rels, worst = [], (0.0, "")
+    gmax = max(v.grad.abs().max().item() for d in (sd, hd) for v in d.values() if v.grad is not None)
+    for d, mod in ((sd, model), (hd, head)):
+        for name, p in mod.named_parameters():
+            rg = d[name].grad
+            if rg is None:
+                assert p.grad is None or float(p.grad.abs().max()) == 0.0, name
+                continue
+            assert p.grad is not None, f"{name}: no gradient"
+            if rg.abs().max().item() < 1e-4 * gmax:
+                continue
+            rel = ((p.grad.float().cpu() - rg).norm() / (rg.norm() + 1e-20)).item()
+            rels.append(rel)
+            if rel > worst[0]:
+                worst = (rel, name)
+    rels = np.array(rels)
+    print(f"{len(rels)} gradient tensors: median rel-L2 {np.median(rels):.3f}, p90 {np.percentile(rels, 90):.3f}, "
+          f"worst {worst[0]:.3f} ({worst[1]})")
+    assert np.median(rels) <= 6e-2 and worst[0] <= 0.35
+    for name, b in model.named_buffers():
+        if name.endswith("running_mean") or name.endswith("running_var"):
+            ref = sd[name]
+            err = (b.float().cpu() - ref).abs().max().item()
+            assert err <= 2e-2 * (ref.abs().max().item() + 1e-3) + 2e-3, (name, err)
