@@ -303,6 +303,14 @@ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 TmaDriver& tma_driver() {
   static TmaDriver drv;
   static std::once_flag once;
+  // cuTensorMapEncode* are DRIVER entry points and need a context current on the calling thread; a thread that has
+  // only ever seen runtime calls that do not touch the device (autograd's backward worker before its first kernel)
+  // has none yet and the encoders return CUDA_ERROR_INVALID_CONTEXT (measured).  cudaFree(0) binds the primary context.
+  thread_local bool bound = false;
+  if (!bound) {
+    cudaFree(0);
+    bound = true;
+  }
   std::call_once(once, [] {
     cudaDriverEntryPointQueryResult q1, q2;
     void *p1 = nullptr, *p2 = nullptr;

