@@ -241,7 +241,7 @@ def train_leg(args, rank, world, dev, steps, warmup, with_e2e=True):
     """configs[2]: one optimisation step per 16-image batch and rank.  Returns a dict (rank 0: full; others: None)."""
     import torch
     from centernet_pytorch_lightning_b200 import _lib
-    from centernet_pytorch_lightning_b200.trainer import FlatTrainer, ctdet_training_step
+    from centernet_pytorch_lightning_b200.trainer import FlatTrainer, GraphedCtdetStep, ctdet_training_step
     from centernet_pytorch_lightning_b200.utils.synthetic import ctdet_targets
 
     B, R = TRAIN["batch"], TRAIN["res"]
@@ -254,29 +254,42 @@ def train_leg(args, rank, world, dev, steps, warmup, with_e2e=True):
               for i in range(2)]
     x_dev = [t.to(dev) for t in x_host]
     t_dev = [{k: v.to(dev) for k, v in t.items()} for t in t_host]
+    if args.no_graph:
+        do_step = lambda x, t: ctdet_training_step(model, head, trainer, x, t)   # noqa: E731
+    else:   # the public training API: the whole step (fwd, losses, bwd, all-reduce, Adam) replayed as one CUDA graph
+        do_step = GraphedCtdetStep(model, head, trainer, B, R)
     losses = []
     for i in range(warmup):
-        losses.append(ctdet_training_step(model, head, trainer, x_dev[i % 2], t_dev[i % 2]))
+        losses.append(do_step(x_dev[i % 2], t_dev[i % 2]).clone())
     sync_all(world)
     n0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
-        losses.append(ctdet_training_step(model, head, trainer, x_dev[i % 2], t_dev[i % 2]))
+        losses.append(do_step(x_dev[i % 2], t_dev[i % 2]).clone())
     e1.record()
     sync_all(world)
     launches = _lib.launch_count() - n0
+    if not args.no_graph:      # replayed kernels are not counted by the library: count one eager twin of the step
+        snap = do_step._snapshot()
+        n1 = _lib.launch_count()
+        ctdet_training_step(model, head, trainer, x_dev[0], t_dev[0])
+        launches = (_lib.launch_count() - n1) * steps
+        do_step._restore(snap)
     ms_total = max_over_ranks(e0.elapsed_time(e1), dev, world)
     overlapped = len(trainer.launch_log)
     # the same steps without the collective (world forced to 1 on the reducer): the difference is the exposed all-reduce
     exposed_ms = None
     if world > 1:
         trainer.world = 1
+        nocoll = do_step if args.no_graph else GraphedCtdetStep(model, head, trainer, B, R)
+        for i in range(2):
+            nocoll(x_dev[i % 2], t_dev[i % 2])
         sync_all(world)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for i in range(steps):
-            ctdet_training_step(model, head, trainer, x_dev[i % 2], t_dev[i % 2])
+            nocoll(x_dev[i % 2], t_dev[i % 2])
         b.record()
         sync_all(world)
         ms_nocoll = max_over_ranks(a.elapsed_time(b), dev, world)
@@ -285,20 +298,20 @@ def train_leg(args, rank, world, dev, steps, warmup, with_e2e=True):
     # end to end: batch and targets from pinned host memory every step, loss read back every step
     e2e_value, h2d = None, None
     if with_e2e:
-        xs = torch.empty_like(x_dev[0])
-        ts = {k: torch.empty_like(v) for k, v in t_dev[0].items()}
         sync_all(world)
         t0 = time.perf_counter()
         for i in range(steps):
-            xs.copy_(x_host[i % 2], non_blocking=True)
-            for k in ts:
-                ts[k].copy_(t_host[i % 2][k], non_blocking=True)
-            loss = ctdet_training_step(model, head, trainer, xs, ts)
+            if args.no_graph:
+                xs = x_host[i % 2].to(dev, non_blocking=True)
+                ts = {k: v.to(dev, non_blocking=True) for k, v in t_host[i % 2].items()}
+                loss = do_step(xs, ts)
+            else:
+                loss = do_step(x_host[i % 2], t_host[i % 2])   # pinned host -> the graph's static input buffers (H2D)
             float(loss)                                   # D2H + sync: the caller logs the loss (centernet.py:75)
         sync_all(world)
         t_e2e = max_over_ranks(time.perf_counter() - t0, dev, world)
         e2e_value = world * B * steps / t_e2e
-        h2d = xs.numel() * 4 + sum(v.numel() * v.element_size() for v in ts.values())
+        h2d = x_host[0].numel() * 4 + sum(v.numel() * v.element_size() for v in t_host[0].values())
     if rank != 0:
         return None
     value = world * B * steps / (ms_total / 1e3)
@@ -317,7 +330,7 @@ def train_leg(args, rank, world, dev, steps, warmup, with_e2e=True):
         "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "how": "pinned host image batch + target dict -> H2D every step, loss scalar D2H + sync every step"},
         "gpu_launches": int(launches),
-        "launch": "eager (autograd tape; not graph-captured)",
+        "launch": "eager (autograd tape)" if args.no_graph else "CUDA graph replay of the whole step (trainer.GraphedCtdetStep)",
         "precision": "bf16 activations / operands, fp32 accumulation, fp32 master weights, gradients and Adam state",
     }
 

@@ -25,6 +25,12 @@ class ConvDesc(Structure):
         "act", "out_nchw_f32", "w_kw", "pad_w1")]
 
 
+class HeadDesc(Structure):
+    """Mirror of `cnb_head_desc` (include/centernet_b200.h)."""
+    _fields_ = [(n, c_int) for n in ("B", "H", "W", "Ci", "x_cstride", "x_coffset", "head_conv", "nheads")] + \
+               [("c_out", c_int * 8), ("act", c_int * 8)]
+
+
 def _declare(lib):
     P = c_void_p
     sigs = {
@@ -45,6 +51,8 @@ def _declare(lib):
         "cnb_conv_packed_weight_bytes": (c_size_t, [c_int] * 4),
         "cnb_conv_pack_weights": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
         "cnb_conv2d_fprop": (c_int, [POINTER(ConvDesc), P, P, P, P, P, P, P]),
+        "cnb_head_fused_supported": (c_int, [POINTER(HeadDesc)]),
+        "cnb_head_fused_fprop": (c_int, [POINTER(HeadDesc), P, P, P, P, P, P, P]),
         "cnb_dcnv2_fprop": (c_int, [POINTER(ConvDesc), P, P, c_int, P, P, P, P, P]),
         "cnb_maxpool2d": (c_int, [P, P] + [c_int] * 9 + [P]),
         "cnb_maxpool2d_pad": (c_int, [P, P] + [c_int] * 7 + [P]),
@@ -69,7 +77,7 @@ def _declare(lib):
         "cnb_dw_deconv_unpack_wgrad": (c_int, [P, P, c_int, c_int, c_int, P]),
         "cnb_dcnv2_im2col": (c_int, [P, P, c_int, P] + [c_int] * 4 + [P]),
         "cnb_dcnv2_col2im": (c_int, [P, P, c_int, P, P, P] + [c_int] * 4 + [P]),
-        "cnb_adam_step": (c_int, [P, P, P, P, c_longlong, c_float, c_float, c_float, c_float, c_int, c_float, P]),
+        "cnb_adam_step": (c_int, [P, P, P, P, c_longlong, c_float, c_float, c_float, c_float, c_int, P, P, c_float, P]),
         # fp32-strict mode
         "cnb_strict_conv2d_f32": (c_int, [P] * 6 + [c_int] * 10 + [P]),
         "cnb_strict_dcn_im2col_f32": (c_int, [P, P, P] + [c_int] * 4 + [P]),

@@ -303,6 +303,8 @@ __global__ void maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ x, const _
 // dx[iy,ix,c] = sum_{ky,kx} dy[iy*f - f/2 + ky, ix*f - f/2 + kx, c] * w[c,ky,kx]     (one thread per (pixel, 8 channels))
 // dw[c,ky,kx] = sum_{b,iy,ix} x[b,iy,ix,c] * dy[b, iy*f - f/2 + ky, ...]              (shared-memory accumulation per
 //               CTA over its pixels, then one atomicAdd per (CTA, tap, channel) into dwt [(2f)^2][C] fp32)
+template <bool REG16>   // REG16: 2f = 4 -> the 16 x 8 weight-gradient partials of a thread live in registers (its 8-channel
+                        // group is fixed: the grid stride is a multiple of C/8) and reach shared memory once at the end
 __global__ void __launch_bounds__(256) dw_deconv_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wt,
                                                             const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx,
                                                             float* __restrict__ dwt, int B, int H, int W, int C, int f) {
@@ -310,9 +312,16 @@ __global__ void __launch_bounds__(256) dw_deconv_bwd_kernel(const __nv_bfloat16*
   const int ks = 2 * f, pad = f / 2, Ho = H * f, Wo = W * f, groups = C / 8, ntap = ks * ks;
   for (int i = threadIdx.x; i < ntap * C; i += blockDim.x) s_dw[i] = 0.f;
   __syncthreads();
+  float racc[REG16 ? 16 : 1][8];
+  if (REG16) {
+#pragma unroll
+    for (int t = 0; t < 16; ++t)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) racc[t][j] = 0.f;
+  }
   const long long total = (long long)B * H * W * groups;
+  const int g = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) % groups);   // constant over the loop
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % groups);
     long long p = i / groups;
     const int ix = (int)(p % W);
     p /= W;
@@ -322,24 +331,51 @@ __global__ void __launch_bounds__(256) dw_deconv_bwd_kernel(const __nv_bfloat16*
     unpack8(__ldg(reinterpret_cast<const uint4*>(x) + i), xv);
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int ky = 0; ky < ks; ++ky) {
-      const int oy = iy * f - pad + ky;
-      if (oy < 0 || oy >= Ho) continue;
-      for (int kx = 0; kx < ks; ++kx) {
-        const int ox = ix * f - pad + kx;
-        if (ox < 0 || ox >= Wo) continue;
-        float gy[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(dy + ((size_t)(b * Ho + oy) * Wo + ox) * C + g * 8)), gy);
-        const float* wp = wt + (size_t)(ky * ks + kx) * C + g * 8;
-        float* sp = s_dw + (size_t)(ky * ks + kx) * C + g * 8;
+    if (REG16) {   // 2f == 4: fully unrolled, every racc index is a compile-time constant (registers, not local memory)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          acc[j] = fmaf(gy[j], __ldg(wp + j), acc[j]);
-          atomicAdd(sp + j, gy[j] * xv[j]);
+      for (int ky = 0; ky < 4; ++ky) {
+        const int oy = iy * 2 - 1 + ky;
+#pragma unroll
+        for (int kx = 0; kx < 4; ++kx) {
+          const int ox = ix * 2 - 1 + kx;
+          if (oy >= 0 && oy < Ho && ox >= 0 && ox < Wo) {
+            float gy[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(dy + ((size_t)(b * Ho + oy) * Wo + ox) * C + g * 8)), gy);
+            const float* wp = wt + (size_t)(ky * 4 + kx) * C + g * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              acc[j] = fmaf(gy[j], __ldg(wp + j), acc[j]);
+              racc[ky * 4 + kx][j] = fmaf(gy[j], xv[j], racc[ky * 4 + kx][j]);
+            }
+          }
+        }
+      }
+    } else {
+      for (int ky = 0; ky < ks; ++ky) {
+        const int oy = iy * f - pad + ky;
+        if (oy < 0 || oy >= Ho) continue;
+        for (int kx = 0; kx < ks; ++kx) {
+          const int ox = ix * f - pad + kx;
+          if (ox < 0 || ox >= Wo) continue;
+          float gy[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(dy + ((size_t)(b * Ho + oy) * Wo + ox) * C + g * 8)), gy);
+          const float* wp = wt + (size_t)(ky * ks + kx) * C + g * 8;
+          float* sp = s_dw + (size_t)(ky * ks + kx) * C + g * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            acc[j] = fmaf(gy[j], __ldg(wp + j), acc[j]);
+            atomicAdd(sp + j, gy[j] * xv[j]);
+          }
         }
       }
     }
     reinterpret_cast<uint4*>(dx)[i] = pack8(acc);
+  }
+  if (REG16) {
+#pragma unroll
+    for (int t = 0; t < 16; ++t)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(s_dw + (size_t)t * C + g * 8 + j, racc[t][j]);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < ntap * C; i += blockDim.x) {
@@ -435,53 +471,125 @@ __global__ void __launch_bounds__(256) dcn_im2col_kernel(const __nv_bfloat16* __
   }
 }
 
-// d(columns) -> dX (fp32 scatter-add), d(offset), d(mask logit): one WARP per (pixel, tap); lanes split the channels
-// (2 per lane and 64-channel pass), three warp reductions per (pixel, tap).
+// d(columns) -> dX (fp32 scatter-add), d(offset), d(mask logit).
+// Work item = (pixel, tap) of one 64-channel slab.  Each lane derives the sampling position of one item; the warp then
+// walks its 32 items two at a time (one per half-warp) broadcasting that state -- no redundant coordinate math -- with
+// the 16 lanes of a half-warp splitting the 64 channels four apiece: one 8-byte load per corner and ONE
+// red.global.add.v4.f32 per (corner, lane).  The L2 reduction units are the limit of this kernel (measured: ~300 G
+// reduction instructions/s whatever their width), so the widest fp32 vector form is used; shared-memory staging does not
+// help because sm_100 has no native shared-memory fp32 add (red.shared.add.f32 compiles to a CAS loop: measured 1.7x
+// SLOWER than going to L2 directly).  The three per-item sums (d offset_y, d offset_x, d mask) are half-warp reductions.
 __global__ void __launch_bounds__(256) dcn_col2im_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ om,
                                                          int om_cstride, const __nv_bfloat16* __restrict__ dcol,
                                                          float* __restrict__ dx_acc, float* __restrict__ dom, int B,
                                                          int H, int W, int C) {
   const int lane = threadIdx.x & 31;
-  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
-  const long long total = (long long)B * H * W * 9;
-  const int HW = H * W;
-  for (long long it = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5); it < total; it += warps) {
-    const int tap = (int)(it % 9);
-    const long long m = it / 9;
-    const int n = (int)(m / HW);
-    const int rem = (int)(m - (long long)n * HW);
-    const int oy = rem / W, ox = rem - oy * W;
-    const Samp s = make_samp(om + (size_t)m * om_cstride, tap, n, oy, ox, H, W, C);
-    float sy = 0.f, sx = 0.f, sm = 0.f;
-    const __nv_bfloat16* gp = dcol + ((size_t)m * 9 + tap) * C;
-    for (int c0 = 2 * lane; c0 < C; c0 += 64) {
-      const float2 g = bf2f(__ldg(reinterpret_cast<const u32*>(gp + c0)));
-      float2 v[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        v[c] = s.valid[c] ? bf2f(__ldg(reinterpret_cast<const u32*>(x + s.idx[c] + c0))) : make_float2(0.f, 0.f);
-      // value before modulation and its coordinate derivatives (torchvision get_coordinate_weight)
-      const float val0 = s.w[0] * v[0].x + s.w[1] * v[1].x + s.w[2] * v[2].x + s.w[3] * v[3].x;
-      const float val1 = s.w[0] * v[0].y + s.w[1] * v[1].y + s.w[2] * v[2].y + s.w[3] * v[3].y;
-      sm += g.x * val0 + g.y * val1;
-      const float hy = 1.f - s.ly, hx = 1.f - s.lx;
-      sy += g.x * (s.lx * (v[3].x - v[1].x) + hx * (v[2].x - v[0].x)) + g.y * (s.lx * (v[3].y - v[1].y) + hx * (v[2].y - v[0].y));
-      sx += g.x * (s.ly * (v[3].x - v[2].x) + hy * (v[1].x - v[0].x)) + g.y * (s.ly * (v[3].y - v[2].y) + hy * (v[1].y - v[0].y));
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (!s.valid[c]) continue;
-        const float w = s.w[c] * s.mk;
-        asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(dx_acc + s.idx[c] + c0), "f"(w * g.x), "f"(w * g.y) : "memory");
+  const int hsel = lane >> 4, q = lane & 15;
+  const int slabs = C / 64;
+  const long long HW = (long long)H * W;
+  const long long items = (long long)B * HW * 9 * slabs;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long base = warp0 * 32; base < items; base += nwarps * 32) {
+    // ---- lane-parallel: the sampling state of item base + lane  (item = ((m * 9 + tap) * slabs + slab))
+    const long long item = base + lane;
+    int flag = 0, y0 = 0, x0 = 0, tap = 0, slab = 0, n = 0;
+    float ly = 0.f, lx = 0.f, mk = 0.f;
+    long long m = 0;
+    if (item < items) {
+      slab = (int)(item % slabs);
+      const long long r = item / slabs;
+      tap = (int)(r % 9);
+      m = r / 9;
+      n = (int)(m / HW);
+      const int rem = (int)(m - (long long)n * HW);
+      const int oy = rem / W, ox = rem - oy * W;
+      const float* omp = om + (size_t)m * om_cstride;
+      const int kh = tap / 3, kw = tap - 3 * kh;
+      const float py = (float)(oy - 1 + kh) + omp[2 * tap];
+      const float px = (float)(ox - 1 + kw) + omp[2 * tap + 1];
+      mk = 1.f / (1.f + expf(-omp[18 + tap]));
+      if (py > -1.f && px > -1.f && py < (float)H && px < (float)W) {
+        y0 = (int)floorf(py);
+        x0 = (int)floorf(px);
+        ly = py - (float)y0;
+        lx = px - (float)x0;
+        flag = 1;
       }
     }
-    sy = warp_sum_f(sy);
-    sx = warp_sum_f(sx);
-    sm = warp_sum_f(sm);
-    if (lane == 0) {
+    float my_sy = 0.f, my_sx = 0.f, my_sm = 0.f;
+    const u32 any = __ballot_sync(0xffffffffu, flag);
+    for (int j = 0; j < 16; ++j) {
+      if (!((any >> (2 * j)) & 3u)) continue;   // warp-uniform: neither item of the pair samples inside the image
+      const int src = 2 * j + hsel;
+      const int jf = __shfl_sync(0xffffffffu, flag, src);
+      const int jy0 = __shfl_sync(0xffffffffu, y0, src), jx0 = __shfl_sync(0xffffffffu, x0, src);
+      const float jly = __shfl_sync(0xffffffffu, ly, src), jlx = __shfl_sync(0xffffffffu, lx, src);
+      const float jmk = __shfl_sync(0xffffffffu, mk, src);
+      const long long jm = __shfl_sync(0xffffffffu, m, src);
+      const int jtap = __shfl_sync(0xffffffffu, tap, src), jslab = __shfl_sync(0xffffffffu, slab, src);
+      const int jn = __shfl_sync(0xffffffffu, n, src);
+      float sy = 0.f, sx = 0.f, sm = 0.f;
+      if (jf) {
+        const int cbase = jslab * 64 + 4 * q;
+        const float hy = 1.f - jly, hx = 1.f - jlx;
+        const bool vy0 = jy0 >= 0, vy1 = jy0 + 1 <= H - 1, vx0 = jx0 >= 0, vx1 = jx0 + 1 <= W - 1;
+        const bool valid[4] = {vy0 && vx0, vy0 && vx1, vy1 && vx0, vy1 && vx1};
+        const float wgt[4] = {hy * hx, hy * jlx, jly * hx, jly * jlx};
+        const uint2 gr = __ldg(reinterpret_cast<const uint2*>(dcol + ((size_t)jm * 9 + jtap) * C + cbase));
+        const float2 g01 = bf2f(gr.x), g23 = bf2f(gr.y);
+        const float g[4] = {g01.x, g01.y, g23.x, g23.y};
+        float v[4][4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int cy = jy0 + (c >> 1), cx = jx0 + (c & 1);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[c][e] = 0.f;
+          if (valid[c]) {
+            const size_t off = (((size_t)jn * H + cy) * W + cx) * C + cbase;
+            const uint2 xr = __ldg(reinterpret_cast<const uint2*>(x + off));
+            const float2 a01 = bf2f(xr.x), a23 = bf2f(xr.y);
+            v[c][0] = a01.x; v[c][1] = a01.y; v[c][2] = a23.x; v[c][3] = a23.y;
+            const float w = wgt[c] * jmk;
+            asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dx_acc + off), "f"(w * g[0]), "f"(w * g[1]),
+                         "f"(w * g[2]), "f"(w * g[3])
+                         : "memory");
+          }
+        }
+        // value before modulation and its coordinate derivatives (torchvision get_coordinate_weight)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          sm += g[e] * (wgt[0] * v[0][e] + wgt[1] * v[1][e] + wgt[2] * v[2][e] + wgt[3] * v[3][e]);
+          sy += g[e] * (jlx * (v[3][e] - v[1][e]) + hx * (v[2][e] - v[0][e]));
+          sx += g[e] * (jly * (v[3][e] - v[2][e]) + hy * (v[1][e] - v[0][e]));
+        }
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {   // half-warp sums
+        sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        sx += __shfl_xor_sync(0xffffffffu, sx, o);
+        sm += __shfl_xor_sync(0xffffffffu, sm, o);
+      }
+      // hand the sums to the lane that owns the item: lane 2j takes half-warp 0's, lane 2j+1 half-warp 1's
+      const float oy_ = __shfl_sync(0xffffffffu, sy, 16), ox_ = __shfl_sync(0xffffffffu, sx, 16), om_ = __shfl_sync(0xffffffffu, sm, 16);
+      const float ey_ = __shfl_sync(0xffffffffu, sy, 0), ex_ = __shfl_sync(0xffffffffu, sx, 0), em_ = __shfl_sync(0xffffffffu, sm, 0);
+      if (lane == 2 * j) {
+        my_sy = ey_ * mk; my_sx = ex_ * mk; my_sm = em_ * mk * (1.f - mk);
+      } else if (lane == 2 * j + 1) {
+        my_sy = oy_ * mk; my_sx = ox_ * mk; my_sm = om_ * mk * (1.f - mk);
+      }
+    }
+    if (flag) {
       float* dp = dom + (size_t)m * om_cstride;
-      dp[2 * tap] = s.inside ? sy * s.mk : 0.f;
-      dp[2 * tap + 1] = s.inside ? sx * s.mk : 0.f;
-      dp[18 + tap] = s.inside ? sm * s.mk * (1.f - s.mk) : 0.f;
+      if (slabs == 1) {
+        dp[2 * tap] = my_sy;
+        dp[2 * tap + 1] = my_sx;
+        dp[18 + tap] = my_sm;
+      } else {   // several channel slabs add into the same three numbers (dom is zero-filled by the host wrapper)
+        atomicAdd(dp + 2 * tap, my_sy);
+        atomicAdd(dp + 2 * tap + 1, my_sx);
+        atomicAdd(dp + 18 + tap, my_sm);
+      }
     }
   }
 }
@@ -501,7 +609,12 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ a, __nv_bfloat16* _
 
 // ---- Adam (torch.optim.Adam defaults: no weight decay, no amsgrad) on flat fp32 buffers ---------------------------
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                            long long n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float gscale) {
+                            long long n, float lr, float b1, float b2, float eps, int step, const int* __restrict__ step_dev,
+                            const float* __restrict__ lr_dev, float gscale) {
+  // step / learning rate may live in device memory so that a captured CUDA graph of the training step sees them change
+  const int t = step_dev ? *step_dev : step;
+  const float lrv = lr_dev ? *lr_dev : lr;
+  const float bc1 = 1.f - powf(b1, (float)t), bc2_sqrt = sqrtf(1.f - powf(b2, (float)t));
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float gi = g[i] * gscale;
     const float mi = b1 * m[i] + (1.f - b1) * gi;
@@ -509,7 +622,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     m[i] = mi;
     v[i] = vi;
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] -= (lr / bc1) * (mi / denom);
+    p[i] -= (lrv / bc1) * (mi / denom);
   }
 }
 
@@ -630,13 +743,18 @@ extern "C" int cnb_dw_deconv_bwd(const void* x, const float* wt, const void* dy,
   CNB_CHECK_ARG(smem <= 160 * 1024, "dw_deconv_bwd: (2f)^2 * C too large for shared memory");
   static PerDeviceOnce once;
   if (once.need()) {
-    CNB_CUDA(cudaFuncSetAttribute(dw_deconv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CNB_CUDA(cudaFuncSetAttribute(dw_deconv_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CNB_CUDA(cudaFuncSetAttribute(dw_deconv_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     once.mark();
   }
   const long long total = (long long)B * H * W * (C / 8);
   long long want = (total + 255) / 256;
   const int grid = (int)(want > 148 * 2 ? 148 * 2 : want);
-  dw_deconv_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((cbf)x, wt, (cbf)dy, (bf)dx, dwt_acc, B, H, W, C, f);
+  // the register path needs a thread's channel group to stay fixed: grid stride (grid * 256) % (C / 8) == 0
+  if (f == 2 && 256 % (C / 8) == 0)
+    dw_deconv_bwd_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>((cbf)x, wt, (cbf)dy, (bf)dx, dwt_acc, B, H, W, C, f);
+  else
+    dw_deconv_bwd_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>((cbf)x, wt, (cbf)dy, (bf)dx, dwt_acc, B, H, W, C, f);
   CNB_LAUNCH_CHECK();
   return CNB_OK;
 }
@@ -665,17 +783,17 @@ extern "C" int cnb_dcnv2_col2im(const void* x, const float* om, int om_cstride, 
   CNB_CHECK_ARG((long long)B * H * W * C < (1ll << 31), "dcnv2_col2im: tensor too large for 32-bit element offsets");
   CNB_CUDA(cudaMemsetAsync(dx_acc, 0, (size_t)B * H * W * C * sizeof(float), st));
   CNB_CUDA(cudaMemsetAsync(dom, 0, (size_t)B * H * W * om_cstride * sizeof(float), st));
-  const long long warps = (long long)B * H * W * 9;
-  dcn_col2im_kernel<<<grid_for(warps * 32), 256, 0, st>>>((cbf)x, om, om_cstride, (cbf)dcol, dx_acc, dom, B, H, W, C);
+  const long long items = (long long)B * H * W * 9 * (C / 64);
+  dcn_col2im_kernel<<<grid_for(items), 256, 0, st>>>((cbf)x, om, om_cstride, (cbf)dcol, dx_acc, dom, B, H, W, C);
   CNB_LAUNCH_CHECK();
   return CNB_OK;
 }
 
 extern "C" int cnb_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
-                             float beta2, float eps, int step, float grad_scale, cnb_stream_t stream) {
-  CNB_CHECK_ARG(p && g && m && v && n >= 1 && step >= 1, "adam_step: bad argument");
-  const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
-  adam_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2), grad_scale);
+                             float beta2, float eps, int step, const int* step_dev, const float* lr_dev, float grad_scale,
+                             cnb_stream_t stream) {
+  CNB_CHECK_ARG(p && g && m && v && n >= 1 && (step >= 1 || step_dev), "adam_step: bad argument");
+  adam_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, step, step_dev, lr_dev, grad_scale);
   CNB_LAUNCH_CHECK();
   return CNB_OK;
 }

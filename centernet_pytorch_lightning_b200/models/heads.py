@@ -2,9 +2,11 @@
 (CenterNet/models/heads.py:4-50: `<name>.fc.0` 3x3 conv + ReLU, `<name>.fc.2` 1x1 conv; heat-map bias
 -2.19, other heads N(0, 0.001)).
 
-Execution: the 3x3 convs of ALL heads run as one tcgen05 implicit GEMM (Co = head_conv * n_heads, bias +
-ReLU in the epilogue, NHWC bf16), then one 1x1 GEMM per head reads its channel slice and writes the
-NCHW fp32 map the decode kernels and the losses consume.
+Execution (eval): ONE kernel for all heads (csrc/head_fused.cu): implicit-GEMM 3x3 on tcgen05, bias + ReLU + bf16 in the
+epilogue, the 256-channel intermediate written back to TENSOR MEMORY and consumed from there by the 1x1 GEMM
+(tcgen05.mma with the A operand in TMEM), bias / sigmoid, NCHW fp32 out -- the intermediate never reaches HBM.
+Geometries the fused kernel does not cover (input channels != 64, head_conv != 256, > 96 output channels) run the
+3x3 convs of all heads as one GEMM and one 1x1 GEMM per head.  Training: models/exec_modes.py.
 """
 import torch
 from torch import nn
@@ -68,7 +70,8 @@ class CenterHead(nn.Module):
             b3 = torch.cat([m.fc[0].bias for m in mods.values()], 0).float().contiguous()
             one = [t for m in mods.values()
                    for t in (ops.pack_conv_weights(m.fc[2].weight), m.fc[2].bias.detach().float().contiguous())]
-        return (ops.pack_conv_weights(w3), b3, *one)     # flat tuple of tensors (ops.PackCache refreshes in place)
+            w1cat = torch.cat([one[2 * i].reshape(-1) for i in range(len(mods))])   # [sum round16(c_out)][256], fused kernel
+        return (ops.pack_conv_weights(w3), b3, w1cat, *one)     # flat tuple of tensors (ops.PackCache refreshes in place)
 
     @staticmethod
     def run_heads(mods, x, packed=None, sigmoid=()):
@@ -78,8 +81,12 @@ class CenterHead(nn.Module):
             v = getattr(x, "_cnb_nhwc", None)
             x = v if v is not None else ops.to_nhwc_bf16(x)
         x = ops.as_view(x)
-        w3, b3, *one = packed if packed is not None else CenterHead._pack(mods)
+        w3, b3, w1cat, *one = packed if packed is not None else CenterHead._pack(mods)
         hc = next(iter(mods.values())).fc[0].out_channels
+        fused = ops.heads_fused(x, w3, b3, w1cat, [one[2 * i + 1] for i in range(len(mods))], hc,
+                                [m.out_channels for m in mods.values()], [2 if n in sigmoid else 0 for n in mods])
+        if fused is not None:
+            return dict(zip(mods, fused))
         mid = ops.conv2d(x, w3, hc * len(mods), 3, 1, 1, None, b3, act=1)
         ret = {}
         for i, (name, m) in enumerate(mods.items()):

@@ -303,6 +303,38 @@ def dcnv2(x, om, wpk, Co, scale, shift, act=0, out=None):
     return o.buf if out is None else o
 
 
+def heads_fused(x, w3pk, bias3, w1cat, bias1, head_conv, c_out, act):
+    """All CenterHead heads in one kernel (cnb_head_fused_fprop): x NHWC bf16 (64 channels) -> [NCHW fp32 map per head],
+    or None when the geometry is not covered (the caller then runs the two-GEMM path).  CNB_HEAD_FUSED=0 disables."""
+    import ctypes
+    import os
+    if os.environ.get("CNB_HEAD_FUSED", "1") == "0":
+        return None
+    x = as_view(x)
+    d = _lib.HeadDesc()
+    d.B, d.H, d.W, d.Ci = x.B, x.H, x.W, x.C
+    d.x_cstride, d.x_coffset, d.head_conv, d.nheads = x.cstride, x.coffset, head_conv, len(c_out)
+    if len(c_out) > 8:
+        return None
+    for i, (c, a) in enumerate(zip(c_out, act)):
+        d.c_out[i], d.act[i] = c, a
+    L = _lib.lib()
+    if not L.cnb_head_fused_supported(d):
+        return None
+    dev = x.buf.device
+    ys = [torch.empty((x.B, c, x.H, x.W), dtype=torch.float32, device=dev) for c in c_out]
+    yp = (ctypes.c_void_p * len(ys))(*[y.data_ptr() for y in ys])
+    bp = (ctypes.c_void_p * len(ys))(*[b.data_ptr() if b is not None else None for b in bias1])
+    prof = LaunchProfiler.active
+    with torch.cuda.device(dev):
+        t0 = prof.begin() if prof else None
+        _lib.check(L.cnb_head_fused_fprop(d, _lib.ptr(x.buf), _lib.ptr(w3pk), _lib.ptr(bias3), _lib.ptr(w1cat), bp, yp,
+                                          _stream(x.buf)), "cnb_head_fused_fprop")
+        if prof:
+            prof.end(t0, "conv", 2.0 * x.B * x.H * x.W * (len(c_out) * head_conv * 9 * x.C + head_conv * sum(c_out)))
+    return ys
+
+
 def maxpool2d(x, k, out=None):
     x = as_view(x)
     Ho, Wo = x.H // k, x.W // k

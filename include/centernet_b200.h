@@ -165,6 +165,22 @@ int cnb_conv2d_wgrad(const cnb_conv_desc* d, const void* x, const void* dy, int 
 int cnb_conv_unpack_wgrad(const float* dw_acc, float* dw, int Co, int Ci, int Ci_pad, int KH, int KW, int KWp,
                           int accumulate, float scale, cnb_stream_t stream);
 
+/* CenterHead in one kernel (models/heads.py:4-50): for every head, conv3x3(Ci=64 -> 256, bias) -> ReLU ->
+ * conv1x1(256 -> c_out, bias) [-> act], with the 256-channel intermediate kept in tensor memory (never written to HBM).
+ *   x     [B,H,W,x_cstride] bf16 NHWC feature map (64 channels at x_coffset)
+ *   w3pk  cnb_conv_pack_weights of the heads' 3x3 filters concatenated along Co: [nheads*256][576]
+ *   bias3 [nheads*256] fp32;  w1pk: the heads' packed 1x1 filters concatenated ([sum round16(c_out)][256]);
+ *   bias1[h] [c_out[h]] fp32 (nullable);  y[h] [B,c_out[h],H,W] fp32 NCHW;  act[h]: 0 none, 2 sigmoid.
+ * bias1 / y are HOST arrays of device pointers (read during the call). */
+typedef struct cnb_head_desc {
+  int B, H, W, Ci, x_cstride, x_coffset, head_conv, nheads;
+  int c_out[8];
+  int act[8];
+} cnb_head_desc;
+int cnb_head_fused_supported(const cnb_head_desc* d);
+int cnb_head_fused_fprop(const cnb_head_desc* d, const void* x, const void* w3pk, const float* bias3,
+                         const void* w1pk, const float* const* bias1, float* const* y, cnb_stream_t stream);
+
 /* Modulated deformable convolution v2 (DCN.dcn_v2.DCN forward; call sites pose_dla_dcn.py:441-449,
  * resnet_dcn.py:202-210): 3x3, stride 1, pad 1, dil 1, deformable_groups 1.
  *   om [B,H,W,om_cstride] fp32 NHWC holds the 27 raw channels of the conv_offset_mask conv (run it
@@ -243,9 +259,11 @@ int cnb_dcnv2_im2col(const void* x, const float* om, int om_cstride, void* col, 
 int cnb_dcnv2_col2im(const void* x, const float* om, int om_cstride, const void* dcol, float* dx_acc,
                      float* dom, int B, int H, int W, int C, cnb_stream_t stream);
 /* torch.optim.Adam step (centernet.py:94-95 defaults) on flat fp32 buffers; g is multiplied by grad_scale first
- * (1/world_size after a sum all-reduce). */
+ * (1/world_size after a sum all-reduce).  step_dev / lr_dev (nullable device scalars) override step / lr: a captured
+ * CUDA graph of the training step reads the values current at replay time. */
 int cnb_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
-                  float beta2, float eps, int step, float grad_scale, cnb_stream_t stream);
+                  float beta2, float eps, int step, const int* step_dev, const float* lr_dev, float grad_scale,
+                  cnb_stream_t stream);
 
 /* ---------------------------------------------------------------- fp32-strict mode (NCHW fp32, CUDA cores) ---- */
 /* The same operators in the reference's own precision, for small-shape END-TO-END parity checks against the fp32

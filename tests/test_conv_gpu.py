@@ -240,3 +240,41 @@ def test_dense_deconv_and_padded_maxpool(cuda_dev):
     x = _bf(torch.randn(2, 64, 17, 30, generator=g)).to(cuda_dev)
     got = ops.maxpool2d_pad(ops.to_nhwc_bf16(x), 3, 2, 1)
     assert torch.equal(got.permute(0, 3, 1, 2).float(), F.max_pool2d(x, 3, 2, 1))
+
+
+@pytest.mark.parametrize("heads,B,H,W", [({"heatmap": 80, "width_height": 2, "regression": 2}, 2, 32, 48),
+                                          ({"heatmap": 1, "width_height": 2, "regression": 2, "heatmap_keypoints": 17,
+                                            "keypoints": 34, "heatmap_keypoints_offset": 2}, 1, 40, 24),
+                                          ({"heatmap": 80, "width_height": 2, "regression": 2}, 3, 128, 128)])
+def test_fused_center_head_matches_torch(cuda_dev, heads, B, H, W):
+    """csrc/head_fused.cu (3x3 -> ReLU -> 1x1 with the intermediate in tensor memory) vs PyTorch fp32 on bf16-rounded
+    operands, and vs the two-GEMM path (CNB_HEAD_FUSED=0).  The intermediate is rounded to bf16 on both GPU paths:
+    <= 1e-2 of the largest output vs fp32; the two GPU paths agree to fp32 accumulation order."""
+    import os
+    from centernet_pytorch_lightning_b200.models.heads import CenterHead
+    from centernet_pytorch_lightning_b200.utils.synthetic import randomize_
+    torch.manual_seed(3)
+    head = CenterHead(heads, 64, 256).eval()
+    randomize_(head.state_dict(), 17)
+    with torch.no_grad():
+        for p in head.parameters():
+            p.copy_(_bf(p))
+    x = _bf(torch.randn(B, 64, H, W, generator=torch.Generator().manual_seed(5)))
+    with torch.no_grad():
+        ref = {n: getattr(head, n).fc(x) for n in heads}       # plain nn.Sequential forward on the CPU
+        head = head.to(cuda_dev)
+        xg = ops.to_nhwc_bf16(x.to(cuda_dev))
+        got = head(xg, sigmoid=("heatmap",))
+        os.environ["CNB_HEAD_FUSED"] = "0"
+        try:
+            two = head(xg, sigmoid=("heatmap",))
+        finally:
+            os.environ.pop("CNB_HEAD_FUSED")
+    torch.cuda.synchronize()
+    for n in heads:
+        want = torch.sigmoid(ref[n]) if n == "heatmap" else ref[n]
+        assert got[n].shape == want.shape and got[n].dtype == torch.float32
+        err = (got[n].cpu() - want).abs().max().item() / (want.abs().max().item() + 1e-12)
+        dif = (got[n] - two[n]).abs().max().item() / (want.abs().max().item() + 1e-12)
+        print(f"{n}: fused vs fp32 {err:.2e}, fused vs two-GEMM path {dif:.2e}")
+        assert err <= 1e-2 and dif <= 2e-3

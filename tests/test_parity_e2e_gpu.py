@@ -33,6 +33,8 @@ def _build(seed, gain=0.05):
     with torch.no_grad():   # heat logits ~ N(-2.19, 1): scores spread over (0, 1) instead of saturating at 1.0 (ties)
         h.heatmap.fc[2].weight.mul_(0.03)
         h.heatmap.fc[2].bias.fill_(-2.19)
+        for name in ("width_height", "regression"):     # box sizes / offsets of a few output pixels, like trained heads
+            getattr(h, name).fc[2].weight.mul_(0.1)
     sd = {k: v.clone() for k, v in m.state_dict().items()}
     hd = {k: v.clone() for k, v in h.state_dict().items()}
     return m, h, sd, hd
@@ -127,15 +129,34 @@ def test_bf16_fast_path_at_benchmark_resolution(cuda_dev, gain, tol_l2, tol_max)
         mx = ((got - ref).abs().max() / ref.abs().max()).item()
         print(f"bf16 512x512 gain {gain} head {k}: rel-L2 {l2:.4f} max-rel {mx:.4f}")
         assert l2 <= tol_l2 and mx <= tol_max
-    kr_all, kg_all = _keys_ref(heat_ref), _keys_gpu(heat)
-    rates, dss, dcs = [], [], []
+    # (1) at the ORACLE's top-100 cells: the engine's score and box there (what a consumer thresholding scores sees)
+    HW = heat_ref.shape[2] * heat_ref.shape[3]
+    kr_all = _keys_ref(heat_ref)
+    g_heat, g_wh, g_reg = heat.cpu().numpy(), o["width_height"].cpu().numpy(), o["regression"].cpu().numpy()
+    r_heat, r_wh, r_reg = heat_ref.numpy(), o_ref["width_height"].numpy(), o_ref["regression"].numpy()
+    ds_cell = dc_cell = 0.0
+    for b in range(2):
+        cls, cell = kr_all[b] // HW, kr_all[b] % HW
+        ds_cell = max(ds_cell, np.abs(g_heat[b].reshape(80, -1)[cls, cell] - r_heat[b].reshape(80, -1)[cls, cell]).max())
+        for gm, rm in ((g_wh, r_wh), (g_reg, r_reg)):
+            dc_cell = max(dc_cell, np.abs(gm[b].reshape(2, -1)[:, cell] - rm[b].reshape(2, -1)[:, cell]).max())
+    # (2) set agreement of the two top-100 lists, and how deep in the engine's ranking the oracle's detections sit
+    kg_all, kg_deep = _keys_gpu(heat), _keys_gpu(heat, K=400)
+    rates, deep, dss, dcs = [], [], [], []
     for b in range(2):
         pairs, ds, dc = _match(kr_all[b], kg_all[b], det_ref[b], det[b])
         rates.append(len(pairs) / 100.0)
+        deep.append(len(set(kr_all[b].tolist()) & set(kg_deep[b].tolist())) / 100.0)
         dss.append(ds)
         dcs.append(dc)
-    extent = float(np.abs(det_ref[..., :4]).max())
-    print(f"bf16 512x512 gain {gain} detections: top-100 (class, cell) match rate {rates}, max |dscore| {max(dss):.3e}, "
-          f"max |dcoord| {max(dcs):.3e} output-stride pixels = {max(dcs) / extent:.3e} of the largest box coordinate ({extent:.1f})")
-    # random-init weights put many candidates within bf16 noise of the 100th score; the bounds are deliberately loose
-    assert min(rates) >= (0.8 if gain == 0.0 else 0.5) and max(dss) <= 5e-2 and max(dcs) <= 0.1 * extent
+    gap = float(det_ref[0][0, 4] - det_ref[0][99, 4])
+    print(f"bf16 512x512 gain {gain}: at the oracle's top-100 cells |dscore| <= {ds_cell:.3e}, |d(wh, reg)| <= {dc_cell:.3e}; "
+          f"the oracle's top-100 scores span only {gap:.3e} (random-init heads: 1.3 M candidates in the tail), so rank "
+          f"agreement is: in the engine's top-100 {rates}, in its top-400 {deep}; on matched detections max |dscore| "
+          f"{max(dss):.3e}, max |dcoord| {max(dcs):.3e} output-stride pixels")
+    # asserted: what a consumer of the detections sees at a given cell (score, box regression); the rank statistics are
+    # reported, with a loose floor only -- among ~1e3 candidates within bf16 noise of each other the rank order is not
+    # a property of the kernels (the fp32-strict test above is where index-exactness is asserted)
+    box_scale = max(float(np.abs(r_wh).max()), float(np.abs(r_reg).max()))
+    assert ds_cell <= 5e-2 and dc_cell <= tol_max * box_scale
+    assert min(rates) >= 0.1 and max(dss) <= 5e-2
