@@ -5,7 +5,7 @@ path raises.  (The CPU oracle lives under oracle/ and is test infrastructure onl
 """
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_longlong, c_size_t, c_ulonglong, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_ulonglong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcenternet_b200.so")
@@ -83,6 +83,12 @@ def _declare(lib):
         "cnb_strict_dcn_im2col_f32": (c_int, [P, P, P] + [c_int] * 4 + [P]),
         "cnb_strict_conv_transpose2d_f32": (c_int, [P] * 6 + [c_int] * 10 + [P]),
         "cnb_strict_maxpool2d_f32": (c_int, [P, P] + [c_int] * 6 + [P]),
+        # callers either side of the path
+        "cnb_ctdet_encode": (c_int, [P] * 8 + [c_int] * 6 + [P]),
+        "cnb_soft_nms": (c_int, [P, P, P, c_int, c_int, c_int, c_double, c_double, c_double, c_int, P]),
+        "cnb_tta_prologue": (c_int, [P, P] + [c_int] * 5 + [P, P, c_int, P]),
+        "cnb_tta_flip_merge": (c_int, [P, P, c_int, c_int, c_int, P]),
+        "cnb_ctdet_post": (c_int, [P, P, P, P, c_int, c_int] + [c_float] * 5 + [P]),
         # decode primitives by name
         "cnb_nms3x3": (c_int, [P, P, c_longlong, c_int, c_int, P]),
         "cnb_topk_rows": (c_int, [P, c_int, c_int, c_int, P, P, P]),

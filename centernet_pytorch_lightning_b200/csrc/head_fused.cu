@@ -184,6 +184,12 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int t = cta; t < a.total_tiles; t += G, ++i) {
       const int head = t / a.m_tiles;
       const u32 buf = i & 1u, bph = (i >> 1) & 1u;
+      if (pending && head != p_head) {
+        // head boundary: the producer loads the new head's 1x1 filter (and only then this tile's K blocks) once the old
+        // head's last GEMM 2 has completed -- which is issued from THIS warp, so it must not wait for those K blocks first
+        mbar_wait_parked(&s_midfull[p_buf], p_ph);
+        gemm2();
+      }
       mbar_wait_parked(&s_tempty[buf], bph ^ 1u);
       tc_fence_after();
       const u32 tmem_d = tmem_base + buf * ACC_COLS;

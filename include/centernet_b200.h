@@ -289,6 +289,30 @@ int cnb_topk_rows(const float* scores, int rows, int n, int K, float* out_scores
 int cnb_gather_feat(const float* feat, const long long* ind, float* out, int B, int C, int N, int K,
                     int feat_is_nchw, cnb_stream_t stream);
 
+/* ---------------------------------------------------------------- callers either side of the path ---- */
+/* (f)2 target encoding, CenterNet/sample/ctdet.py:39-90 + utils/gaussian.py:6-58 (umich Gaussian), batched on the device:
+ * boxes [B,M,4] float64 COCO (x,y,w,h) in input pixels, cls [B,M] int32, nobj [B] int32 ->
+ * heatmap [B,C,H,W] fp32 (zero-filled here), indices [B,M] int64, mask [B,M] uint8 (bool), wh / reg [B,M,2] fp32. */
+int cnb_ctdet_encode(const double* boxes, const int* cls, const int* nobj, float* heatmap, long long* indices,
+                     unsigned char* mask, float* wh, float* reg, int B, int C, int H, int W, int M,
+                     int down_ratio, cnb_stream_t stream);
+/* (f)3 soft-NMS, CenterNet/utils/nms.py:5-106 (ncol = 5) / :109-206 (ncol = 39): nlists independent lists of
+ * counts[l] <= max_boxes rows [x1,y1,x2,y2,score,...], processed in place (kept rows first, selection order,
+ * decayed scores); kept[l] = number of rows kept.  method 0 hard, 1 linear, 2 gaussian. */
+int cnb_soft_nms(float* boxes, const int* counts, int* kept, int nlists, int max_boxes, int ncol, double sigma,
+                 double Nt, double threshold, int method, cnb_stream_t stream);
+/* (f)1 test-time augmentation around the engine (centernet_detection.py:143-171, 188-204):
+ * prologue: img [3,H,W] fp32 -> out [(flip ? 2 : 1),3,H+2*pad_tb,W+2*pad_lr] = normalize(zero-pad(img)) (+ its hflip);
+ *           mean3 / std3 are HOST arrays of 3 floats;
+ * flip merge: pair [2,C,H,W] -> out [C,H,W] = (pair[0] + hflip(pair[1])) / 2;
+ * post: det [K,6] -> out [K,5] rows (x1,y1,x2,y2,score) in image pixels ((v * down_ratio - pad) / scale) grouped by class
+ *       (class c occupies rows [offsets[c], offsets[c] + counts[c]), input order kept inside a class). */
+int cnb_tta_prologue(const float* img, float* out, int C, int H, int W, int pad_lr, int pad_tb, const float* mean3,
+                     const float* std3, int flip, cnb_stream_t stream);
+int cnb_tta_flip_merge(const float* pair, float* out, int C, int H, int W, cnb_stream_t stream);
+int cnb_ctdet_post(const float* det, float* out, int* counts, int* offsets, int K, int C, float down_ratio,
+                   float pad_x, float pad_y, float scale_x, float scale_y, cnb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
