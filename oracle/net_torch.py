@@ -169,4 +169,55 @@ def pose_resnet_forward(sd, x, num_layers, dcn_variant):
     return h
 
 
+# ---- Hourglass-104 ------------------------------------------------------------------------------------------------
+def _hg_conv(sd, p, x, stride=1):
+    """`convolution` (large_hourglass.py:8-28): conv (+ BN) + ReLU."""
+    w = sd[p + ".conv.weight"]
+    y = F.conv2d(x, w, sd.get(p + ".conv.bias"), stride=stride, padding=(w.shape[2] - 1) // 2)
+    if (p + ".bn.weight") in sd:
+        y = _bn(sd, p + ".bn", y)
+    return F.relu(y)
+
+
+def _hg_res(sd, p, x, stride=1):
+    """`residual` (:51-93)."""
+    h = F.relu(_bn(sd, p + ".bn1", F.conv2d(x, sd[p + ".conv1.weight"], stride=stride, padding=1)))
+    h = _bn(sd, p + ".bn2", F.conv2d(h, sd[p + ".conv2.weight"], padding=1))
+    skip = x
+    if (p + ".skip.0.weight") in sd:
+        skip = _bn(sd, p + ".skip.1", F.conv2d(x, sd[p + ".skip.0.weight"], stride=stride))
+    return F.relu(h + skip)
+
+
+def _hg_seq(sd, p, x, first_stride=1):
+    i = 0
+    while (f"{p}.{i}.conv1.weight") in sd:
+        x = _hg_res(sd, f"{p}.{i}", x, first_stride if i == 0 else 1)
+        i += 1
+    return x
+
+
+def _hg_kp(sd, p, x):
+    """`kp_module.forward` (:206-213); the stride-2 first block of low1 replaces pooling (make_hg_layer :315-319)."""
+    up1 = _hg_seq(sd, p + ".up1", x)
+    low1 = _hg_seq(sd, p + ".low1", x, first_stride=2)
+    low2 = _hg_kp(sd, p + ".low2", low1) if (p + ".low2.up1.0.conv1.weight") in sd else _hg_seq(sd, p + ".low2", low1)
+    low3 = _hg_seq(sd, p + ".low3", low2)
+    return up1 + F.interpolate(low3, scale_factor=2)
+
+
+def hourglass_forward(sd, x, nstack=2):
+    """`exkp.forward` (:297-313) with the HourglassNet arguments -> [stack outputs [B,256,H/4,W/4]]."""
+    inter = _hg_res(sd, "pre.1", _hg_conv(sd, "pre.0", x, stride=2), stride=2)
+    outs = []
+    for ind in range(nstack):
+        cnv = _hg_conv(sd, f"cnvs.{ind}", _hg_kp(sd, f"kps.{ind}", inter))
+        outs.append(cnv)
+        if ind < nstack - 1:
+            a = _bn(sd, f"inters_.{ind}.1", F.conv2d(inter, sd[f"inters_.{ind}.0.weight"]))
+            b = _bn(sd, f"cnvs_.{ind}.1", F.conv2d(cnv, sd[f"cnvs_.{ind}.0.weight"]))
+            inter = _hg_res(sd, f"inters.{ind}", F.relu(a + b))
+    return outs
+
+
 from centernet_pytorch_lightning_b200.utils.synthetic import randomize_  # noqa: E402,F401 (seeded weights shared with bench.py)

@@ -157,3 +157,32 @@ def test_packed_weight_caches_follow_parameter_updates(cuda_dev):
             p.mul_(0.5)
     halved = run(parent)
     assert not torch.equal(halved["width_height"], after["width_height"])
+
+
+def test_hourglass_backbone_matches_oracle(cuda_dev):
+    """Hourglass-104 (two stacks) + per-stack ctdet heads vs the fp32 CPU oracle (bf16 bound), and the reference's
+    tests/test_models.py shape contract for `hourglass`."""
+    torch.manual_seed(13)
+    m = create_model("hourglass").eval()
+    randomize_(m.state_dict(), 13)
+    heads = [CenterHead(HEADS, m.out_channels, 256).eval() for _ in range(2)]
+    for i, h in enumerate(heads):
+        randomize_(h.state_dict(), 14 + i)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    hds = [{k: v.clone() for k, v in h.state_dict().items()} for h in heads]
+    x = torch.rand(1, 3, 128, 128, generator=torch.Generator().manual_seed(4))
+    with torch.no_grad():
+        ref = net_torch.hourglass_forward(sd, x)
+        ref_heads = [net_torch.center_head_forward(hd, f, HEADS) for hd, f in zip(hds, ref)]
+        m = m.to(cuda_dev)
+        out = m(x.to(cuda_dev))
+        assert isinstance(out, list) and len(out) == 2 and all(o.shape == (1, 256, 32, 32) for o in out)
+        got_heads = [h.to(cuda_dev)(o) for h, o in zip(heads, out)]
+    torch.cuda.synchronize()
+    for s in range(2):
+        l2, mx = _rel(out[s], ref[s])
+        print(f"hourglass stack {s} rel-L2 {l2:.4f} max-rel {mx:.4f}")
+        assert l2 <= 3e-2 and mx <= 8e-2
+        for k in HEADS:
+            l2, mx = _rel(got_heads[s][k], ref_heads[s][k])
+            assert l2 <= 3e-2 and mx <= 8e-2, (s, k, l2, mx)

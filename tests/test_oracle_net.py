@@ -118,3 +118,24 @@ def test_train_mode_oracle_equals_reference_dlaseg():
     for k, b in ref.named_buffers():
         if not k.endswith("num_batches_tracked"):
             assert torch.allclose(sd[k], b), k
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="needs the reference checkout")
+def test_hourglass_oracle_equals_reference():
+    """`net_torch.hourglass_forward` vs the reference HourglassNet (large_hourglass.py:322-343): both stack outputs
+    bit-equal, and this package's containers carry the same 960 state-dict entries."""
+    ref_shim.install()
+    from CenterNet.models.backbones.large_hourglass import HourglassNet
+    from centernet_pytorch_lightning_b200.models import create_model
+    ref = HourglassNet().eval()
+    randomize_(ref.state_dict(), 4)
+    mine = create_model("hourglass")
+    assert {k: tuple(v.shape) for k, v in mine.state_dict().items()} == {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+    assert mine.out_channels == ref.out_channels == 256
+    x = torch.rand(1, 3, 128, 128, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        want = ref(x)
+        got = net_torch.hourglass_forward({k: v.clone() for k, v in ref.state_dict().items()}, x)
+    assert len(want) == len(got) == 2
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)

@@ -12,13 +12,13 @@ from centernet_pytorch_lightning_b200.decode import ctdet_decode  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 dev = torch.device("cuda:0")
-model, head = bench.seeded_weights()
+model, head = bench.seeded_weights(bench.CONFIGS[2])
 model, head = model.to(dev), head.to(dev)
 x = torch.rand(B, 3, 512, 512, device=dev)
 
 # record geometry next to each launch
 geo = []
-_conv, _dcn = ops.conv2d, ops.dcnv2
+_conv, _dcn, _heads = ops.conv2d, ops.dcnv2, ops.heads_fused
 
 
 def conv2d(x, wpk, Co, k, stride, pad, *a, **kw):
@@ -33,7 +33,15 @@ def dcnv2(x, om, wpk, Co, *a, **kw):
     return _dcn(x, om, wpk, Co, *a, **kw)
 
 
-ops.conv2d, ops.dcnv2 = conv2d, dcnv2
+def heads_fused(x, w3pk, bias3, w1cat, bias1, head_conv, c_out, act):
+    v = ops.as_view(x)
+    r = _heads(x, w3pk, bias3, w1cat, bias1, head_conv, c_out, act)
+    if r is not None:
+        geo.append(f"head {v.C:4d}->{head_conv}x{len(c_out)}->{sum(c_out)} 3x3+1x1 fused @{v.H}x{v.W}")
+    return r
+
+
+ops.conv2d, ops.dcnv2, ops.heads_fused = conv2d, dcnv2, heads_fused
 
 
 def step():
