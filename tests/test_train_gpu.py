@@ -382,3 +382,89 @@ def test_graphed_training_step_equals_eager(cuda_dev):
     d = (rm_e - rm_g).abs().max().item()
     print(f"stem running_mean after 6 steps: max |eager - graph| {d:.3e} (max |value| {rm_e.abs().max().item():.3e})")
     assert d <= 3e-2 * rm_e.abs().max().item() + 2e-3
+
+
+def test_multi_pose_training_step(cuda_dev):
+    """CenterNetMultiPose's 6-head loss (centernet_multi_pose.py:97-155) through the restated task on this package's
+    modules in train mode: forward -> loss -> backward; head gradients vs the CPU oracle evaluated on the ENGINE's own
+    feature map (so that only the heads + losses are compared: <= 3 % per tensor), every head parameter gets a gradient."""
+    from centernet_pytorch_lightning_b200.models import create_model
+    from centernet_pytorch_lightning_b200.utils.synthetic import randomize_
+    from oracle import net_torch, task_torch
+    ns = task_torch.namespace("b200")
+    torch.manual_seed(0)
+    task = task_torch.MultiPoseTask(ns, "dla_34")
+    randomize_(task.backbone.state_dict(), 3, offset_gain=0.02)
+    hd = {k: v.clone() for k, v in task.heads[0].state_dict().items()}
+    task = task.to(cuda_dev).train()
+    x = torch.rand(2, 3, 128, 128, generator=torch.Generator().manual_seed(1)).to(cuda_dev)
+    _, tgt = task_torch.task_inputs("pose", B=2, H=32, W=32)
+    feat = task.backbone(x)
+    outs = [task.heads[0](feat[0])]
+    loss, stats = task.loss(outs, {k: v.to(cuda_dev) for k, v in tgt.items()})
+    loss.backward()
+    torch.cuda.synchronize()
+    assert torch.isfinite(loss) and set(stats) == {"loss", "hm_loss", "kp_loss", "hm_kp_loss", "hm_offset_loss", "wh_loss", "off_loss"}
+    # oracle heads + loss on the engine's feature map (bf16-rounded, as the heads consume it)
+    f = feat[0].detach().float().cpu().to(BF).float()
+    for v in hd.values():
+        v.requires_grad_(True)
+    o = net_torch.center_head_forward(hd, f, task_torch.POSE_HEADS)
+    ref_task = _pose_loss_task()
+    ref_loss, _ = ref_task.loss([o], tgt)
+    ref_loss.backward()
+    print(f"multi-pose loss engine {loss.item():.5f} oracle-on-engine-features {ref_loss.item():.5f}")
+    assert abs(loss.item() - ref_loss.item()) <= 1e-2 * abs(ref_loss.item())
+    for name, p in task.heads[0].named_parameters():
+        assert p.grad is not None, name
+        rg = hd[name].grad
+        rel = ((p.grad.float().cpu() - rg).norm() / (rg.norm() + 1e-20)).item()
+        assert rel <= 3e-2 or rg.abs().max() < 1e-7, (name, rel)
+    assert any(p.grad is not None for p in task.backbone.parameters())
+
+
+def _pose_loss_task():
+    """MultiPoseTask.loss bound to the plain-torch functions below, without modules (only `loss` is used)"""
+    from oracle import task_torch
+    t = task_torch.MultiPoseTask.__new__(task_torch.MultiPoseTask)
+    nn.Module.__init__(t)
+    ns = _TorchNS()
+    t.ns, t.w = ns, (1, 0.1, 1, 1, 1)
+    t.criterion, t.criterion_heatmap_keypoints = ns.FocalLoss(), ns.FocalLoss()
+    t.criterion_keypoints = ns.RegWeightedL1Loss()
+    t.criterion_regression, t.criterion_width_height = ns.RegL1Loss(), ns.RegL1Loss()
+    return t
+
+
+class _TorchNS:
+    """plain-torch restatement of the reference's loss functions (utils/losses.py:14-91, utils/decode.py:43-63) for the
+    CPU side of the test above (the reference itself is absent on the GPU box)"""
+
+    @staticmethod
+    def sigmoid_clamped(x, clamp=1e-4):
+        return torch.clamp(torch.sigmoid(x), min=clamp, max=1 - clamp)
+
+    class FocalLoss(nn.Module):
+        def forward(self, pred, gt):
+            pos, neg = gt.eq(1).float(), gt.lt(1).float()
+            pl = (torch.log(pred) * torch.pow(1 - pred, 2) * pos).sum()
+            nl = (torch.log(1 - pred) * torch.pow(pred, 2) * torch.pow(1 - gt, 4) * neg).sum()
+            n = pos.sum()
+            return -nl if n == 0 else -(pl + nl) / n
+
+    class RegL1Loss(nn.Module):
+        def forward(self, output, mask, ind, target):
+            B, C = output.shape[:2]
+            p = output.permute(0, 2, 3, 1).contiguous().view(B, -1, C).gather(1, ind.unsqueeze(2).expand(B, ind.shape[1], C))
+            m = mask.unsqueeze(2).expand_as(p).float()
+            return F.l1_loss(p * m, target * m, reduction="sum") / (m.sum() + 1e-4)
+
+    class RegWeightedL1Loss(nn.Module):
+        def forward(self, output, mask, ind, target):
+            B, C = output.shape[:2]
+            p = output.permute(0, 2, 3, 1).contiguous().view(B, -1, C).gather(1, ind.unsqueeze(2).expand(B, ind.shape[1], C))
+            m = mask.float()
+            return F.l1_loss(p * m, target * m, reduction="sum") / (m.sum() + 1e-4)
+
+    CenterHead = None
+    create_model = None
