@@ -96,3 +96,36 @@ def test_reg_l1_config3_size(cuda_dev):
     # empty mask: loss 0 / (0 + 1e-4) = 0, gradient 0
     l = RegL1Loss()(_t(out, cuda_dev), _t(np.zeros_like(mask), cuda_dev), _t(ind, cuda_dev), _t(tgt, cuda_dev))
     assert l.item() == 0.0
+
+
+def test_loss_wrappers_cast_half_inputs_and_drop_bad_indices(cuda_dev):
+    """(a) fp16 / bf16 predictions (AMP) are cast to fp32 instead of being reinterpreted -- same loss as the
+    fp32 call on the rounded values, gradient returned in the input dtype; (b) an index outside [0, H*W) is dropped
+    (no out-of-bounds read / atomicAdd), the loss equals the one without that object."""
+    from centernet_pytorch_lightning_b200.utils.losses import FocalLoss, RegL1Loss
+    g = torch.Generator().manual_seed(0)
+    pred = torch.rand(2, 3, 16, 16, generator=g).clamp(1e-3, 1 - 1e-3)
+    gt = torch.rand(2, 3, 16, 16, generator=g) ** 4
+    gt[0, 1, 3, 4] = 1.0
+    for dt in (torch.float16, torch.bfloat16):
+        p16 = pred.to(dt).to(cuda_dev).requires_grad_(True)
+        p32 = pred.to(dt).float().to(cuda_dev).requires_grad_(True)
+        l16, l32 = FocalLoss()(p16, gt.to(cuda_dev)), FocalLoss()(p32, gt.to(cuda_dev))
+        l16.backward()
+        l32.backward()
+        assert torch.equal(l16, l32) and p16.grad.dtype == dt
+        assert torch.allclose(p16.grad.float(), p32.grad, rtol=1e-2, atol=1e-6)
+    out = torch.randn(2, 2, 8, 8, generator=g).to(cuda_dev).requires_grad_(True)
+    ind = torch.randint(0, 64, (2, 5), generator=g)
+    mask = torch.ones(2, 5, dtype=torch.bool)
+    tgt = torch.randn(2, 5, 2, generator=g)
+    bad = ind.clone()
+    bad[1, 2] = 64 + 1000                      # out of range
+    good_mask = mask.clone()
+    good_mask[1, 2] = False
+    l_bad = RegL1Loss()(out, mask.to(cuda_dev), bad.to(cuda_dev), tgt.to(cuda_dev))
+    l_bad.backward()
+    torch.cuda.synchronize()
+    assert torch.isfinite(l_bad) and torch.isfinite(out.grad).all()
+    num_ref = RegL1Loss()(out.detach(), good_mask.to(cuda_dev), ind.to(cuda_dev), tgt.to(cuda_dev)) * (good_mask.sum() * 2 + 1e-4)
+    assert torch.allclose(l_bad * (good_mask.sum() * 2 + 1e-4), num_ref, rtol=1e-5)

@@ -38,6 +38,36 @@ elif what == "up":
     wt = ops.relayout_dw_weights(torch.randn(64, 1, 4, 4, device=dev), 2)
     for _ in range(4):
         ops.dw_deconv_up(x, wt, 2, add=add)
+elif what == "headfused":      # CenterHead (ctdet) through csrc/head_fused.cu at the benchmark shape
+    from centernet_pytorch_lightning_b200.models.heads import CenterHead
+    from centernet_pytorch_lightning_b200.utils.synthetic import randomize_
+    head = CenterHead({"heatmap": 80, "width_height": 2, "regression": 2}, 64, 256).eval()
+    randomize_(head.state_dict(), 1)
+    head = head.to(dev)
+    x = torch.randn(B, 128, 128, 64, device=dev).to(torch.bfloat16)
+    with torch.no_grad():
+        for _ in range(4):
+            head(x, sigmoid=("heatmap",))
+elif what in ("wgrad64", "wgrad256", "col2im64", "im2col64"):   # backward kernels at config-3 shapes (batch 16)
+    from centernet_pytorch_lightning_b200 import autograd_ops as ag
+    from centernet_pytorch_lightning_b200.DCN.dcn_v2 import DCN
+    Bt = 16
+    if what.startswith("wgrad"):
+        ci, hw = (64, 128) if what == "wgrad64" else (256, 32)
+        conv = torch.nn.Conv2d(ci, ci, 3, 1, 1, bias=False).to(dev)
+        x = torch.randn(Bt, hw, hw, ci, device=dev).to(torch.bfloat16).requires_grad_(True)
+        for _ in range(4):
+            y = ag.conv(x, conv)
+            y.backward(torch.randn_like(y))
+    else:
+        m = DCN(64, 64, (3, 3), 1, 1).to(dev).train()
+        with torch.no_grad():
+            m.conv_offset_mask.weight.normal_(std=0.01)
+            m.conv_offset_mask.bias.uniform_(-0.3, 0.3)
+        x = torch.randn(Bt, 128, 128, 64, device=dev).to(torch.bfloat16).requires_grad_(True)
+        for _ in range(4):
+            y = ag.dcn(x, m)
+            y.backward(torch.randn_like(y))
 elif what == "s2d":
     x4 = ops.to_nhwc_bf16(torch.randn(B, 3, 512, 512, device=dev), c_pad=4)
     wpk, geom = ops.pack_stem_s2d_weights(torch.randn(16, 3, 7, 7, device=dev) * 0.05)
