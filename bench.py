@@ -259,7 +259,18 @@ def train_leg(args, rank, world, dev, steps, warmup, with_e2e=True):
     else:   # the public training API: the whole step (fwd, losses, bwd, all-reduce, Adam) replayed as one CUDA graph
         do_step = GraphedCtdetStep(model, head, trainer, B, R)
     losses = []
-    for i in range(warmup):
+    launch_mode = "eager (autograd tape)" if args.no_graph else "CUDA graph replay of the whole step (trainer.GraphedCtdetStep)"
+    try:
+        losses.append(do_step(x_dev[0], t_dev[0]).clone())
+        torch.cuda.synchronize()
+    except Exception as e:   # a capture that the NCCL build at hand refuses must not cost the line: run the same step eagerly
+        if args.no_graph:
+            raise
+        launch_mode = f"eager (graph capture failed: {repr(e)[:120]})"
+        args.no_graph = True
+        do_step = lambda x, t: ctdet_training_step(model, head, trainer, x, t)   # noqa: E731
+        losses.append(do_step(x_dev[0], t_dev[0]).clone())
+    for i in range(1, warmup):
         losses.append(do_step(x_dev[i % 2], t_dev[i % 2]).clone())
     sync_all(world)
     n0 = _lib.launch_count()
@@ -330,7 +341,7 @@ def train_leg(args, rank, world, dev, steps, warmup, with_e2e=True):
         "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "how": "pinned host image batch + target dict -> H2D every step, loss scalar D2H + sync every step"},
         "gpu_launches": int(launches),
-        "launch": "eager (autograd tape)" if args.no_graph else "CUDA graph replay of the whole step (trainer.GraphedCtdetStep)",
+        "launch": launch_mode,
         "precision": "bf16 activations / operands, fp32 accumulation, fp32 master weights, gradients and Adam state",
     }
 

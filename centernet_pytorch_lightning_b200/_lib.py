@@ -78,6 +78,10 @@ def _declare(lib):
         "cnb_dcnv2_im2col": (c_int, [P, P, c_int, P] + [c_int] * 4 + [P]),
         "cnb_dcnv2_col2im": (c_int, [P, P, c_int, P, P, P] + [c_int] * 4 + [P]),
         "cnb_adam_step": (c_int, [P, P, P, P, c_longlong, c_float, c_float, c_float, c_float, c_int, P, P, c_float, P]),
+        "cnb_p2p_signal_bytes": (c_size_t, []),
+        "cnb_p2p_next_step": (c_int, [P, P]),
+        "cnb_p2p_allreduce": (c_int, [P, P, P, P, P, c_longlong, c_longlong, c_int, c_int, c_int, c_int, P]),
+        "cnb_p2p_wait": (c_int, [P, P, c_int, c_int, P]),
         # fp32-strict mode
         "cnb_strict_conv2d_f32": (c_int, [P] * 6 + [c_int] * 10 + [P]),
         "cnb_strict_dcn_im2col_f32": (c_int, [P, P, P] + [c_int] * 4 + [P]),

@@ -22,8 +22,13 @@ from . import _lib
 
 
 class FlatTrainer:
-    def __init__(self, modules, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, bucket_mb=8.0, process_group=None, world_size=None):
-        """modules: iterable of nn.Modules (backbone, heads) already on their CUDA device."""
+    def __init__(self, modules, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, bucket_mb=8.0, process_group=None, world_size=None,
+                 comm=None):
+        """modules: iterable of nn.Modules (backbone, heads) already on their CUDA device.
+        comm: "nccl" (default: torch.distributed all_reduce per bucket) or "p2p" (this library's own kernel over NVLink
+        peer memory, csrc/p2p_allreduce.cu: the gradient buffer is symmetric memory; CNB_GRAD_COMM selects it too)."""
+        import os
+        self.comm = comm or os.environ.get("CNB_GRAD_COMM", "nccl")
         params, seen = [], set()
         for m in modules:
             for p in m.parameters():
@@ -45,14 +50,30 @@ class FlatTrainer:
         self.world = world_size
         # ---- flat buffers (16-byte aligned segments)
         order = list(reversed(params))                       # gradient-production order, approximately
+        limit = int(bucket_mb * (1 << 20) / 4)
         offs, total = {}, 0
+        self.buckets = []                                     # [start, end, n_params]: contiguous slices of the buffers
+        start, count = 0, 0
         for p in order:
             offs[id(p)] = total
             total += (p.numel() + 3) // 4 * 4
+            count += 1
+            if total - start >= limit:
+                total = (total + 31) // 32 * 32               # bucket ends on 32 floats: shards of 4 floats x <= 8 ranks
+                self.buckets.append([start, total, count])
+                start, count = total, 0
+        if count:
+            total = (total + 31) // 32 * 32
+            self.buckets.append([start, total, count])
         self.numel = total
         dev = self.device
         self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._p2p = None
+        if self.comm == "p2p" and self.world > 1:
+            self._p2p = _P2PComm(total, dev, self.pg, len(self.buckets))
+            self.flat_g = self._p2p.grad
+        else:
+            self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_m = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_v = torch.zeros(total, dtype=torch.float32, device=dev)
         with torch.no_grad():
@@ -62,18 +83,6 @@ class FlatTrainer:
                 view.copy_(p.detach().float())
                 p.data = view                                  # the parameter now lives in the flat buffer
                 p._cnb_grad = self.flat_g[o:o + n].view_as(p)
-        # ---- buckets: contiguous slices of the flat gradient buffer
-        limit = int(bucket_mb * (1 << 20) / 4)
-        self.buckets = []                                     # [start, end, n_params]
-        start, count = 0, 0
-        for p in order:
-            end = offs[id(p)] + (p.numel() + 3) // 4 * 4
-            count += 1
-            if end - start >= limit:
-                self.buckets.append([start, end, count])
-                start, count = end, 0
-        if count:
-            self.buckets.append([start, total, count])
         self._bucket_of = {}
         bi = 0
         for p in order:
@@ -99,7 +108,10 @@ class FlatTrainer:
         if self._launched[b]:
             return
         self._launched[b] = True
-        if self.world > 1:
+        if self._p2p is not None:
+            s, e, _ = self.buckets[b]
+            self._p2p.allreduce(b, s, e - s)
+        elif self.world > 1:
             s, e, _ = self.buckets[b]
             # async: NCCL's stream waits for everything enqueued on the compute stream so far (the kernels that wrote
             # this bucket), the compute stream does not wait for NCCL until `finish_backward`
@@ -107,6 +119,8 @@ class FlatTrainer:
         self.launch_log.append(b)
 
     def zero_grad(self):
+        if self._p2p is not None:
+            self._p2p.next_step()
         self.flat_g.zero_()
         self._pending = [b[2] for b in self.buckets]
         self._launched = [False] * len(self.buckets)
@@ -121,6 +135,8 @@ class FlatTrainer:
             self._launch(b)
         for w in self._works:
             w.wait()
+        if self._p2p is not None:
+            self._p2p.wait_all()
         return overlapped
 
     def optimizer_step(self):
@@ -140,6 +156,58 @@ class FlatTrainer:
     def grads(self):
         """name-free access for tests: parameter -> its gradient view"""
         return {id(p): p._cnb_grad for p in self.params}
+
+
+class _P2PComm:
+    """Symmetric-memory gradient buffer + signal pads for csrc/p2p_allreduce.cu (torch.distributed._symmetric_memory is
+    the plumbing: allocation, handle exchange, peer / multicast mappings)."""
+
+    def __init__(self, numel, device, group, nslots):
+        import ctypes
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else dist.group.WORLD
+        L = _lib.lib()
+        self.device, self.nslots = device, nslots
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.grad = symm.empty(numel, dtype=torch.float32, device=device)
+        self.grad.zero_()
+        self.sig = symm.empty(L.cnb_p2p_signal_bytes() // 4, dtype=torch.int32, device=device)
+        self.sig.zero_()
+        hg, hs = symm.rendezvous(self.grad, group), symm.rendezvous(self.sig, group)
+        self._handles = (hg, hs)
+        self.bufs = (ctypes.c_void_p * self.world)(*[int(p) for p in hg.buffer_ptrs])
+        self.sigs = (ctypes.c_void_p * self.world)(*[int(p) for p in hs.buffer_ptrs])
+        import os
+        mc = int(hg.multicast_ptr) if (hg.has_multicast_support(device.type, device.index or 0) if hasattr(
+            hg, "has_multicast_support") else False) else 0
+        self.multicast = mc if os.environ.get("CNB_P2P_MULTICAST", "1") != "0" else 0
+        self.counters = torch.zeros(64, dtype=torch.int32, device=device)
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
+        self.stream = torch.cuda.Stream(device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)
+
+    def next_step(self):
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().cnb_p2p_next_step(_lib.ptr(self.epoch), _lib.stream_ptr(self.device)), "cnb_p2p_next_step")
+
+    def allreduce(self, slot, off, n):
+        """on the communication stream, ordered after everything enqueued on the compute stream so far"""
+        import ctypes
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().cnb_p2p_allreduce(self.bufs, self.sigs, ctypes.c_void_p(self.multicast) if self.multicast else None,
+                                                    _lib.ptr(self.counters), _lib.ptr(self.epoch), off, n, self.rank,
+                                                    self.world, slot, 16, ctypes.c_void_p(self.stream.cuda_stream)),
+                       "cnb_p2p_allreduce")
+
+    def wait_all(self):
+        import ctypes
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().cnb_p2p_wait(_lib.ptr(self.sig), _lib.ptr(self.epoch), self.nslots, self.world,
+                                               ctypes.c_void_p(self.stream.cuda_stream)), "cnb_p2p_wait")
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
 
 
 def ctdet_training_step(model, head, trainer, x, target, weights=(1.0, 0.1, 1.0)):

@@ -265,6 +265,22 @@ int cnb_adam_step(float* p, const float* g, float* m, float* v, long long n, flo
                   float beta2, float eps, int step, const int* step_dev, const float* lr_dev, float grad_scale,
                   cnb_stream_t stream);
 
+/* Gradient all-reduce over NVLink peer memory (no NCCL on the data path): every rank's flat gradient buffer is a
+ * symmetric-memory allocation mapped into all peers; one kernel per rank and bucket publishes "written", waits for the
+ * peers, reduces its 1/world shard over all peers' buffers (peer loads; multimem.ld_reduce in the switch when a
+ * multicast mapping is given) and stores the sum back to every peer.  bufs / sigs: HOST arrays of `world` device
+ * pointers (buffer and signal pad of each rank, cnb_p2p_signal_bytes() bytes each, zero-initialised); counters: >= 64
+ * zeroed u32 (local); epoch_dev: device u32 advanced once per step by cnb_p2p_next_step; [off, off+n) floats with
+ * off % 4 == 0 and n % (4*world) == 0; slot < 64 identifies the bucket.  cnb_p2p_wait blocks the stream until the
+ * shards of slots [0, nslots) have arrived from every peer. */
+size_t cnb_p2p_signal_bytes(void);
+int cnb_p2p_next_step(unsigned int* epoch_dev, cnb_stream_t stream);
+int cnb_p2p_allreduce(float* const* bufs, unsigned int* const* sigs, float* multicast_or_null,
+                      unsigned int* counters, const unsigned int* epoch_dev, long long off, long long n,
+                      int rank, int world, int slot, int ctas, cnb_stream_t stream);
+int cnb_p2p_wait(const unsigned int* sig_local, const unsigned int* epoch_dev, int nslots, int world,
+                 cnb_stream_t stream);
+
 /* ---------------------------------------------------------------- fp32-strict mode (NCHW fp32, CUDA cores) ---- */
 /* The same operators in the reference's own precision, for small-shape END-TO-END parity checks against the fp32
  * CPU path (hard part 2).  Not the measured fast path. */
