@@ -134,15 +134,17 @@ __global__ void __launch_bounds__(256) soft_nms_kernel(float* __restrict__ boxes
         s_box[maxpos * ncol + tid] = t;
       }
       __syncthreads();
-      const double tx1 = s_box[i * ncol], ty1 = s_box[i * ncol + 1], tx2 = s_box[i * ncol + 2], ty2 = s_box[i * ncol + 3];
+      // numba's typing of the original: box coordinates are float32, differences / min / max are formed in float32 and
+      // only the "+ 1" promotes to float64 -- reproduced literally so that threshold decisions cannot differ
+      const float tx1 = s_box[i * ncol], ty1 = s_box[i * ncol + 1], tx2 = s_box[i * ncol + 2], ty2 = s_box[i * ncol + 3];
       for (int p = i + 1 + tid; p < N; p += 256) {
-        const double x1 = s_box[p * ncol], y1 = s_box[p * ncol + 1], x2 = s_box[p * ncol + 2], y2 = s_box[p * ncol + 3];
-        const double area = (x2 - x1 + 1) * (y2 - y1 + 1);
-        const double iw = fmin(tx2, x2) - fmax(tx1, x1) + 1;
+        const float x1 = s_box[p * ncol], y1 = s_box[p * ncol + 1], x2 = s_box[p * ncol + 2], y2 = s_box[p * ncol + 3];
+        const double area = ((double)(x2 - x1) + 1) * ((double)(y2 - y1) + 1);
+        const double iw = (double)(fminf(tx2, x2) - fmaxf(tx1, x1)) + 1;
         if (iw > 0) {
-          const double ih = fmin(ty2, y2) - fmax(ty1, y1) + 1;
+          const double ih = (double)(fminf(ty2, y2) - fmaxf(ty1, y1)) + 1;
           if (ih > 0) {
-            const double ua = (tx2 - tx1 + 1) * (ty2 - ty1 + 1) + area - iw * ih;
+            const double ua = ((double)(tx2 - tx1) + 1) * ((double)(ty2 - ty1) + 1) + area - iw * ih;
             const double ov = iw * ih / ua;
             double weight;
             if (method == 1) weight = ov > Nt ? 1 - ov : 1;
