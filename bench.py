@@ -550,25 +550,37 @@ def run_b200(args, rank, local_rank, world):
         hw = (RES // 4) ** 2
         dec_bytes = BATCH * (80 * hw * 4 + 100 * 16 + 100 * 24)
         dec_kernel = "decode_stream_kernel + decode_merge_kernel (fused nms+topk+gather: warp-autonomous streaming scan, per-image merge; timed together with the workspace memset)"
-    for _ in range(3):
-        dec()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    dts = []
-    for _ in range(10):
-        flush.fill_(1)                                 # evict L2 (256 MB > 126 MB)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        dec()
-        b.record()
-        torch.cuda.synchronize()
-        dts.append(a.elapsed_time(b))
-    dec_ms = statistics.median(dts)
+
+    def time_decode(fn):
+        for _ in range(3):
+            fn()
+        dts = []
+        for _ in range(10):
+            flush.fill_(1)                                 # evict L2 (256 MB > 126 MB)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            dts.append(a.elapsed_time(b))
+        return statistics.median(dts)
+
+    dec_ms = time_decode(dec)
     dec_gbs = dec_bytes / (dec_ms * 1e-3) / 1e9
     dec_traffic = tj.get("decode [32,80,128,128]", {}).get("bytes") if (args.config == 2) else None
+    variants = {"network head maps of this step (random-init weights: heat logits saturate, plateaus of equal scores)":
+                {"ms": dec_ms, "GB/s": dec_gbs, "frac": dec_gbs / pk["hbm"]}}
+    if not pose:   # the decode micro-benchmark on standalone maps in two distributions
+        from centernet_pytorch_lightning_b200.utils import synthetic
+        for kind, label in (("uniform", "distinct-uniform (SURVEY 8d-i)"), ("bumps", "COCO-shaped Gaussian bumps (SURVEY 8d-ii)")):
+            hm, wh, rg = (torch.from_numpy(t).to(dev) for t in synthetic.ctdet_maps(BATCH, 80, RES // 4, RES // 4, seed=1, kind=kind))
+            ms = time_decode(lambda: ctdet_decode(hm, wh, reg=rg))
+            variants[label] = {"ms": ms, "GB/s": dec_bytes / (ms * 1e-3) / 1e9, "frac": dec_bytes / (ms * 1e-3) / 1e9 / pk["hbm"]}
     roofline_decode = {"bound": "hbm", "kernel": dec_kernel,
                        "achieved": dec_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": dec_gbs / pk["hbm"],
                        "traffic": dec_traffic, "ms": dec_ms, "bytes_per_launch": dec_bytes, "peak_source": pk["src"],
-                       "l2": "flushed (256 MB write) before every timed launch"}
+                       "l2": "flushed (256 MB write) before every timed launch", "by_input": variants}
     # host-buffer C-ABI entry (cnb_ctdet_decode_host): H2D of the maps + decode + D2H inside the call
     decode_host = None
     if not pose:
