@@ -179,8 +179,10 @@ class _P2PComm:
         self.bufs = (ctypes.c_void_p * self.world)(*[int(p) for p in hg.buffer_ptrs])
         self.sigs = (ctypes.c_void_p * self.world)(*[int(p) for p in hs.buffer_ptrs])
         import os
-        mc = int(hg.multicast_ptr) if (hg.has_multicast_support(device.type, device.index or 0) if hasattr(
-            hg, "has_multicast_support") else False) else 0
+        try:
+            mc = int(hg.multicast_ptr)          # 0 when the fabric / driver offers no multicast mapping (no NVLS)
+        except Exception:
+            mc = 0
         self.multicast = mc if os.environ.get("CNB_P2P_MULTICAST", "1") != "0" else 0
         self.counters = torch.zeros(64, dtype=torch.int32, device=device)
         self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
