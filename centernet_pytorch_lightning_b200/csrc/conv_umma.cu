@@ -27,6 +27,9 @@ int conv_tma_run(const cnb_conv_desc* d, const void* x, const void* wpk, const f
 bool conv_rows_supported(const cnb_conv_desc* d);                // conv_rows.cu
 int conv_rows_run(const cnb_conv_desc* d, const void* x, const void* wpk, const float* scale, const float* shift,
                   const void* res, void* y, cudaStream_t st);
+bool dcn_fp_supported(const cnb_conv_desc* d, int om_cstride);                  // dcn_fp.cu
+int dcn_fp_run(const cnb_conv_desc* d, const void* x, const float* om, int om_cstride, const void* wpk,
+               const float* scale, const float* shift, void* y, cudaStream_t st);
 bool dcn_ws_supported(const cnb_conv_desc* d, int om_cstride);                  // dcn_ws.cu
 int dcn_ws_run(const cnb_conv_desc* d, const void* x, const float* om, int om_cstride, const void* wpk,
                const float* scale, const float* shift, void* y, cudaStream_t st);
@@ -440,6 +443,8 @@ static int run_conv(const cnb_conv_desc* d, const void* x, const float* om, int 
                   "dcnv2: only 3x3 / stride 1 / pad 1 / dil 1 (the reference's configuration)");
     CNB_CHECK_ARG(d->Ci % 8 == 0, "dcnv2: Ci must be a multiple of 8");
     CNB_CHECK_ARG(d->out_nchw_f32 == 0 && ((uintptr_t)om & 15) == 0, "dcnv2: NHWC bf16 output, 16-byte aligned om");
+    // sampling footprint staged in shared memory (dcn_fp.cu); CNB_DCN_IMPL=ws keeps the global-gather kernel
+    if (dcn_fp_supported(d, om_cstride)) return dcn_fp_run(d, x, om, om_cstride, wpk, scale, shift, y, st);
     // warp-specialised sampler kernel (dcn_ws.cu); CNB_DCN_IMPL=v1 keeps the gather kernel below for A/B runs
     if (dcn_ws_supported(d, om_cstride)) return dcn_ws_run(d, x, om, om_cstride, wpk, scale, shift, y, st);
   }

@@ -53,9 +53,8 @@ struct DArgs {
   int M, m_tiles;
   int BN;          // = Co rounded up to 16, <= 256
   int nkb;         // 9 * Ci/64
-  int kper;        // K blocks (taps) per pipeline stage: 2 when two such stages fit (stage handshake amortised)
-  int nsteps;      // ceil(nkb / kper)
-  u32 bstage;      // bytes of one K block's weight tile inside a stage (b_bytes rounded up to 1 KB)
+  int ngroups;     // sampler groups (1, 2 or 4): K block k of the CTA's stream is sampled by group k % ngroups
+  u32 bstage;      // bytes of the K block's weight tile inside its stage (b_bytes rounded up to 1 KB)
   int stages;
   u32 b_bytes, stage_bytes, tmem_cols, acc_stride, idesc;
   long long* trace;  // CNB_DCN_TRACE: clock stamps of CTA 0 (see dcn_ws_run)
@@ -123,7 +122,7 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
 
   if (tid == 0) {
     for (int s = 0; s < a.stages; ++s) {
-      mbar_init(&s_full[s], NPROD_WARPS + 1);   // one arrival per sampler warp + the weight tile's expect_tx
+      mbar_init(&s_full[s], NPROD_WARPS / a.ngroups + 1);   // one arrival per sampler warp of the stage's group + the weight tile's expect_tx
       mbar_init(&s_empty[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -156,125 +155,131 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
 
   if (warp < NPROD_WARPS) {
     // =============================== samplers ===============================================================
-    // A thread owns ONE pixel row of the tile and a PAIR of 16-byte channel chunks (16 channels): the table entry
-    // and the corner addresses are worked out once per 32 bytes sampled, and each corner is one 256-bit load when the
-    // tensor allows it (32-byte aligned pixels), two 128-bit loads otherwise.
-    const int cp = tid & 3;             // chunk pair inside the 64-channel slab: chunks 2cp, 2cp+1
-    const int row = tid >> 2;           // 0..127
+    // The 16 sampler warps form `ngroups` independent groups; K block k of the CTA's stream (tile-major, then
+    // slab-major / tap-minor) belongs to group k % ngroups and to ring stage k % stages, so the groups run out of
+    // phase: while one group waits for its gathers the other blends (one lock-stepped group leaves L1 idle while it
+    // blends and the issue slots idle while it loads).  Inside a group a thread owns the pixel rows
+    // r0, r0 + 128/ngroups, ... and a PAIR of 16-byte channel chunks (4 threads cover the 128-byte line of one
+    // corner: one L1 wavefront per pixel); each corner is one 256-bit load when the tensor allows it.
+    const int ng = a.ngroups;
+    const int wpg = NPROD_WARPS / ng;                 // warps per group
+    const int grp = warp / wpg;
+    const int ltid = tid - grp * wpg * 32;
+    const int cp = ltid & 3;                          // chunk pair inside the 64-channel slab: chunks 2cp, 2cp+1
+    const int row0 = ltid >> 2;
+    const int row_stride = BM / ng;
     const u32 cs = (u32)d.x_cstride;
     const u32 row_step = (u32)d.Wi * cs;
     const bool wide_ld = ((d.x_cstride | d.x_coffset) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.x) & 31) == 0;
-    const u32 dst_lo = (u32)row * 128u + ((u32)((2 * cp) ^ (row & 7)) << 4);
-    const u32 dst_hi = (u32)row * 128u + ((u32)((2 * cp + 1) ^ (row & 7)) << 4);
-    u32 s = 0, ph = 0, t = 0;
-    for (int tile = tile_begin; tile < tile_end; ++tile, ++t) {
+    const bool issuer = (warp == grp * wpg);
+    const int nslabs = d.Ci >> 6;
+    u32 s = (u32)grp % (u32)a.stages, ph = ((u32)grp / (u32)a.stages) & 1u, t = 0;
+    int slab = 0, tap = grp;                          // ngroups <= 4 < 9
+    bool have_tab = false;
+    const long long kb_end = (long long)(tile_end - tile_begin) * a.nkb;
+    for (long long kb = grp; kb < kb_end; kb += ng) {
       const u32 tb = t & 1u;
-      mbar_wait_parked(&s_tabfull[tb], (t >> 1) & 1u);
-      const float4* tw = s_tabw + tb * NTAB + row * 9;
-      const u32* tbs = s_tabb + tb * NTAB + row * 9;
-      int slab = 0, tap = 0;
-      for (int st = 0; st < a.nsteps; ++st) {
-        const int kc = min(a.kper, a.nkb - st * a.kper);   // K blocks (taps) in this stage
-        mbar_wait_parked(&s_empty[s], ph ^ 1u);
-        if (tid == 0) DCN_STAMP(0, (int)(t * a.nsteps) + st);
-        const u32 sa0 = smem_base + s * a.stage_bytes;
-        if (warp == 0 && elect_one()) {   // (elected, not `tid == 0`: uniform operands, no broadcast loop; a separate
-                                          // warp for this was measured slower: 26 warps contend more than this costs)
-          mbar_expect_tx(&s_full[s], (u32)kc * a.b_bytes);
-          int tp = tap, sl = slab;
-          for (int j = 0; j < kc; ++j) {
-            tma_load_2d(sa0 + (u32)a.kper * A_BYTES + (u32)j * a.bstage, &tmB, tp * d.Ci + sl * 64, 0, &s_full[s]);
-            if (++tp == 9) {
-              tp = 0;
-              ++sl;
-            }
+      if (!have_tab) {
+        mbar_wait_parked(&s_tabfull[tb], (t >> 1) & 1u);
+        have_tab = true;
+      }
+      mbar_wait_parked(&s_empty[s], ph ^ 1u);
+      if (ltid == 0 && grp < 2) DCN_STAMP(2 * grp, (int)(kb / ng));
+      const u32 sa = smem_base + s * a.stage_bytes;
+      if (issuer && elect_one()) {   // (elected: uniform operands, no broadcast loop)
+        mbar_expect_tx(&s_full[s], a.b_bytes);
+        tma_load_2d(sa + A_BYTES, &tmB, tap * d.Ci + slab * 64, 0, &s_full[s]);
+      }
+      const __nv_bfloat16* xs = a.x + d.x_coffset + slab * 64 + cp * 16;
+      for (int row = row0; row < BM; row += row_stride) {
+        const u32 dst_lo = (u32)row * 128u + ((u32)((2 * cp) ^ (row & 7)) << 4);
+        const u32 dst_hi = (u32)row * 128u + ((u32)((2 * cp + 1) ^ (row & 7)) << 4);
+        u32 q[4][8];
+        const float4 w = s_tabw[tb * NTAB + row * 9 + tap];
+        const u32 b = s_tabb[tb * NTAB + row * 9 + tap];
+        const u32 o00 = b & 0x3FFFFFFFu;                       // element offset of the clamped (y0, x0) pixel
+        const u32 o01 = o00 + (((b >> 30) & 1u) ? cs : 0u);
+        const u32 ddy = (b >> 31) ? row_step : 0u;
+        const u32 off[4] = {o00, o01, o00 + ddy, o01 + ddy};
+        if (DCN_DBG(a) & 1) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) q[c][e] = off[c] + e;
+        } else if (wide_ld) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(q[c][0]), "=r"(q[c][1]), "=r"(q[c][2]), "=r"(q[c][3]), "=r"(q[c][4]), "=r"(q[c][5]),
+                           "=r"(q[c][6]), "=r"(q[c][7])
+                         : "l"(xs + off[c]));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint4 lo = __ldg(reinterpret_cast<const uint4*>(xs + off[c]));
+            const uint4 hi = __ldg(reinterpret_cast<const uint4*>(xs + off[c] + 8));
+            q[c][0] = lo.x; q[c][1] = lo.y; q[c][2] = lo.z; q[c][3] = lo.w;
+            q[c][4] = hi.x; q[c][5] = hi.y; q[c][6] = hi.z; q[c][7] = hi.w;
           }
         }
-        for (int j = 0; j < kc; ++j) {
-        const u32 sa = sa0 + (u32)j * A_BYTES;
-        const __nv_bfloat16* xs = a.x + d.x_coffset + slab * 64 + cp * 16;
-        {
-          u32 q[4][8];
-          const float4 w = tw[tap];
-          const u32 b = tbs[tap];
-          const u32 o00 = b & 0x3FFFFFFFu;                       // element offset of the clamped (y0, x0) pixel
-          const u32 o01 = o00 + (((b >> 30) & 1u) ? cs : 0u);
-          const u32 ddy = (b >> 31) ? row_step : 0u;
-          const u32 off[4] = {o00, o01, o00 + ddy, o01 + ddy};
-          if (DCN_DBG(a) & 1) {
+        if (!(DCN_DBG(a) & 2)) {
+          u32 o[8];
+          if constexpr (BLEND_BF16) {
+            const u32 wh0 = pack_bf16x2(w.x, w.x), wh1 = pack_bf16x2(w.y, w.y), wh2 = pack_bf16x2(w.z, w.z),
+                      wh3 = pack_bf16x2(w.w, w.w);
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-#pragma unroll
-              for (int e = 0; e < 8; ++e) q[c][e] = off[c] + e;
-          } else if (wide_ld) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-              asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                           : "=r"(q[c][0]), "=r"(q[c][1]), "=r"(q[c][2]), "=r"(q[c][3]), "=r"(q[c][4]), "=r"(q[c][5]),
-                             "=r"(q[c][6]), "=r"(q[c][7])
-                           : "l"(xs + off[c]));
+            for (int e = 0; e < 8; ++e) {
+              u32 acc;
+              asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(acc) : "r"(wh0), "r"(q[0][e]));
+              asm("fma.rn.bf16x2 %0, %1, %2, %0;" : "+r"(acc) : "r"(wh1), "r"(q[1][e]));
+              asm("fma.rn.bf16x2 %0, %1, %2, %0;" : "+r"(acc) : "r"(wh2), "r"(q[2][e]));
+              asm("fma.rn.bf16x2 %0, %1, %2, %0;" : "+r"(acc) : "r"(wh3), "r"(q[3][e]));
+              o[e] = acc;
+            }
           } else {
+            const u64 w0 = dup2(w.x), w1 = dup2(w.y), w2 = dup2(w.z), w3 = dup2(w.w);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const uint4 lo = __ldg(reinterpret_cast<const uint4*>(xs + off[c]));
-              const uint4 hi = __ldg(reinterpret_cast<const uint4*>(xs + off[c] + 8));
-              q[c][0] = lo.x; q[c][1] = lo.y; q[c][2] = lo.z; q[c][3] = lo.w;
-              q[c][4] = hi.x; q[c][5] = hi.y; q[c][6] = hi.z; q[c][7] = hi.w;
+            for (int e = 0; e < 8; ++e) {
+              // bf16 -> fp32 is a 16-bit shift: low element = v << 16, high element = v & 0xffff0000;
+              // the (low, high) pair is blended with one packed fp32x2 FMA per corner
+              u64 acc = mul2(w0, pair_from_bf16x2(q[0][e]));
+              acc = fma2(w1, pair_from_bf16x2(q[1][e]), acc);
+              acc = fma2(w2, pair_from_bf16x2(q[2][e]), acc);
+              acc = fma2(w3, pair_from_bf16x2(q[3][e]), acc);
+              float lo, hi;
+              asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc));
+              o[e] = pack_bf16x2(lo, hi);
             }
           }
-          if (!(DCN_DBG(a) & 2)) {
-            u32 o[8];
-            if constexpr (BLEND_BF16) {
-              const u32 wh0 = pack_bf16x2(w.x, w.x), wh1 = pack_bf16x2(w.y, w.y), wh2 = pack_bf16x2(w.z, w.z),
-                        wh3 = pack_bf16x2(w.w, w.w);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                u32 acc;
-                asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(acc) : "r"(wh0), "r"(q[0][e]));
-                asm("fma.rn.bf16x2 %0, %1, %2, %0;" : "+r"(acc) : "r"(wh1), "r"(q[1][e]));
-                asm("fma.rn.bf16x2 %0, %1, %2, %0;" : "+r"(acc) : "r"(wh2), "r"(q[2][e]));
-                asm("fma.rn.bf16x2 %0, %1, %2, %0;" : "+r"(acc) : "r"(wh3), "r"(q[3][e]));
-                o[e] = acc;
-              }
-            } else {
-              const u64 w0 = dup2(w.x), w1 = dup2(w.y), w2 = dup2(w.z), w3 = dup2(w.w);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                // bf16 -> fp32 is a 16-bit shift: low element = v << 16, high element = v & 0xffff0000;
-                // the (low, high) pair is blended with one packed fp32x2 FMA per corner
-                u64 acc = mul2(w0, pair_from_bf16x2(q[0][e]));
-                acc = fma2(w1, pair_from_bf16x2(q[1][e]), acc);
-                acc = fma2(w2, pair_from_bf16x2(q[2][e]), acc);
-                acc = fma2(w3, pair_from_bf16x2(q[3][e]), acc);
-                float lo, hi;
-                asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc));
-                o[e] = pack_bf16x2(lo, hi);
-              }
-            }
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sa + dst_lo), "r"(o[0]), "r"(o[1]), "r"(o[2]),
-                         "r"(o[3])
-                         : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sa + dst_hi), "r"(o[4]), "r"(o[5]), "r"(o[6]),
-                         "r"(o[7])
-                         : "memory");
-          }
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sa + dst_lo), "r"(o[0]), "r"(o[1]), "r"(o[2]),
+                       "r"(o[3])
+                       : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sa + dst_hi), "r"(o[4]), "r"(o[5]), "r"(o[6]),
+                       "r"(o[7])
+                       : "memory");
         }
-        if (++tap == 9) {
-          tap = 0;
-          ++slab;
-        }
-        }   // K blocks of the stage
-        if (!(DCN_DBG(a) & 8)) fence_proxy_async_smem();       // generic-proxy stores -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_full[s]);
-        if (tid == 0) DCN_STAMP(1, (int)(t * a.nsteps) + st);
-        if (++s == (u32)a.stages) {
-          s = 0;
-          ph ^= 1u;
+      }   // rows of this thread
+      if (!(DCN_DBG(a) & 8)) fence_proxy_async_smem();       // generic-proxy stores -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_full[s]);
+      if (ltid == 0 && grp < 2) DCN_STAMP(2 * grp + 1, (int)(kb / ng));
+      // next K block of this group: ng further in the stream and in the ring
+      s += (u32)ng;
+      while (s >= (u32)a.stages) {
+        s -= (u32)a.stages;
+        ph ^= 1u;
+      }
+      tap += ng;
+      if (tap >= 9) {
+        tap -= 9;
+        if (++slab == nslabs) {   // the group leaves this tile
+          slab = 0;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_tabempty[tb]);
+          ++t;
+          have_tab = false;
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_tabempty[tb]);
     }
   } else if (warp < W_MMA) {
     // =============================== setup: (pixel, tap) -> weights + corner address =========================
@@ -298,7 +303,6 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
       const u32 tb = t & 1u;
       mbar_wait_parked(&s_tabempty[tb], ((t >> 1) & 1u) ^ 1u);
       mbar_wait_parked(&s_omfull[tb], (t >> 1) & 1u);
-      if (stid == 0) DCN_STAMP(4, (int)t);
       const float* oms = s_om + tb * (BM * OM_CS);
       const int m0 = tile * BM;
 #pragma unroll 3
@@ -350,9 +354,8 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
     {   // all lanes walk the loop (warp-uniform operands -> uniform registers); one elected lane issues
       u32 s = 0, ph = 0, t = 0;
       const u64 da0 = make_sdesc(smem_base, 16, 1024, 2);
-      const u64 db0 = make_sdesc(smem_base + (u32)a.kper * A_BYTES, 16, 1024, 2);
+      const u64 db0 = make_sdesc(smem_base + A_BYTES, 16, 1024, 2);
       const u32 stage16 = a.stage_bytes >> 4;
-      const u32 bstage16 = a.bstage >> 4;
       u32 soff16 = 0;
       for (int tile = tile_begin; tile < tile_end; ++tile, ++t) {
         const u32 acc = t & 1u, acc_ph = (t >> 1) & 1u;
@@ -360,26 +363,20 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
         tc_fence_after();
         const u32 tmem_d = tmem_base + acc * a.acc_stride;
         u32 accumulate = 0;
-        for (int st = 0; st < a.nsteps; ++st) {
-          const int kc = min(a.kper, a.nkb - st * a.kper);
+        for (int kb = 0; kb < a.nkb; ++kb) {
           mbar_wait_parked(&s_full[s], ph);
           tc_fence_after();
-          if (lane == 0) DCN_STAMP(2, (int)(t * a.nsteps) + st);
+          if (lane == 0) DCN_STAMP(4, (int)(t * a.nkb) + kb);
           if (elect_one()) {
-            u64 da = da0 + (u64)soff16, db = db0 + (u64)soff16;
+            const u64 da = da0 + (u64)soff16, db = db0 + (u64)soff16;
             if (!(DCN_DBG(a) & 4)) {
-              for (int j = 0; j < kc; ++j) {
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)   // +32 bytes of K inside the swizzle atom
-                  umma_bf16(tmem_d, da + (u64)(2 * kk), db + (u64)(2 * kk), a.idesc, (kk | j) == 0 ? accumulate : 1u);
-                da += (u64)(A_BYTES >> 4);
-                db += (u64)bstage16;
-              }
+              for (int kk = 0; kk < 4; ++kk)   // +32 bytes of K inside the swizzle atom
+                umma_bf16(tmem_d, da + (u64)(2 * kk), db + (u64)(2 * kk), a.idesc, kk == 0 ? accumulate : 1u);
             }
             umma_commit(&s_empty[s]);
           }
           __syncwarp();
-          if (lane == 0) DCN_STAMP(3, (int)(t * a.nsteps) + st);
           accumulate = 1;
           soff16 += stage16;
           if (++s == (u32)a.stages) {
@@ -457,19 +454,16 @@ int dcn_ws_run(const cnb_conv_desc* d, const void* x, const float* om, int om_cs
   a.bstage = (a.b_bytes + 1023u) & ~1023u;
   const size_t fixed = (size_t)2 * NTAB * (sizeof(float4) + sizeof(u32)) + (size_t)2 * BM * OM_CS * 4 +
                        (size_t)a.BN * 8 + 1024;
-  // Every sampler warp takes part in every stage, so a stage costs one warp's dependent chain plus a ~400-clock
-  // handshake (fence, arrive, wait); the ring depth does not matter (2..6 stages measured equal).  Two taps per stage
-  // halve the handshakes when two such stages fit (CNB_DCN_KPER / CNB_DCN_STAGES override).
-  static const int env_kper = [] { const char* e = getenv("CNB_DCN_KPER"); return e ? atoi(e) : 0; }();
+  // One ring stage = one K block (sampled operand 16 KB + weight tile); the sampler groups take the K blocks of the
+  // CTA's stream round-robin (CNB_DCN_GROUPS / CNB_DCN_STAGES override).
+  static const int env_groups = [] { const char* e = getenv("CNB_DCN_GROUPS"); return e ? atoi(e) : 0; }();
   static const int env_stages = [] { const char* e = getenv("CNB_DCN_STAGES"); return e ? atoi(e) : 0; }();
-  a.kper = env_kper > 0 ? env_kper : 2;
-  if (a.kper > 3) a.kper = 3;
-  while (a.kper > 1 && (size_t)2 * a.kper * (A_BYTES + a.bstage) + fixed > 220 * 1024) --a.kper;
-  a.stage_bytes = (u32)a.kper * (A_BYTES + a.bstage);
-  a.nsteps = (a.nkb + a.kper - 1) / a.kper;
-  a.stages = env_stages > 0 ? env_stages : 3;
+  a.ngroups = env_groups == 1 || env_groups == 2 || env_groups == 4 ? env_groups : 2;
+  a.stage_bytes = A_BYTES + a.bstage;
+  a.stages = env_stages > 0 ? env_stages : MAX_STAGES;
   if (a.stages > MAX_STAGES) a.stages = MAX_STAGES;
   while (a.stages > 2 && (size_t)a.stages * a.stage_bytes + fixed > 220 * 1024) --a.stages;
+  while (a.ngroups > a.stages) a.ngroups >>= 1;   // a group must not lap the ring (mbarrier phase parity)
   a.acc_stride = (u32)round_up(a.BN, 32);
   a.tmem_cols = 32;
   while (a.tmem_cols < 2 * a.acc_stride) a.tmem_cols <<= 1;
@@ -521,14 +515,15 @@ int dcn_ws_run(const cnb_conv_desc* d, const void* x, const float* om, int om_cs
       static long long h[8 * 512];
       cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
       const long long t0 = h[0];
-      fprintf(stderr, "dcn_ws trace Ci=%d Co=%d nkb=%d stages=%d (clocks since the first K block)\n", d->Ci, d->Co, a.nkb,
-              a.stages);
+      fprintf(stderr, "dcn_ws trace Ci=%d Co=%d nkb=%d stages=%d groups=%d (clocks since the first K block)\n", d->Ci, d->Co,
+              a.nkb, a.stages, a.ngroups);
       for (int k = 0; k < 45 && h[k]; ++k)
-        fprintf(stderr, "k=%3d sampler0 got_stage %7lld arrived %7lld | mma got_data %7lld committed %7lld\n", k, h[k] - t0,
-                h[512 + k] - t0, h[1024 + k] - t0, h[1536 + k] - t0);
-      for (int t = 0; t < 6 && h[2048 + t]; ++t)
-        fprintf(stderr, "tile %d setup start %7lld table_done %7lld | epilogue start %7lld done %7lld\n", t, h[2048 + t] - t0,
-                h[2560 + t] - t0, h[3072 + t] - t0, h[3584 + t] - t0);
+        fprintf(stderr, "k=%3d group0 got_stage %7lld arrived %7lld | group1 got_stage %7lld arrived %7lld | mma got K block %d %7lld, %d %7lld\n",
+                k, h[k] - t0, h[512 + k] - t0, h[1024 + k] - t0, h[1536 + k] - t0, 2 * k, h[2048 + 2 * k] - t0, 2 * k + 1,
+                h[2048 + 2 * k + 1] - t0);
+      for (int t = 0; t < 6 && h[2560 + t]; ++t)
+        fprintf(stderr, "tile %d table_done %7lld | epilogue start %7lld done %7lld\n", t, h[2560 + t] - t0, h[3072 + t] - t0,
+                h[3584 + t] - t0);
     }
   }
   return CNB_OK;

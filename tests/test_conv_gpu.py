@@ -150,6 +150,10 @@ def test_conv_nchw_f32_head_output(cuda_dev):
                                                  (1, 256, 256, 8, 8, False),
                                                  (1, 128, 128, 20, 24, False),   # BN=128: two taps per stage, 18 K blocks
                                                  (2, 64, 24, 12, 40, False),     # Co not a multiple of 16
+                                                 (2, 64, 64, 24, 32, False),     # 8 x 16 pixel tiles (W % 16 == 0)
+                                                 (1, 128, 64, 20, 16, False),    # ... last tile row cut by the image
+                                                 (1, 128, 128, 16, 48, False),   # two slabs, BN = 128
+                                                 (1, 64, 64, 16, 32, True),      # ... on a channel slice
                                                  (1, 64, 64, 16, 24, True)])     # 16-byte-aligned channel slice of a
                                                                                  # wider tensor: 128-bit corner loads
 def test_dcnv2_matches_torchvision(cuda_dev, B, Ci, Co, H, W, sliced):

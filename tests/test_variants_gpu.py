@@ -18,8 +18,12 @@ VARIANTS = [
     ({"CNB_CONV_IMPL": "v1"}, "test_conv_matches_torch or test_stem_space_to_depth"),
     ({"CNB_CONV_ROWS": "0"}, "test_conv_matches_torch"),
     ({"CNB_DCN_BLEND": "bf16"}, "dcn"),
-    ({"CNB_DCN_KPER": "1"}, "dcn"),
+    ({"CNB_DCN_GROUPS": "1"}, "dcn"),
+    ({"CNB_DCN_GROUPS": "4"}, "dcn"),
     ({"CNB_DCN_IMPL": "v1"}, "dcn"),
+    ({"CNB_DCN_IMPL": "ws"}, "dcn"),
+    ({"CNB_DCN_REACH": "1"}, "dcn"),
+    ({"CNB_DCN_REACH": "1", "CNB_DCN_STAGES": "2", "CNB_DCN_GROUPS": "1"}, "dcn"),
     ({"CNB_PDL": "0"}, "test_conv_matches_torch or dcn"),
 ]
 
