@@ -20,7 +20,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr", "--expt-extended-lambda",
     "-Xptxas", "-v",
-]
+] + os.environ.get("CNB_NVCC_EXTRA", "").split()   # e.g. -DCNB_DCN_EXPERIMENTS for the timing switches
 
 
 def sources():

@@ -18,10 +18,20 @@
 // (offsets beyond R) is flagged in the table and sampled from global memory through the same generic-address loads,
 // so the result does not depend on R.
 //
-// GEMM view and roles are those of dcn_ws.cu: D[128 pixels, Co] = A[128, 9*Ci] * W^T, A sampled on the fly into a ring of
-// K-major SWIZZLE_128B stages (one K block = one tap of one 64-channel slab per stage); the sampler warps form groups
-// that take the K blocks round-robin; setup warps turn offsets/masks into a table of bilinear weights + box (or global)
-// pixel index; one MMA warp (tcgen05.mma, elected lane); 4 epilogue warps; one loader warp (footprint boxes).
+// Shared-memory bandwidth is then what bounds the sampler (ncu, first version of this kernel: ~1180 bank wavefronts per K
+// block -- 560 corner/table loads, 160 operand stores, 190 operand reads by the tensor core, 120 TMA writes -- at 0.7 per
+// clock), so the sampled operand does not go through shared memory at all: a sampler thread owns one pixel ROW of the
+// tile, blends its 64 channels chunk by chunk and writes them with tcgen05.st into a ring of A stages in TENSOR MEMORY
+// (32 columns per K block, up to 12 stages next to the two accumulators); tcgen05.mma reads A from there.  One thread
+// per row also means one table entry and one set of corner addresses per 128 output bytes instead of per 32.  The box
+// is stored with the 128-byte swizzle (16-byte chunk index XOR pixel index mod 8), so the 8 lanes of a shared-memory
+// wavefront -- 8 neighbouring pixels reading the same logical chunk of 8 different box pixels -- hit 8 different bank
+// groups whenever the sampled pixels are distinct mod 8 (always for smooth offsets).
+//
+// GEMM view: D[128 pixels, Co] = A[128, 9*Ci] * W^T, one K block = one tap of one 64-channel slab.  Roles: 16 sampler
+// warps in 4 groups (one warp per TMEM lane quarter) that take the K blocks of the CTA's stream round-robin; 4 setup warps
+// (offsets/masks -> table of bilinear weights + box or global pixel index); one MMA warp (tcgen05.mma with the A operand
+// in tensor memory, weight tile by TMA into a shared-memory ring, elected lane); 4 epilogue warps; one loader warp (boxes).
 #include "umma.cuh"
 #include "tma_host.h"
 #include <stdlib.h>
@@ -31,23 +41,21 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int NPROD_WARPS = 16;
-constexpr int NPROD = NPROD_WARPS * 32;
+
 constexpr int NSETUP_WARPS = 4;
 constexpr int NSETUP = NSETUP_WARPS * 32;
 constexpr int W_SETUP0 = NPROD_WARPS;                // warps 16..19
 constexpr int W_MMA = W_SETUP0 + NSETUP_WARPS;       // warp 20
 constexpr int W_EPI0 = W_MMA + 1;                    // warps 21..24 (TMEM lane quarters 1,2,3,0)
 constexpr int W_LOAD = W_EPI0 + 4;                   // warp 25: footprint boxes
-constexpr int NWARPS = 28;                           // warps 26, 27 idle: whole warpgroups for setmaxnreg
-constexpr int NTHREADS = NWARPS * 32;                // 896 threads x 72 registers at launch
-constexpr int NG = 2;                                // sampler groups: K block k of the CTA's stream belongs to group k % NG
-constexpr int WPG = NPROD_WARPS / NG;                // warps per group
-constexpr int ROW_STRIDE = BM / NG;                  // a thread owns the rows r0 and r0 + 64
-constexpr int REGS_SAMPLER = 96, REGS_OTHER = 40;    // 16 x 96 + 12 x 40 = 28 x 72
-constexpr int MAX_STAGES = 6;
+constexpr int NTHREADS = (W_LOAD + 1) * 32;          // 832
+constexpr int NG = 4;                                // sampler groups: K block k of the CTA's stream belongs to group k % NG
+constexpr int WPG = NPROD_WARPS / NG;                // 4 warps per group = the 4 TMEM lane quarters
+constexpr int MAX_STAGES = 12;
+constexpr int MAX_B = 18;
+constexpr int A_COLS = 32;                           // TMEM columns of one K block of A: 64 bf16 per row
 constexpr int NTAB = BM * 9;                         // (pixel, tap) entries per tile
 constexpr int OM_CS = 32;                            // channel stride of the offset/mask map this kernel takes
-constexpr u32 A_BYTES = BM * 64 * 2;                 // one K block of the sampled operand: 128 rows x 128 B
 
 struct FArgs {
   cnb_conv_desc d;
@@ -66,9 +74,12 @@ struct FArgs {
   u32 fp_stride;   // fp_bytes rounded up to 1 KB
   int BN;          // = Co rounded up to 16, <= 128
   int nkb;         // 9 * Ci/64
-  u32 bstage;      // bytes of the K block's weight tile inside its stage (b_bytes rounded up to 1 KB)
-  int stages;
-  u32 b_bytes, stage_bytes, tmem_cols, acc_stride, idesc;
+  u32 bstage;      // bytes of one weight-tile slot (b_bytes rounded up to 1 KB)
+  int stages;      // A ring depth: stage i = tensor-memory columns a_col0 + 32 i
+  int nb;          // weight-tile slots in shared memory; K block j of the CTA's stream uses slot j % nb
+  int b_resident;  // nb >= nkb: the 9 * Ci/64 weight tiles are loaded once and stay
+  u32 b_bytes, tmem_cols, acc_stride, a_col0, idesc;
+  int debug;       // timing experiments (-DCNB_DCN_EXPERIMENTS): 1 no corner loads, 2 no blend, 4 no tcgen05.st, 8 no table read
 };
 
 // packed fp32x2 helpers (Blackwell FFMA2): a 64-bit register holds (low, high) floats
@@ -108,6 +119,21 @@ __device__ __forceinline__ uint4 ldgen128(u64 addr) {   // generic address: shar
   uint4 v;
   asm volatile("ld.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(addr));
   return v;
+}
+
+__device__ __forceinline__ void tmem_st4(u32 taddr, const uint4 v) {   // 32 lanes x 4 columns: lane = tile row
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (128 rows x 16 bf16 = 8 packed columns) is read from tensor memory
+__device__ __forceinline__ void umma_bf16_ts(u32 tmem_d, u32 tmem_a, u64 desc_b, u32 idesc, u32 accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 
 // 4-corner blend of one 16-byte chunk (8 channels): fp32 (packed FFMA2), one rounding to bf16
@@ -159,12 +185,21 @@ __device__ __forceinline__ TileXY tile_xy(const FArgs& a, int tile) {
   return t;
 }
 
+#ifdef CNB_DCN_EXPERIMENTS
+#define FP_DBG(a) ((a).debug)
+#else
+#define FP_DBG(a) 0
+#endif
+
 template <bool BLEND_BF16>
 __global__ void __launch_bounds__(NTHREADS, 1)
-dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmX, const FArgs a) {
+dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmX,
+              const __grid_constant__ CUtensorMap tmO, const FArgs a) {
   extern __shared__ unsigned char smem_dyn[];
   __shared__ __align__(8) u64 s_full[MAX_STAGES];
   __shared__ __align__(8) u64 s_empty[MAX_STAGES];
+  __shared__ __align__(8) u64 s_bfull[MAX_B];
+  __shared__ __align__(8) u64 s_bempty[MAX_B];
   __shared__ __align__(8) u64 s_tfull[2];
   __shared__ __align__(8) u64 s_tempty[2];
   __shared__ __align__(8) u64 s_tabfull[2];
@@ -178,8 +213,8 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const u32 smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* smem_al = smem_dyn + (smem_base - smem_u32(smem_dyn));
-  const u32 fp_s = smem_base + (u32)a.stages * a.stage_bytes;                        // two footprint boxes
-  unsigned char* after_fp = smem_al + (size_t)a.stages * a.stage_bytes + 2 * (size_t)a.fp_stride;
+  const u32 fp_s = smem_base + (u32)a.nb * a.bstage;                                 // two footprint boxes
+  unsigned char* after_fp = smem_al + (size_t)a.nb * a.bstage + 2 * (size_t)a.fp_stride;
   float4* s_tabw = reinterpret_cast<float4*>(after_fp);                              // [2][NTAB]
   u32* s_tabb = reinterpret_cast<u32*>(s_tabw + 2 * NTAB);                           // [2][NTAB]
   float* s_om = reinterpret_cast<float*>(s_tabb + 2 * NTAB);                         // [BM][OM_CS]
@@ -188,8 +223,12 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
 
   if (tid == 0) {
     for (int s = 0; s < a.stages; ++s) {
-      mbar_init(&s_full[s], WPG + 1);   // the stage's sampler group + the weight tile's expect_tx
+      mbar_init(&s_full[s], WPG);       // the four warps of the stage's sampler group
       mbar_init(&s_empty[s], 1);
+    }
+    for (int s = 0; s < a.nb; ++s) {
+      mbar_init(&s_bfull[s], 1);
+      mbar_init(&s_bempty[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_tfull[i], 1);
@@ -203,8 +242,11 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
     fence_mbar_init();
     fence_proxy_async_smem();
   }
-  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmB);
-  if (warp == W_LOAD && lane == 0) tma_prefetch_desc(&tmX);
+  if (warp == W_LOAD && lane == 0) {
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmO);
+  }
   if (warp == W_MMA) tmem_alloc(&s_tmem, a.tmem_cols);
   pdl_launch_dependents();
   pdl_wait();   // global memory (x, offsets, scale/shift) is read only after the previous kernel has completed
@@ -222,106 +264,90 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
   const int tile_begin = (int)((long long)blockIdx.x * a.m_tiles / gridDim.x);
   const int tile_end = (int)((long long)(blockIdx.x + 1) * a.m_tiles / gridDim.x);
 
-  // Register file: the samplers keep two (pixel, tap) items in flight per thread (64 data registers); every other role
-  // needs few.  Whole warpgroups trade registers: 12 warps shrink to 40, the 16 sampler warps grow to 96.
-  if (warp < NPROD_WARPS) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_SAMPLER));
-  } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_OTHER));
-  }
-
   if (warp < NPROD_WARPS) {
     // =============================== samplers ===============================================================
-    // Group g takes the K blocks k = g, g + 2, ... of the CTA's stream (tile-major, slab-major, tap-minor); inside a
-    // group a thread owns the tile rows r0 and r0 + 64 and a PAIR of 16-byte channel chunks.  The four threads of a
-    // row cover the 128 bytes of each corner pixel; odd rows read their two chunks in the opposite order, so the 8
-    // lanes of one shared-memory wavefront (two rows) touch 8 different 16-byte bank groups whatever pixels they
-    // sample.  Software pipeline: the table entry and the 8 corner loads of the NEXT (row, tap) item are issued before
-    // the current item is blended (two register buffers, statically named A / B), so the shared-memory latency hides
-    // behind ~110 blend instructions of the same warp instead of needing other warps to be ready.
-    const int grp = warp / WPG;
-    const int ltid = tid - grp * WPG * 32;
-    const int cp = ltid & 3;
-    const int row0 = ltid >> 2;                        // rows row0, row0 + 64: same parity
-    const u32 odd = (u32)(row0 & 1);
-    const u32 c_first = (u32)(2 * cp) + odd, c_second = (u32)(2 * cp + 1) - odd;
+    // Group g = warp / 4 takes the K blocks k = g, g + 4, ... of the CTA's stream (tile-major, slab-major, tap-minor);
+    // warp q = warp % 4 of the group owns TMEM lanes 32q..32q+31, i.e. a thread owns tile row 32q + lane: one table
+    // entry, four corner addresses, then 8 chunks of (4 shared-memory loads, fp32 blend, tcgen05.st of 4 columns).  The
+    // loads of chunk c+1 are issued before chunk c is blended.
+    const int grp = warp >> 2;
+    const int row = ((warp & 3) << 5) + lane;
     const u32 cs2 = (u32)d.x_cstride * 2u;             // bytes per pixel of the global tensor
     const u32 rowb = (u32)d.Wi * cs2;
-    const u32 boxrow = (u32)a.FW * 128u;
     const u64 xg = reinterpret_cast<u64>(a.x + d.x_coffset);
-    const bool issuer = (warp == grp * WPG);
-    // swizzled destinations of this thread's two chunks inside a stage, for its two rows ((row + 64) & 7 == row & 7)
-    const u32 dst_lo0 = (u32)row0 * 128u + ((u32)((2 * cp) ^ (row0 & 7)) << 4);
-    const u32 dst_hi0 = (u32)row0 * 128u + ((u32)((2 * cp + 1) ^ (row0 & 7)) << 4);
-
-    struct Item {
-      float4 w;
-      uint4 q[8];      // corners 0..3 of chunk c_first, then of chunk c_second
-      u32 b;
-      bool pre;        // corners already loaded (every lane of the warp samples inside the staged box)
-    };
-    // table entry + (if the whole warp is inside the box) the 8 shared-memory loads of one item
-    auto fetch = [&](Item& it, int row, int tap, u32 tb, u32 fpb) {
-      it.w = s_tabw[tb * NTAB + row * 9 + tap];
-      it.b = s_tabb[tb * NTAB + row * 9 + tap];
-      it.pre = __all_sync(0xffffffffu, (int)(it.b >> 31) == 0) != 0;
-      if (it.pre) {
-        const u32 a0 = fpb + (it.b & 0x1FFFFFFFu) * 128u;
-        const u32 adr[4] = {a0, a0 + 128u, a0 + boxrow, a0 + boxrow + 128u};
-#pragma unroll
-        for (int c = 0; c < 4; ++c) it.q[c] = lds128(adr[c] + (c_first << 4));
-#pragma unroll
-        for (int c = 0; c < 4; ++c) it.q[4 + c] = lds128(adr[c] + (c_second << 4));
-      }
-    };
-    // blend + store into the stage; items with a corner outside the box load here, each lane from its own window
-    auto finish = [&](Item& it, u32 sa_row, u32 fpb, u64 xgs) {
-      if (!it.pre) {
-        const bool g = (it.b >> 31) != 0;
-        const u32 pix = it.b & 0x1FFFFFFFu;
-        const u64 base = g ? xgs + (u64)pix * cs2 : (u64)__cvta_shared_to_generic(fpb) + (u64)pix * 128u;
-        const u32 d1 = g ? (((it.b >> 29) & 1u) ? cs2 : 0u) : 128u;
-        const u32 d2 = g ? (((it.b >> 30) & 1u) ? rowb : 0u) : boxrow;
-        const u64 adr[4] = {base, base + d1, base + d2, base + d2 + d1};
-#pragma unroll
-        for (int c = 0; c < 4; ++c) it.q[c] = ldgen128(adr[c] + (c_first << 4));
-#pragma unroll
-        for (int c = 0; c < 4; ++c) it.q[4 + c] = ldgen128(adr[c] + (c_second << 4));
-      }
-      const uint4 oa = blend4<BLEND_BF16>(it.w, it.q[0], it.q[1], it.q[2], it.q[3]);
-      const uint4 ob = blend4<BLEND_BF16>(it.w, it.q[4], it.q[5], it.q[6], it.q[7]);
-      // even chunk first (the two rows of a wavefront then differ in bit 0 of the swizzled chunk index: conflict-free)
-      const uint4 lo = odd ? ob : oa, hi = odd ? oa : ob;
-      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sa_row + dst_lo0), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w) : "memory");
-      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sa_row + dst_hi0), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
-    };
-
+    const u32 ta_row = tmem_base + ((u32)((warp & 3) << 5) << 16) + a.a_col0;   // this warp's lanes, first A stage
     u32 s = (u32)grp % (u32)a.stages, ph = ((u32)grp / (u32)a.stages) & 1u, t = 0, u = 0;
     int tap = grp;
-    Item A, B;
     for (int tile = tile_begin; tile < tile_end; ++tile, ++t) {
       const u32 tb = t & 1u;
       mbar_wait_parked(&s_tabfull[tb], (t >> 1) & 1u);
+      const float4* tw = s_tabw + tb * NTAB + row * 9;
+      const u32* tbs = s_tabb + tb * NTAB + row * 9;
       for (int slab = 0; slab < nslabs; ++slab, ++u) {
-        // this group's taps of the (tile, slab) box: tap, tap + 2, ... < 9
+        // this group's taps of the (tile, slab) box: tap, tap + 4, ... < 9
         const u32 fb = u & 1u;
         const u32 fpb = fp_s + fb * a.fp_stride;
-        const u64 xgs = xg + (u64)(slab * 128);
         mbar_wait_parked(&s_fpfull[fb], (u >> 1) & 1u);
-        fetch(A, row0, tap, tb, fpb);
-        while (tap < 9) {
-          mbar_wait_parked(&s_empty[s], ph ^ 1u);
-          const u32 sa = smem_base + s * a.stage_bytes;
-          if (issuer && elect_one()) {
-            mbar_expect_tx(&s_full[s], a.b_bytes);
-            tma_load_2d(sa + A_BYTES, &tmB, tap * d.Ci + slab * 64, 0, &s_full[s]);
+        float4 w_next = tw[tap];          // the table entry of the next K block is read one K block ahead
+        u32 b_next = tbs[tap];
+        for (; tap < 9; tap += NG) {
+          const float4 w = (FP_DBG(a) & 8) ? make_float4(0.25f, 0.25f, 0.25f, 0.25f) : w_next;
+          const u32 b = (FP_DBG(a) & 8) ? (u32)(row + tap) : b_next;
+          if (tap + NG < 9) {
+            w_next = tw[tap + NG];
+            b_next = tbs[tap + NG];
           }
-          fetch(B, row0 + ROW_STRIDE, tap, tb, fpb);
-          finish(A, sa, fpb, xgs);
-          const int tap_next = tap + NG;
-          if (tap_next < 9) fetch(A, row0, tap_next, tb, fpb);
-          finish(B, sa + (u32)ROW_STRIDE * 128u, fpb, xgs);
-          fence_proxy_async_smem();       // generic-proxy stores -> visible to the tensor core (async proxy)
+          if (FP_DBG(a) & 128) mbar_wait_spin(&s_empty[s], ph ^ 1u); else mbar_wait_parked(&s_empty[s], ph ^ 1u);
+          tc_fence_after();
+          const u32 pix = b & 0x1FFFFFFFu;
+          const u32 ta = ta_row + s * A_COLS;
+          if (__all_sync(0xffffffffu, (int)(b >> 31) == 0)) {
+            // every lane's corners are inside the staged box.  Corner k is box pixel pk; its logical chunk c sits at
+            // 16-byte slot c ^ (pk & 7) of the pixel's 128 bytes: e_k = pixel address | swizzle, load address = e_k ^ 16c
+            const u32 p1 = pix + 1u, p2 = pix + (u32)a.FW, p3 = p2 + 1u;
+            const u32 e0 = (fpb + pix * 128u) | ((pix & 7u) << 4), e1 = (fpb + p1 * 128u) | ((p1 & 7u) << 4),
+                      e2 = (fpb + p2 * 128u) | ((p2 & 7u) << 4), e3 = (fpb + p3 * 128u) | ((p3 & 7u) << 4);
+            uint4 q0[4], q1[4];
+            const int dbg = FP_DBG(a);
+            auto ld = [&](u32 adr) { return (dbg & 1) ? make_uint4(adr, adr + 1, adr + 2, adr + 3) : lds128(adr); };
+            auto bl = [&](const uint4 (&q)[4]) {
+              return (dbg & 2) ? make_uint4(q[0].x ^ q[1].y, q[2].z ^ q[3].w, q[0].w, q[1].x) : blend4<BLEND_BF16>(w, q[0], q[1], q[2], q[3]);
+            };
+            auto st = [&](u32 adr, const uint4 v) {
+              if (!(dbg & 4)) tmem_st4(adr, v);
+              else if (v.x == 0x12345678u && v.w == 0x9abcdef0u) tmem_st4(adr, v);
+            };
+            q0[0] = ld(e0); q0[1] = ld(e1); q0[2] = ld(e2); q0[3] = ld(e3);
+#pragma unroll
+            for (int c = 0; c < 8; c += 2) {
+              const u32 x1 = (u32)(c + 1) << 4;
+              q1[0] = ld(e0 ^ x1); q1[1] = ld(e1 ^ x1); q1[2] = ld(e2 ^ x1); q1[3] = ld(e3 ^ x1);
+              st(ta + (u32)(4 * c), bl(q0));
+              if (c + 2 < 8) {
+                const u32 x2 = (u32)(c + 2) << 4;
+                q0[0] = ld(e0 ^ x2); q0[1] = ld(e1 ^ x2); q0[2] = ld(e2 ^ x2); q0[3] = ld(e3 ^ x2);
+              }
+              st(ta + (u32)(4 * c + 4), bl(q1));
+            }
+          } else {
+            // some (pixel, tap) of this warp reaches beyond the box: generic loads, each lane from its own window
+            const bool g = (b >> 31) != 0;
+            const u64 base = g ? xg + (u64)(slab * 128) + (u64)pix * cs2 : (u64)__cvta_shared_to_generic(fpb) + (u64)pix * 128u;
+            const u32 d1 = g ? (((b >> 29) & 1u) ? cs2 : 0u) : 128u;
+            const u32 d2 = g ? (((b >> 30) & 1u) ? rowb : 0u) : (u32)a.FW * 128u;
+            const u64 adr[4] = {base, base + d1, base + d2, base + d2 + d1};
+            const u32 p1 = pix + 1u, p2 = pix + (u32)a.FW, p3 = p2 + 1u;
+            const u32 sw[4] = {g ? 0u : (pix & 7u) << 4, g ? 0u : (p1 & 7u) << 4, g ? 0u : (p2 & 7u) << 4, g ? 0u : (p3 & 7u) << 4};
+#pragma unroll 1
+            for (int c = 0; c < 8; ++c) {
+              uint4 q[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) q[k] = ldgen128(adr[k] + (((u32)c << 4) ^ sw[k]));
+              tmem_st4(ta + (u32)(4 * c), blend4<BLEND_BF16>(w, q[0], q[1], q[2], q[3]));
+            }
+          }
+          tmem_st_wait();                 // the row's 32 columns are in tensor memory
+          tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&s_full[s]);
           s += (u32)NG;                   // next K block of this group: NG further in the stream and in the ring
@@ -329,7 +355,6 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
             s -= (u32)a.stages;
             ph ^= 1u;
           }
-          tap = tap_next;
         }
         tap -= 9;
         __syncwarp();
@@ -339,78 +364,103 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
     }
   } else if (warp < W_MMA) {
     // =============================== setup: (pixel, tap) -> weights + corner index ============================
-    // The tile's offset/mask values (TH runs of TW pixels x 32 floats) are staged by 1-D bulk copies; the single
-    // buffer is refilled for tile t+1 as soon as the table of tile t is written, long before it is needed.
-    const int stid = tid - W_SETUP0 * 32;
-    const int TH = BM >> a.tw_shift;
-    auto issue_om = [&](int tile) {
-      const TileXY tc = tile_xy(a, tile);
-      const int rows = min(TH, d.Hi - tc.y0);
-      const u32 run = (u32)TW * OM_CS * 4u;
-      mbar_expect_tx(&s_omfull, (u32)rows * run);
-      for (int r = 0; r < rows; ++r)
-        bulk_g2s(s_om + r * TW * OM_CS, a.om + ((size_t)(tc.n * d.Hi + tc.y0 + r) * d.Wi + tc.x0) * OM_CS, run, &s_omfull);
-    };
-    if (stid == 0 && tile_begin < tile_end) issue_om(tile_begin);
+    // A setup thread owns one tile row: it pulls the row's 27 offset/mask values into registers (7 x 16 bytes; the box of
+    // offsets arrives by ONE tensor-map copy with the 128-byte swizzle, so the 8 lanes of a wavefront read 8 different
+    // bank groups), hands the staging buffer back at once -- the copy for tile t+1 flies while the table of tile t is
+    // computed -- and then works out its 9 taps as 9 independent instruction streams.  (First version: one (pixel, tap)
+    // item per thread and step, the buffer refilled after the table was written: a serial chain of load latency +
+    // lone-warp arithmetic of ~10000 clocks per tile, which bounded the whole kernel.)
+    const int r = tid - W_SETUP0 * 32;                 // tile row 0..127
+    if (r == 0 && tile_begin < tile_end) {
+      const TileXY tc = tile_xy(a, tile_begin);
+      mbar_expect_tx(&s_omfull, BM * OM_CS * 4u);
+      tma_load_tile_4d(smem_u32(s_om), &tmO, 0, tc.x0, tc.y0, tc.n, &s_omfull);
+    }
+    const u32 om_row = smem_u32(s_om) + (u32)r * 128u;
+    const u32 om_sw = (u32)(r & 7) << 4;
     u32 t = 0;
     for (int tile = tile_begin; tile < tile_end; ++tile, ++t) {
       const u32 tb = t & 1u;
-      mbar_wait_parked(&s_tabempty[tb], ((t >> 1) & 1u) ^ 1u);
       mbar_wait_parked(&s_omfull, t & 1u);
+      float om[28];
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        const uint4 v = lds128(om_row + (((u32)j << 4) ^ om_sw));
+        om[4 * j] = __uint_as_float(v.x); om[4 * j + 1] = __uint_as_float(v.y);
+        om[4 * j + 2] = __uint_as_float(v.z); om[4 * j + 3] = __uint_as_float(v.w);
+      }
+      // all 128 rows are in registers: refill the staging buffer for the next tile
+      asm volatile("bar.sync 1, %0;" ::"n"(NSETUP) : "memory");
+      if (r == 0 && tile + 1 < tile_end) {
+        const TileXY tn = tile_xy(a, tile + 1);
+        mbar_expect_tx(&s_omfull, BM * OM_CS * 4u);
+        tma_load_tile_4d(smem_u32(s_om), &tmO, 0, tn.x0, tn.y0, tn.n, &s_omfull);
+      }
       const TileXY tc = tile_xy(a, tile);
       const int bx0 = tc.x0 - 1 - a.R, by0 = tc.y0 - 1 - a.R;   // box origin (may be negative: zero-filled)
-#pragma unroll 3
-      for (int item = stid; item < NTAB; item += NSETUP) {
-        const int r = item / 9, tap = item - r * 9;
-        const int oy = tc.y0 + (r >> a.tw_shift), ox = tc.x0 + (r & (TW - 1));
-        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-        u32 b = 0;
-        if (oy < d.Hi) {
+      const int oy = tc.y0 + (r >> a.tw_shift), ox = tc.x0 + (r & (TW - 1));
+      const u32 gbase = (u32)(tc.n * d.Hi) * (u32)d.Wi;
+      mbar_wait_parked(&s_tabempty[tb], ((t >> 1) & 1u) ^ 1u);
+      float4* ow = s_tabw + tb * NTAB + r * 9;
+      u32* ob = s_tabb + tb * NTAB + r * 9;
+      const float fH = (float)d.Hi, fW = (float)d.Wi;
+      const float fy = (float)(oy - 1), fx = (float)(ox - 1);
+      const int boff = -by0 * a.FW - bx0;                // box pixel index = y0 * FW + x0 + boff
+      u32 far = 0;                                       // taps of this row that leave the box (rare)
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int kh = tap / 3, kw = tap - 3 * kh;
+        const float mk = __fdividef(1.f, 1.f + __expf(-om[18 + tap]));
+        const float py = fy + (float)kh + om[2 * tap];
+        const float px = fx + (float)kw + om[2 * tap + 1];
+        const float fy0 = floorf(py), fx0 = floorf(px);
+        const float ly = py - fy0, lx = px - fx0;
+        const float hy = 1.f - ly, hx = 1.f - lx;
+        const int y0 = (int)fy0, x0 = (int)fx0;
+        const bool valid = (oy < d.Hi) && py > -1.f && px > -1.f && py < fH && px < fW;
+        // inside the box all four corners are read as they are: corners outside the image hit the zero fill
+        const bool inbox = y0 >= by0 && x0 >= bx0 && y0 + 1 < by0 + a.FH && x0 + 1 < bx0 + a.FW;
+        const float m = valid ? mk : 0.f;
+        const float wy0 = hy * m, wy1 = ly * m;
+        ow[tap] = make_float4(wy0 * hx, wy0 * lx, wy1 * hx, wy1 * lx);
+        ob[tap] = (valid && inbox) ? (u32)(y0 * a.FW + x0 + boff) : 0u;
+        far |= (valid && !inbox) ? (1u << tap) : 0u;
+      }
+      if (FP_DBG(a) & 16) far = 0;
+      if (__any_sync(0xffffffffu, far != 0)) {
+        // samples beyond the box: clamped global pixel + validity-masked weights, flagged for the generic-load path
+        for (int tap = 0; tap < 9; ++tap) {
+          if (!((far >> tap) & 1u)) continue;
           const int kh = tap / 3, kw = tap - 3 * kh;
-          const float* omp = s_om + r * OM_CS;
-          const float dy = omp[2 * tap];
-          const float dx = omp[2 * tap + 1];
-          const float mk = 1.f / (1.f + __expf(-omp[18 + tap]));
-          const float py = (float)(oy - 1 + kh) + dy;
-          const float px = (float)(ox - 1 + kw) + dx;
-          if (py > -1.f && px > -1.f && py < (float)d.Hi && px < (float)d.Wi) {
-            const int y0 = (int)floorf(py), x0 = (int)floorf(px);
-            const float ly = py - (float)y0, lx = px - (float)x0;
-            const float hy = 1.f - ly, hx = 1.f - lx;
-            const int by = y0 - by0, bx = x0 - bx0;
-            if (by >= 0 && bx >= 0 && by + 1 < a.FH && bx + 1 < a.FW) {
-              // all four corners inside the box; corners outside the image read the zero fill
-              w = make_float4(hy * hx * mk, hy * lx * mk, ly * hx * mk, ly * lx * mk);
-              b = (u32)(by * a.FW + bx);
-            } else {
-              const bool vy0 = y0 >= 0, vy1 = y0 + 1 <= d.Hi - 1, vx0 = x0 >= 0, vx1 = x0 + 1 <= d.Wi - 1;
-              w.x = (vy0 && vx0) ? hy * hx * mk : 0.f;
-              w.y = (vy0 && vx1) ? hy * lx * mk : 0.f;
-              w.z = (vy1 && vx0) ? ly * hx * mk : 0.f;
-              w.w = (vy1 && vx1) ? ly * lx * mk : 0.f;
-              const int y0c = max(y0, 0), y1c = min(y0 + 1, d.Hi - 1);
-              const int x0c = max(x0, 0), x1c = min(x0 + 1, d.Wi - 1);
-              b = 0x80000000u | ((u32)(y1c - y0c) << 30) | ((u32)(x1c - x0c) << 29) |
-                  (u32)((tc.n * d.Hi + y0c) * d.Wi + x0c);
-            }
-          }
+          float dyv = 0.f, dxv = 0.f, mv = 0.f;
+#pragma unroll
+          for (int k = 0; k < 9; ++k)
+            if (k == tap) { dyv = om[2 * k]; dxv = om[2 * k + 1]; mv = om[18 + k]; }
+          const float mk = __fdividef(1.f, 1.f + __expf(-mv));
+          const float py = fy + (float)kh + dyv, px = fx + (float)kw + dxv;
+          const int y0 = (int)floorf(py), x0 = (int)floorf(px);
+          const float ly = py - (float)y0, lx = px - (float)x0;
+          const float hy = 1.f - ly, hx = 1.f - lx;
+          const bool vy0 = y0 >= 0, vy1 = y0 + 1 <= d.Hi - 1, vx0 = x0 >= 0, vx1 = x0 + 1 <= d.Wi - 1;
+          float4 w;
+          w.x = (vy0 && vx0) ? hy * hx * mk : 0.f;
+          w.y = (vy0 && vx1) ? hy * lx * mk : 0.f;
+          w.z = (vy1 && vx0) ? ly * hx * mk : 0.f;
+          w.w = (vy1 && vx1) ? ly * lx * mk : 0.f;
+          const int y0c = max(y0, 0), y1c = min(y0 + 1, d.Hi - 1);
+          const int x0c = max(x0, 0), x1c = min(x0 + 1, d.Wi - 1);
+          ow[tap] = w;
+          ob[tap] = 0x80000000u | ((u32)(y1c - y0c) << 30) | ((u32)(x1c - x0c) << 29) | (gbase + (u32)(y0c * d.Wi + x0c));
         }
-        s_tabw[tb * NTAB + item] = w;
-        s_tabb[tb * NTAB + item] = b;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_tabfull[tb]);
-      // all setup warps are done with the om buffer: refill it for the next tile
-      asm volatile("bar.sync 1, %0;" ::"n"(NSETUP) : "memory");
-      if (stid == 0 && tile + 1 < tile_end) issue_om(tile + 1);
     }
   } else if (warp == W_MMA) {
     // =============================== MMA issuer ==============================================================
-    u32 s = 0, ph = 0, t = 0;
-    const u64 da0 = make_sdesc(smem_base, 16, 1024, 2);
-    const u64 db0 = make_sdesc(smem_base + A_BYTES, 16, 1024, 2);
-    const u32 stage16 = a.stage_bytes >> 4;
-    u32 soff16 = 0;
+    u32 s = 0, ph = 0, t = 0, sb = 0, phb = 0;
+    const u64 db0 = make_sdesc(smem_base, 16, 1024, 2);
+    const u32 bstage16 = a.bstage >> 4;
     for (int tile = tile_begin; tile < tile_end; ++tile, ++t) {
       const u32 acc = t & 1u, acc_ph = (t >> 1) & 1u;
       mbar_wait_parked(&s_tempty[acc], acc_ph ^ 1u);
@@ -418,22 +468,27 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
       const u32 tmem_d = tmem_base + acc * a.acc_stride;
       u32 accumulate = 0;
       for (int kb = 0; kb < a.nkb; ++kb) {
-        mbar_wait_parked(&s_full[s], ph);
+        if (!a.b_resident || t == 0) mbar_wait_parked(&s_bfull[sb], phb);   // the weight tile (prefetched far ahead)
+        mbar_wait_parked(&s_full[s], ph);                                   // the sampled rows
         tc_fence_after();
         if (elect_one()) {
-          const u64 da = da0 + (u64)soff16, db = db0 + (u64)soff16;
+          const u64 db = db0 + (u64)(sb * bstage16);
+          const u32 ta = tmem_base + a.a_col0 + s * A_COLS;
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)   // +32 bytes of K inside the swizzle atom
-            umma_bf16(tmem_d, da + (u64)(2 * kk), db + (u64)(2 * kk), a.idesc, kk == 0 ? accumulate : 1u);
+          for (int kk = 0; kk < 4; ++kk)   // K = 16: 8 packed columns of A, +32 bytes of B inside the swizzle atom
+            if (!(FP_DBG(a) & 32)) umma_bf16_ts(tmem_d, ta + (u32)(8 * kk), db + (u64)(2 * kk), a.idesc, kk == 0 ? accumulate : 1u);
           umma_commit(&s_empty[s]);
+          if (!a.b_resident) umma_commit(&s_bempty[sb]);
         }
         __syncwarp();
         accumulate = 1;
-        soff16 += stage16;
         if (++s == (u32)a.stages) {
           s = 0;
           ph ^= 1u;
-          soff16 = 0;
+        }
+        if (++sb == (u32)a.nb || (a.b_resident && sb == (u32)a.nkb)) {
+          sb = 0;
+          phb ^= 1u;
         }
       }
       if (elect_one()) umma_commit(&s_tfull[acc]);
@@ -466,18 +521,54 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
     }
   } else if (warp == W_LOAD) {
     // =============================== loader: one box per (tile, slab), two in flight ===========================
-    u32 u = 0;
-    for (int tile = tile_begin; tile < tile_end; ++tile) {
-      const TileXY tc = tile_xy(a, tile);
-      for (int slab = 0; slab < nslabs; ++slab, ++u) {
-        const u32 fb = u & 1u;
-        mbar_wait_parked(&s_fpempty[fb], ((u >> 1) & 1u) ^ 1u);
+    // Boxes and weight tiles share the SM's TMA queue; each is requested as early as its slot allows (a weight tile
+    // requested only when its K block is sampled arrives ~1500 clocks later, behind 40 KB boxes: measured as a
+    // ~850-clock floor per K block).  Non-blocking polls, whichever slot is free goes next.
+    const int ntiles = tile_end - tile_begin;
+    const long long u_total = (long long)ntiles * nslabs;
+    const long long j_total = a.b_resident ? (ntiles > 0 ? a.nkb : 0) : (long long)ntiles * a.nkb;
+    long long u = 0, j = 0;
+    int utile = tile_begin, uslab = 0, jtap = 0, jslab = 0;
+    u32 jslot = 0, juse = 0;
+    while (u < u_total || j < j_total) {
+      bool progressed = false;
+      if (j < j_total && (juse == 0 || mbar_test_wait(&s_bempty[jslot], (juse - 1u) & 1u))) {
         if (elect_one()) {
-          mbar_expect_tx(&s_fpfull[fb], a.fp_bytes);
-          tma_load_tile_4d(fp_s + fb * a.fp_stride, &tmX, slab * 64, tc.x0 - 1 - a.R, tc.y0 - 1 - a.R, tc.n, &s_fpfull[fb]);
+          mbar_expect_tx(&s_bfull[jslot], a.b_bytes);
+          tma_load_2d(smem_base + jslot * a.bstage, &tmB, jtap * d.Ci + jslab * 64, 0, &s_bfull[jslot]);
         }
         __syncwarp();
+        if (++jtap == 9) {
+          jtap = 0;
+          if (++jslab == nslabs) jslab = 0;
+        }
+        if (++jslot == (u32)a.nb) {
+          jslot = 0;
+          ++juse;
+        }
+        ++j;
+        progressed = true;
       }
+      if (u < u_total && (u < 2 || mbar_test_wait(&s_fpempty[u & 1], (u32)((u >> 1) - 1) & 1u))) {
+        const TileXY tc = tile_xy(a, utile);
+        const u32 fb = (u32)(u & 1);
+        if (elect_one()) {
+          if (FP_DBG(a) & 256) {
+            mbar_arrive(&s_fpfull[fb]);   // experiment: no box load
+          } else {
+            mbar_expect_tx(&s_fpfull[fb], a.fp_bytes);
+            tma_load_tile_4d(fp_s + fb * a.fp_stride, &tmX, uslab * 64, tc.x0 - 1 - a.R, tc.y0 - 1 - a.R, tc.n, &s_fpfull[fb]);
+          }
+        }
+        __syncwarp();
+        if (++uslab == nslabs) {
+          uslab = 0;
+          ++utile;
+        }
+        ++u;
+        progressed = true;
+      }
+      if (!progressed && !(FP_DBG(a) & 512)) __nanosleep(100);
     }
   }
   tc_fence_before();
@@ -488,32 +579,45 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 struct Plan {
-  int tw_shift, R, stages, BN;
+  int tw_shift, R, stages, nb, BN;
   u32 bstage, fp_bytes, fp_stride;
   size_t smem;
 };
 
-// (reach R, ring depth) in order of preference: three stages before a third pixel of reach, reach 2 before depth
+// Shared memory: tables + offset staging (fixed), two boxes of reach R, nb weight-tile slots.  All 9 * Ci/64 weight tiles
+// resident (no reloads at all) is worth one pixel of reach; otherwise >= 4 slots, then the largest reach.  The A ring lives
+// in the tensor-memory columns the two accumulators leave free (>= NG stages: a group must not lap the ring).
 bool make_plan(const cnb_conv_desc* d, Plan* p) {
   static const int env_r = [] { const char* e = getenv("CNB_DCN_REACH"); return e ? atoi(e) : 0; }();
   static const int env_stages = [] { const char* e = getenv("CNB_DCN_STAGES"); return e ? atoi(e) : 0; }();
+  static const int env_nb = [] { const char* e = getenv("CNB_DCN_NB"); return e ? atoi(e) : 0; }();
   p->tw_shift = d->Wi % 16 == 0 ? 4 : 3;
   const int TW = 1 << p->tw_shift, TH = BM >> p->tw_shift;
   p->BN = round_up(d->Co, 16);
   p->bstage = ((u32)p->BN * 128u + 1023u) & ~1023u;
-  const size_t stage = A_BYTES + p->bstage;
+  const int nkb = 9 * (d->Ci / 64);
+  int st = (512 - 2 * round_up(p->BN, 32)) / A_COLS;
+  if (st > MAX_STAGES) st = MAX_STAGES;
+  if (env_stages > 0 && st > env_stages) st = env_stages;
+  if (st < NG) return false;
+  p->stages = st;
   const size_t fixed = (size_t)2 * NTAB * (sizeof(float4) + sizeof(u32)) + (size_t)BM * OM_CS * 4 + (size_t)p->BN * 8 + 1024;
   const size_t budget = 226 * 1024;
-  static const int pref[][2] = {{3, 3}, {2, 3}, {3, 2}, {2, 2}, {1, 3}, {1, 2}};
+  static const int pref[][2] = {{3, -1}, {2, -1}, {3, 4}, {2, 4}, {1, 2}};   // (R, minimum slots; -1 = all tiles resident)
   for (const auto& c : pref) {
     const int R = env_r > 0 ? env_r : c[0];
-    const int st = env_stages > 0 ? (env_stages > MAX_STAGES ? MAX_STAGES : env_stages) : c[1];
     const int FW = TW + 2 * R + 3, FH = TH + 2 * R + 3;
     const u32 fpb = (u32)FW * FH * 128u;
     const u32 fps = (fpb + 1023u) & ~1023u;
-    const size_t smem = fixed + 2 * (size_t)fps + (size_t)st * stage;
-    if (smem <= budget && st >= 2 && R >= 1) {
-      p->R = R; p->stages = st; p->fp_bytes = fpb; p->fp_stride = fps; p->smem = smem;
+    if (fixed + 2 * (size_t)fps + 2 * (size_t)p->bstage > budget) continue;
+    int nb = (int)((budget - fixed - 2 * (size_t)fps) / p->bstage);
+    if (nb > nkb) nb = nkb;
+    if (nb > MAX_B) nb = MAX_B;
+    if (env_nb > 0 && nb > env_nb) nb = env_nb;
+    const int need = env_nb > 0 ? 2 : (c[1] < 0 ? nkb : c[1]);
+    if (nb >= need && nb >= 2) {
+      p->R = R; p->nb = nb; p->fp_bytes = fpb; p->fp_stride = fps;
+      p->smem = fixed + 2 * (size_t)fps + (size_t)nb * p->bstage;
       return true;
     }
   }
@@ -566,14 +670,15 @@ int dcn_fp_run(const cnb_conv_desc* d, const void* x, const float* om, int om_cs
   a.nkb = 9 * (d->Ci / 64);
   a.b_bytes = (u32)a.BN * 128u;
   a.bstage = p.bstage;
-  a.stage_bytes = A_BYTES + a.bstage;
   a.stages = p.stages;
+  a.nb = p.nb;
+  a.b_resident = p.nb >= a.nkb ? 1 : 0;
   a.acc_stride = (u32)round_up(a.BN, 32);
-  a.tmem_cols = 32;
-  while (a.tmem_cols < 2 * a.acc_stride) a.tmem_cols <<= 1;
+  a.a_col0 = 2 * a.acc_stride;
+  a.tmem_cols = 512;   // one CTA per SM: two accumulators + the A ring
   a.idesc = make_idesc_bf16(BM, a.BN);
 
-  CUtensorMap tmB, tmX;
+  CUtensorMap tmB, tmX, tmO;
   {
     const int Kpad = 9 * d->Ci;   // Ci % 64 == 0: already a multiple of the packing granularity
     cuuint64_t dims[2] = {(cuuint64_t)Kpad, (cuuint64_t)a.BN};
@@ -589,22 +694,39 @@ int dcn_fp_run(const cnb_conv_desc* d, const void* x, const float* om, int om_cs
     }
   }
   {
-    // the input as {C, W, H, N}; one box = 64 channels x FW x FH pixels, 128 bytes per pixel in shared memory,
-    // out-of-image pixels zero-filled
+    // the input as {C, W, H, N}; one box = 64 channels x FW x FH pixels, 128 bytes per pixel in shared memory with the
+    // 128-byte swizzle (chunk index XOR box pixel index mod 8), out-of-image pixels zero-filled
     const cuuint64_t cs2 = (cuuint64_t)d->x_cstride * 2;
     cuuint64_t dims[4] = {(cuuint64_t)d->Ci, (cuuint64_t)d->Wi, (cuuint64_t)d->Hi, (cuuint64_t)d->B};
     cuuint64_t strides[3] = {cs2, cs2 * d->Wi, cs2 * d->Wi * d->Hi};
     cuuint32_t box[4] = {64u, (cuuint32_t)a.FW, (cuuint32_t)a.FH, 1u};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = drv.tiled(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)((const __nv_bfloat16*)x + d->x_coffset), dims,
-                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       set_error("dcnv2: cuTensorMapEncodeTiled (input box %dx%d) failed (%d)", a.FW, a.FH, (int)r);
       return CNB_ERR_CUDA;
     }
   }
+  {
+    // the offset/mask map as {32 floats, W, H, N}: one box = the tile's TW x TH pixels, 128 bytes each, 128-byte swizzle;
+    // rows below the image are zero-filled (their table entries are never used)
+    cuuint64_t dims[4] = {(cuuint64_t)OM_CS, (cuuint64_t)d->Wi, (cuuint64_t)d->Hi, (cuuint64_t)d->B};
+    cuuint64_t strides[3] = {(cuuint64_t)OM_CS * 4, (cuuint64_t)OM_CS * 4 * d->Wi, (cuuint64_t)OM_CS * 4 * d->Wi * d->Hi};
+    cuuint32_t box[4] = {(cuuint32_t)OM_CS, (cuuint32_t)TW, (cuuint32_t)TH, 1u};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = drv.tiled(&tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)om, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("dcnv2: cuTensorMapEncodeTiled (offset map) failed (%d)", (int)r);
+      return CNB_ERR_CUDA;
+    }
+  }
   static const bool blend_bf16 = [] { const char* e = getenv("CNB_DCN_BLEND"); return e && e[0] == 'b'; }();
+  static const int env_dbg = [] { const char* e = getenv("CNB_DCN_DEBUG"); return e ? atoi(e) : 0; }();
+  a.debug = env_dbg;
   static PerDeviceOnce once;
   if (once.need()) {
     CNB_CUDA(cudaFuncSetAttribute(dcn_fp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
@@ -613,9 +735,9 @@ int dcn_fp_run(const cnb_conv_desc* d, const void* x, const float* om, int om_cs
   }
   const int grid = a.m_tiles < drv.num_sms ? a.m_tiles : drv.num_sms;
   if (blend_bf16)
-    CNB_CUDA(launch_pdl(dcn_fp_kernel<true>, dim3(grid), dim3(NTHREADS), p.smem, st, tmB, tmX, a));
+    CNB_CUDA(launch_pdl(dcn_fp_kernel<true>, dim3(grid), dim3(NTHREADS), p.smem, st, tmB, tmX, tmO, a));
   else
-    CNB_CUDA(launch_pdl(dcn_fp_kernel<false>, dim3(grid), dim3(NTHREADS), p.smem, st, tmB, tmX, a));
+    CNB_CUDA(launch_pdl(dcn_fp_kernel<false>, dim3(grid), dim3(NTHREADS), p.smem, st, tmB, tmX, tmO, a));
   CNB_LAUNCH_CHECK();
   return CNB_OK;
 }

@@ -1,4 +1,6 @@
-"""Times single DCNv2 layers of the DLA-34 schedule (B=32): python tools/dcn_bench.py [case ...]"""
+"""Times single DCNv2 layers of the DLA-34 schedule (B=32): python tools/dcn_bench.py [case ...]
+DCN_BENCH_OFFSETS=smooth (default: per-tap displacement + small per-pixel noise, what a network produces) | random
+(independent N(0, 0.5) per pixel and tap: neighbouring pixels sample unrelated positions)"""
 import os
 import sys
 
@@ -15,7 +17,10 @@ for name in (sys.argv[1:] or list(CASES)):
     x = torch.randn(B, hw, hw, ci, device=dev).to(torch.bfloat16)
     w = ops.pack_conv_weights(torch.randn(co, ci, 3, 3, device=dev) * 0.05)
     sc, sh = torch.ones(co, device=dev), torch.zeros(co, device=dev)
-    om = torch.randn(B, hw, hw, 32, device=dev) * 0.5
+    if os.environ.get("DCN_BENCH_OFFSETS", "smooth") == "random":
+        om = torch.randn(B, hw, hw, 32, device=dev) * 0.5
+    else:
+        om = (torch.rand(1, 1, 1, 32, device=dev) * 2 - 1) * 0.8 + torch.randn(B, hw, hw, 32, device=dev) * 0.05
     run = lambda: ops.dcnv2(x, om, w, co, sc, sh, act=1)
     for _ in range(3):
         run()
