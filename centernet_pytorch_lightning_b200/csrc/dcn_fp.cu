@@ -72,7 +72,8 @@ struct FArgs {
   int FW, FH;      // box: (TW + 2R + 3) x (TH + 2R + 3) pixels
   u32 fp_bytes;    // FW * FH * 128
   u32 fp_stride;   // fp_bytes rounded up to 1 KB
-  int BN;          // = Co rounded up to 16, <= 128
+  int BN;          // = Co rounded up to 16, <= 256
+  int nacc;        // accumulators in tensor memory: 2 (epilogue of tile i overlaps tile i+1), 1 for BN > 128
   int nkb;         // 9 * Ci/64
   u32 bstage;      // bytes of one weight-tile slot (b_bytes rounded up to 1 KB)
   int stages;      // A ring depth: stage i = tensor-memory columns a_col0 + 32 i
@@ -462,7 +463,7 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
     const u64 db0 = make_sdesc(smem_base, 16, 1024, 2);
     const u32 bstage16 = a.bstage >> 4;
     for (int tile = tile_begin; tile < tile_end; ++tile, ++t) {
-      const u32 acc = t & 1u, acc_ph = (t >> 1) & 1u;
+      const u32 acc = a.nacc == 2 ? (t & 1u) : 0u, acc_ph = (a.nacc == 2 ? (t >> 1) : t) & 1u;
       mbar_wait_parked(&s_tempty[acc], acc_ph ^ 1u);
       tc_fence_after();
       const u32 tmem_d = tmem_base + acc * a.acc_stride;
@@ -499,7 +500,7 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
     const int q = warp & 3;
     u32 t = 0;
     for (int tile = tile_begin; tile < tile_end; ++tile, ++t) {
-      const u32 acc = t & 1u, acc_ph = (t >> 1) & 1u;
+      const u32 acc = a.nacc == 2 ? (t & 1u) : 0u, acc_ph = (a.nacc == 2 ? (t >> 1) : t) & 1u;
       const TileXY tc = tile_xy(a, tile);
       const int r = 32 * q + lane;
       const int oy = tc.y0 + (r >> a.tw_shift), ox = tc.x0 + (r & (TW - 1));
@@ -596,14 +597,14 @@ bool make_plan(const cnb_conv_desc* d, Plan* p) {
   p->BN = round_up(d->Co, 16);
   p->bstage = ((u32)p->BN * 128u + 1023u) & ~1023u;
   const int nkb = 9 * (d->Ci / 64);
-  int st = (512 - 2 * round_up(p->BN, 32)) / A_COLS;
+  int st = (512 - (p->BN > 128 ? 1 : 2) * round_up(p->BN, 32)) / A_COLS;
   if (st > MAX_STAGES) st = MAX_STAGES;
   if (env_stages > 0 && st > env_stages) st = env_stages;
   if (st < NG) return false;
   p->stages = st;
   const size_t fixed = (size_t)2 * NTAB * (sizeof(float4) + sizeof(u32)) + (size_t)BM * OM_CS * 4 + (size_t)p->BN * 8 + 1024;
   const size_t budget = 226 * 1024;
-  static const int pref[][2] = {{3, -1}, {2, -1}, {3, 4}, {2, 4}, {1, 2}};   // (R, minimum slots; -1 = all tiles resident)
+  static const int pref[][2] = {{3, -1}, {2, -1}, {3, 4}, {2, 4}, {2, 2}, {1, 2}};   // (R, minimum slots; -1 = all tiles resident)
   for (const auto& c : pref) {
     const int R = env_r > 0 ? env_r : c[0];
     const int FW = TW + 2 * R + 3, FH = TH + 2 * R + 3;
@@ -631,7 +632,7 @@ bool make_plan(const cnb_conv_desc* d, Plan* p) {
 bool dcn_fp_supported(const cnb_conv_desc* d, int om_cstride) {
   static const bool off = [] { const char* e = getenv("CNB_DCN_IMPL"); return e && (e[0] == 'v' || e[0] == 'w'); }();
   Plan p;
-  return !off && om_cstride == OM_CS && d->Ci % 64 == 0 && d->Co % 8 == 0 && round_up(d->Co, 16) <= 128 && d->Wi % 8 == 0 &&
+  return !off && om_cstride == OM_CS && d->Ci % 64 == 0 && d->Co % 8 == 0 && round_up(d->Co, 16) <= 256 && d->Wi % 8 == 0 &&
          (long long)d->B * d->Hi * d->Wi < (1ll << 29) &&
          d->x_cstride % 8 == 0 && d->x_coffset % 8 == 0 && make_plan(d, &p);
 }
@@ -674,7 +675,8 @@ int dcn_fp_run(const cnb_conv_desc* d, const void* x, const float* om, int om_cs
   a.nb = p.nb;
   a.b_resident = p.nb >= a.nkb ? 1 : 0;
   a.acc_stride = (u32)round_up(a.BN, 32);
-  a.a_col0 = 2 * a.acc_stride;
+  a.nacc = a.BN > 128 ? 1 : 2;
+  a.a_col0 = (u32)a.nacc * a.acc_stride;
   a.tmem_cols = 512;   // one CTA per SM: two accumulators + the A ring
   a.idesc = make_idesc_bf16(BM, a.BN);
 

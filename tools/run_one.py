@@ -80,7 +80,7 @@ else:
     x = torch.randn(B, hw, hw, ci, device=dev).to(torch.bfloat16)
     w = ops.pack_conv_weights(torch.randn(co, ci, k, k, device=dev) * 0.05)
     sc, sh = torch.ones(co, device=dev), torch.zeros(co, device=dev)
-    om = (torch.randn(B, hw, hw, 32, device=dev) * 0.5) if what.startswith("dcn") else None
+    om = ((torch.rand(1, 1, 1, 32, device=dev) * 2 - 1) * 0.8 + torch.randn(B, hw, hw, 32, device=dev) * 0.05) if what.startswith("dcn") else None
     for _ in range(4):
         if om is not None:
             ops.dcnv2(x, om, w, co, sc, sh, act=1)
