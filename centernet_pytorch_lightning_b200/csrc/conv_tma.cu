@@ -60,8 +60,10 @@ struct TArgs {
   int debug;       // CNB_TMA_DEBUG (timing experiments only): 1 no A loads, 2 no B loads, 4 no MMAs, 8 no stores, 16 no epilogue
 };
 
-template <bool CL, bool DBG>   // CL: launched as clusters of a.csize > 1 CTAs (multicast weight tiles); DBG: the
-                              // CNB_TMA_DEBUG / CNB_TMA_TRACE timing experiments (kept out of the production loops)
+// CL: launched as clusters of a.csize > 1 CTAs (multicast weight tiles); DBG: the CNB_TMA_DEBUG / CNB_TMA_TRACE timing
+// experiments (kept out of the production loops); PAIR (implies CL, csize 2): the two CTAs run ONE 256-row
+// tcgen05.mma.cta_group::2 per K step -- each holds its 128 rows of A and half of the weight tile, the leader issues.
+template <bool CL, bool DBG, bool PAIR = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TArgs a) {
   extern __shared__ unsigned char smem_dyn[];
@@ -81,11 +83,12 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (tid == 0) {
     for (int s = 0; s < a.stages; ++s) {
       mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], CL ? (u32)a.csize : 1u);   // one tcgen05.commit per CTA of the cluster
+      mbar_init(&s_empty[s], (CL && !PAIR) ? (u32)a.csize : 1u);   // one tcgen05.commit per CTA of the cluster
+                                                                   // (pair: the leader's, multicast to both)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_tfull[i], 1);
-      mbar_init(&s_tempty[i], NEPI);   // one arrival per epilogue warp
+      mbar_init(&s_tempty[i], PAIR ? 2 * NEPI : NEPI);   // one arrival per epilogue warp (pair: of both CTAs, on the leader)
     }
     fence_mbar_init();
   }
@@ -93,7 +96,11 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
-  if (warp == 1) tmem_alloc(&s_tmem, a.tmem_cols);
+  if (PAIR) cluster_sync_all();   // both CTAs are resident before the pair allocates tensor memory
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair(&s_tmem, a.tmem_cols);
+    else tmem_alloc(&s_tmem, a.tmem_cols);
+  }
   pdl_launch_dependents();      // the next kernel may start its prologue as soon as SMs free up ...
   pdl_wait();                   // ... and this one reads global memory (scale/shift included: they may have been
                                 // produced in-stream) only after its predecessor has completed
@@ -140,7 +147,10 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int w0 = ox * d.stride - d.pad, h0 = oy * d.stride - d.pad;
         const int n0 = n_tile * a.BN + (CL ? crank * a.bn_share : 0);
         const bool ldA = valid && !(dbg & 1);
-        const u32 slab_tx = (ldA ? a.a_slab_bytes : 0u) + (ldB ? a.b_slab_bytes : 0u);
+        // pair: the leader's barrier collects the bytes of BOTH CTAs (its own tile is always valid)
+        const bool peer_valid = PAIR && (m_group * 2 + 1 < a.m_tiles);
+        const u32 slab_tx = PAIR ? a.a_slab_bytes * (peer_valid ? 2u : 1u) + 2u * a.b_slab_bytes
+                                 : (ldA ? a.a_slab_bytes : 0u) + (ldB ? a.b_slab_bytes : 0u);
         int c0 = 0, kw = 0, kh = 0, k0 = 0;     // slab cursor: channel offset, filter tap, K index
         int left = a.nslabs;
         for (int ks = 0; ks < a.nsteps; ++ks) {
@@ -149,16 +159,23 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           ++kcount;
           const int nsl = min(a.g, left);
           left -= nsl;
-          if (elect_one()) mbar_expect_tx(&s_full[s], (u32)nsl * slab_tx);
-          u32 da = sa, db = sa + a.a_bytes + b_share_off;
+          if (elect_one() && (!PAIR || crank == 0)) mbar_expect_tx(&s_full[s], (u32)nsl * slab_tx);
+          u32 da = sa, db = sa + a.a_bytes + (PAIR ? 0u : b_share_off);
           for (int j = 0; j < nsl; ++j) {
             if (elect_one()) {
+            if (PAIR) {   // own A rows and own half of the weight tile into own shared memory, bytes onto the leader's barrier
+              if (ldA)
+                tma_load_im2col_4d_pair(da, &tmA, c0, w0, h0, n, (unsigned short)((kh < d.KH ? kw : d.KW - 1) * d.dil),
+                                        (unsigned short)((kh < d.KH ? kh : d.KH - 1) * d.dil), &s_full[s]);
+              tma_load_2d_pair(db, &tmB, k0, n0, &s_full[s]);
+            } else {
             if (ldA)   // past the last tap (K padding, zero weights) any finite activations do: repeat the last tap
               tma_load_im2col_4d(da, &tmA, c0, w0, h0, n, (unsigned short)((kh < d.KH ? kw : d.KW - 1) * d.dil),
                                  (unsigned short)((kh < d.KH ? kh : d.KH - 1) * d.dil), &s_full[s]);
             if (ldB) {
               if (!CL) tma_load_2d(db, &tmB, k0, n0, &s_full[s]);
               else tma_load_2d_mc(db, &tmB, k0, n0, &s_full[s], cmask);   // this CTA's rows, into every CTA
+            }
             }
             }
             da += a.a_slab_bytes;
@@ -184,7 +201,8 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===========================================================
-    {   // every lane walks the loop; one elected lane (always the same one) issues MMAs and commits
+    if (!PAIR || crank == 0) {   // every lane walks the loop; one elected lane (always the same one) issues MMAs and
+                                 // commits; in a pair only the leader CTA issues (for both)
       u32 t = 0;
       const int mma_per_slab = a.slabW >= 16 ? a.slabW / 16 : 1;
       const bool wide = a.slabW >= 16;
@@ -216,7 +234,8 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int nmma = wide ? nsl : (nsl + 1) >> 1;
             for (int j = 0; j < nmma; ++j) {
               for (int kk = 0; kk < mma_per_slab; ++kk) {   // +32 bytes of K inside the swizzle atom
-                umma_bf16(tmem_d, da + (u64)(2 * kk), db + (u64)(2 * kk), a.idesc, accumulate);
+                if (PAIR) umma_bf16_pair(tmem_d, da + (u64)(2 * kk), db + (u64)(2 * kk), a.idesc, accumulate);
+                else umma_bf16(tmem_d, da + (u64)(2 * kk), db + (u64)(2 * kk), a.idesc, accumulate);
                 accumulate = 1;
               }
               da += (u64)aslab16;
@@ -225,6 +244,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
           // stage is free once these MMAs have read it -- in every CTA of the cluster, whose producers multicast into it
           if (dbg & 32) mbar_arrive(&s_empty[s]);   // (timing experiment, only meaningful without MMAs)
+          else if (PAIR) umma_commit_pair(&s_empty[s]);
           else if (!CL) umma_commit(&s_empty[s]);
           else umma_commit_mc(&s_empty[s], cmask);
           }
@@ -238,7 +258,10 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             soff16 = 0;
           }
         }
-        if (elect_one()) umma_commit(&s_tfull[acc]);      // accumulator complete
+        if (elect_one()) {   // accumulator complete (pair: in both CTAs' tensor memories)
+          if (PAIR) umma_commit_pair(&s_tfull[acc]);
+          else umma_commit(&s_tfull[acc]);
+        }
         __syncwarp();
       }
     }
@@ -286,13 +309,19 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_tempty[acc]);
+      if (lane == 0) {
+        if (PAIR && crank != 0) mbar_arrive_cluster(&s_tempty[acc], 0);   // the leader's MMA warp owns both accumulators
+        else mbar_arrive(&s_tempty[acc]);
+      }
     }
   }
   tc_fence_before();
   if (CL) cluster_sync_all();   // no CTA leaves while a peer can still signal its barriers
   else __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
+  if (warp == 1) {
+    if (PAIR) tmem_dealloc_pair(tmem_base, a.tmem_cols);
+    else tmem_dealloc(tmem_base, a.tmem_cols);
+  }
 }
 
 // ---- host side (tensor-map encode entry points: tma_host.h) ------------------------------------------------
@@ -329,6 +358,33 @@ TmaDriver& tma_driver() {
     drv.ok = drv.num_sms > 0;
   });
   return drv;
+}
+
+static int max_active_clusters_pair(size_t smem) {   // CTA pairs of the cta_group::2 instantiation; cached per KB
+  static std::mutex mu;
+  static int cache[2] = {};
+  std::lock_guard<std::mutex> lock(mu);
+  const int kb = (int)((smem + 1023) / 1024);
+  if (cache[0] == kb && cache[1] > 0) return cache[1];
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(128);
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, conv_tma_kernel<true, false, true>, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  cache[0] = kb;
+  cache[1] = n;
+  return n;
 }
 
 // clusters of `c` CTAs (one CTA per SM at this shared-memory size) that can be resident at once; cached
@@ -392,8 +448,15 @@ int conv_tma_run(const cnb_conv_desc* d, const void* x, const void* wpk, const f
   a.nslabs = round_up(Ktot, 16) / a.slabW;
   if (a.slabW == 8) a.nslabs = round_up(a.nslabs, 2);
   CNB_CHECK_ARG(a.nslabs * a.slabW <= Kpad, "conv: internal K padding error");
+  // CTA pairs (tcgen05.mma.cta_group::2, M = 256): wide-N layers are bound by shared-memory bandwidth -- per K block the TMA
+  // engine writes and the tensor core reads A (16 KB) + B (BN * 128 B) -- and a pair halves the B part per SM.
+  // CNB_CONV_PAIR=0 disables, =1 forces it for every eligible geometry.
+  static const int env_pair = [] { const char* e = getenv("CNB_CONV_PAIR"); return e ? atoi(e) : -1; }();
+  static const int env_c = [] { const char* e = getenv("CNB_CONV_CLUSTER"); return e ? atoi(e) : 0; }();
+  const bool pair = env_pair != 0 && env_c == 0 && a.slabW == 64 && a.BN % 16 == 0 && a.m_tiles >= 2 &&
+                    (env_pair == 1 || a.BN >= 192);   // measured: BN = 256 +10-12 %, BN = 128 +-0
   a.a_slab_bytes = (u32)(BM * a.slabW * 2);
-  a.b_slab_bytes = (u32)(a.BN * a.slabW * 2);
+  a.b_slab_bytes = (u32)((pair ? a.BN / 2 : a.BN) * a.slabW * 2);
   a.nscale = a.n_tiles * a.BN;
   const size_t budget = 200 * 1024 - (size_t)a.nscale * 8;
   // K per pipeline stage: the two single-thread roles pay a few hundred clocks of bookkeeping per stage (barrier
@@ -431,13 +494,14 @@ int conv_tma_run(const cnb_conv_desc* d, const void* x, const void* wpk, const f
   a.acc_stride = (u32)round_up(a.BN, 32);
   a.tmem_cols = 32;
   while (a.tmem_cols < 2 * a.acc_stride) a.tmem_cols <<= 1;
-  a.idesc = make_idesc_bf16(BM, a.BN);
+  a.idesc = make_idesc_bf16(pair ? 2 * BM : BM, a.BN);
   const size_t smem = (size_t)a.stages * a.stage_bytes + (size_t)a.nscale * 8 + 1024;
   static PerDeviceOnce once;
   if (once.need()) {
     CNB_CUDA(cudaFuncSetAttribute(conv_tma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     CNB_CUDA(cudaFuncSetAttribute(conv_tma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     CNB_CUDA(cudaFuncSetAttribute(conv_tma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CNB_CUDA(cudaFuncSetAttribute(conv_tma_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     once.mark();
   }
 
@@ -445,10 +509,14 @@ int conv_tma_run(const cnb_conv_desc* d, const void* x, const void* wpk, const f
   // from 16 KB + BN*128 to 16 KB + BN*128/c, but measured on B200 it buys nothing: the kernel is paced by the MMA
   // issue thread (tcgen05.mma with both operands in shared memory accepts one 128 x BN x 16 instruction per
   // ~BN clocks) plus its per-stage bookkeeping, not by the loads.  Default: no clusters.
-  static const int env_c = [] { const char* e = getenv("CNB_CONV_CLUSTER"); return e ? atoi(e) : 0; }();
   a.csize = 1;
   int nclusters = drv.num_sms;
-  if ((env_c == 2 || env_c == 4) && a.slabW == 64 && a.BN % (8 * env_c) == 0 && a.m_tiles >= env_c) {
+  if (pair) {
+    const int ncl = max_active_clusters_pair(smem);
+    CNB_CHECK_ARG(ncl >= 1, "conv: no CTA pair fits (shared memory %zu bytes)", smem);
+    a.csize = 2;
+    nclusters = ncl;
+  } else if ((env_c == 2 || env_c == 4) && a.slabW == 64 && a.BN % (8 * env_c) == 0 && a.m_tiles >= env_c) {
     const int ncl = max_active_clusters(env_c, smem);
     if (ncl >= 1) {
       a.csize = env_c;
@@ -528,7 +596,18 @@ int conv_tma_run(const cnb_conv_desc* d, const void* x, const void* wpk, const f
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CNB_CUDA(cudaLaunchKernelEx(&cfg, conv_tma_kernel<true, false>, tmA, tmB, a));
+    if (pair) {   // programmatic dependent launch as for the single-CTA kernel
+      static const bool pdl_on = [] { const char* e = getenv("CNB_PDL"); return !(e && e[0] == '0'); }();
+      cudaLaunchAttribute attr2[2];
+      attr2[0] = attr[0];
+      attr2[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr2[1].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr2;
+      cfg.numAttrs = pdl_on ? 2 : 1;
+      CNB_CUDA(cudaLaunchKernelEx(&cfg, conv_tma_kernel<true, false, true>, tmA, tmB, a));
+    } else {
+      CNB_CUDA(cudaLaunchKernelEx(&cfg, conv_tma_kernel<true, false>, tmA, tmB, a));
+    }
   }
   CNB_LAUNCH_CHECK();
   if (env_trace) {   // debugging aid: per-K-block clock stamps of CTA 0 (producer got the stage | MMA thread got the

@@ -74,6 +74,64 @@ __device__ __forceinline__ void tmem_ld64_nowait(u32 taddr, u32 (&v)[64]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- CTA pairs (cta_group::2): two CTAs of a cluster on neighbouring SMs run ONE 256-row MMA ---------------------
+// Each CTA holds its 128 rows of A and HALF of the B tile at the same shared-memory offsets and receives its 128 rows
+// of D in its own tensor memory; only the leader (cluster rank 0) issues tcgen05.mma / tcgen05.commit.  Per SM a K block
+// then costs the shared-memory traffic of A + B/2 instead of A + B -- the measured limiter of the wide-N layers.
+__device__ __forceinline__ void tmem_alloc_pair(u32* smem_dst, u32 ncols) {   // the same warp of BOTH CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(u32 taddr, u32 ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(u32 tmem_d, u64 desc_a, u64 desc_b, u32 idesc, u32 accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this shared-memory offset in both CTAs of the pair once the pair's MMAs have completed
+__device__ __forceinline__ void umma_commit_pair(void* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((unsigned short)3)
+      : "memory");
+}
+// shared-memory address of `bar` in the pair's leader CTA (its shared::cluster address with the peer bit cleared)
+__device__ __forceinline__ u32 pair_leader_addr(const void* bar) { return smem_u32(bar) & 0xFEFFFFFFu; }
+// TMA loads issued by either CTA of a pair: data into the issuing CTA's shared memory, transaction bytes onto the
+// LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_pair(u32 dst_smem, const void* tmap, int c0, int c1, void* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+          "r"(dst_smem),
+      "l"(reinterpret_cast<u64>(tmap)), "r"(pair_leader_addr(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d_pair(u32 dst_smem, const void* tmap, int c, int w, int h, int n,
+                                                        unsigned short off_w, unsigned short off_h, void* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(dst_smem),
+      "l"(reinterpret_cast<u64>(tmap)), "r"(pair_leader_addr(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w),
+      "h"(off_h)
+      : "memory");
+}
+// mbarrier arrive on the barrier at this shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(void* bar, u32 rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+
 // ---- shared-memory matrix descriptors (K-major operands) ----------------------------------------------
 // layout_type: 2 = SWIZZLE_128B (rows of 128 B, 8-row groups 1024 B apart), 4 = SWIZZLE_64B (64 B rows, 512 B
 // groups), 6 = SWIZZLE_32B (32 B rows, 256 B groups), 0 = no swizzle (core matrix = 8 rows x 16 B contiguous;

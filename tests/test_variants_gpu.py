@@ -17,6 +17,8 @@ VARIANTS = [
     ({"CNB_CONV_CLUSTER": "4"}, "test_conv_matches_torch"),
     ({"CNB_CONV_IMPL": "v1"}, "test_conv_matches_torch or test_stem_space_to_depth"),
     ({"CNB_CONV_ROWS": "0"}, "test_conv_matches_torch"),
+    ({"CNB_CONV_PAIR": "1"}, "test_conv_matches_torch or test_conv_concat_slices or head"),   # CTA pairs for every eligible N
+    ({"CNB_CONV_PAIR": "0"}, "test_conv_matches_torch or test_conv_concat_slices"),
     ({"CNB_DCN_BLEND": "bf16"}, "dcn"),
     ({"CNB_DCN_GROUPS": "1"}, "dcn"),
     ({"CNB_DCN_GROUPS": "4"}, "dcn"),
