@@ -526,7 +526,7 @@ def run_b200(args, rank, local_rank, world):
     conv_ms, conv_fl, n_conv = conv_ms / 2, conv_fl / 2, n_conv // 2
     tf = conv_fl / (conv_ms * 1e-3) / 1e12
     dcn_ms, dcn_fl, n_dcn = prof.summary("dcn")
-    roofline = {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM family: conv_tma_kernel, conv_rows_kernel, dcn_ws_kernel",
+    roofline = {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM family: conv_tma_kernel (CTA pairs for N >= 192), conv_rows_kernel, dcn_fp_kernel, head_fused_kernel",
                 "achieved": tf, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": tf / pk["tf_sust"],
                 "traffic": None, "peak_source": pk["src"] + " (sustained bf16, kernel timed inside a long step)",
                 "launches_per_step": n_conv, "kernel_ms_per_step": conv_ms, "flops_per_step": conv_fl,

@@ -17,10 +17,10 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --
    --log-file $o/launches_$tag.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph --no-train-leg > $o/ncu_bench_$tag.log 2>&1
 echo "ncu launches exit $?"
 # DRAM traffic of the tensor-core family over one eager step (two cheap metrics, one pass): -> profiles/traffic.json
-timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:"conv_|dcn_ws|head_fused" -c 400 --csv \
+timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:"conv_|dcn_|head_fused" -c 400 --csv \
    --log-file $o/traffic_$tag.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph --no-train-leg > $o/ncu_traffic_$tag.log 2>&1
 echo "ncu traffic exit $?"
-for k in "headfused:head_fused:headfused" "wgrad64:conv_wgrad:wgrad64" "wgrad256:conv_wgrad:wgrad256" "col2im64:dcn_col2im:col2im64" "im2col64:dcn_im2col:im2col64" "dcn64:dcn_ws:dcn64" "decode:decode_:decode" "conv256:conv_tma:tma256"; do
+for k in "headfused:head_fused:headfused" "wgrad64:conv_wgrad:wgrad64" "wgrad256:conv_wgrad:wgrad256" "col2im64:dcn_col2im:col2im64" "im2col64:dcn_im2col:im2col64" "dcn64:dcn_fp:dcn64" "decode:decode_:decode" "conv256:conv_tma:tma256"; do
   what=${k%%:*}; rest=${k#*:}; pat=${rest%%:*}; name=${rest#*:}
   cnt=1; [ "$what" = decode ] && cnt=2
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$pat -s 2 -c $cnt \
