@@ -151,6 +151,30 @@ __device__ __forceinline__ void mbar_wait_parked(void* bar, u32 parity) {
     if (t1 - t0 > 4000000000ull) __trap();   // 4 s: a lost arrival becomes a CUDA error, not a hang
   }
 }
+// The same on a precomputed shared-memory address: single-warp role loops that touch a barrier per K block keep the
+// addresses as loop-carried state (the generic-to-shared conversion of `&bar[i]` costs a special-register read and a few
+// dependent uniform instructions each time, which a lone warp cannot hide).
+__device__ __forceinline__ bool mbar_try_wait_parked_a(u32 addr, u32 parity) {
+  u32 ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(addr), "r"(parity), "r"(20000u)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_parked_a(u32 addr, u32 parity) {
+  if (mbar_try_wait_parked_a(addr, parity)) return;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (!mbar_try_wait_parked_a(addr, parity)) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 4000000000ull) __trap();   // 4 s: a lost arrival becomes a CUDA error, not a hang
+  }
+}
 // Non-blocking poll (mbarrier.test_wait never suspends the thread): for single-thread roles whose wake-up latency
 // after a suspended try_wait would sit on the critical path.
 __device__ __forceinline__ bool mbar_test_wait(void* bar, u32 parity) {

@@ -30,6 +30,9 @@ int conv_rows_run(const cnb_conv_desc* d, const void* x, const void* wpk, const 
 bool dcn_fp_supported(const cnb_conv_desc* d, int om_cstride);                  // dcn_fp.cu
 int dcn_fp_run(const cnb_conv_desc* d, const void* x, const float* om, int om_cstride, const void* wpk,
                const float* scale, const float* shift, void* y, cudaStream_t st);
+bool conv_fp_supported(const cnb_conv_desc* d);                                 // dcn_fp.cu (plain mode)
+int conv_fp_run(const cnb_conv_desc* d, const void* x, const void* wpk, const float* scale, const float* shift,
+                const void* res, void* y, cudaStream_t st);
 bool dcn_ws_supported(const cnb_conv_desc* d, int om_cstride);                  // dcn_ws.cu
 int dcn_ws_run(const cnb_conv_desc* d, const void* x, const float* om, int om_cstride, const void* wpk,
                const float* scale, const float* shift, void* y, cudaStream_t st);
@@ -453,6 +456,8 @@ static int run_conv(const cnb_conv_desc* d, const void* x, const float* om, int 
     // cp.async gather kernel below for A/B comparisons
     static const bool use_v1 = [] { const char* e = getenv("CNB_CONV_IMPL"); return e && e[0] == 'v' && e[1] == '1'; }();
     CNB_CHECK_ARG(d->w_kw == 0 || d->w_kw >= d->KW, "conv: w_kw=%d smaller than KW=%d", d->w_kw, d->KW);
+    // 3x3 / stride 1 with Ci % 64 == 0 and N <= 128: input box in shared memory, A operand through tensor memory (dcn_fp.cu)
+    if (!use_v1 && conv_fp_supported(d)) return conv_fp_run(d, x, wpk, scale, shift, res, y, st);
     // wide thin layers (W_out % 128 == 0, Ci <= 64, KxK): row-window kernel, every input pixel fetched once
     if (!use_v1 && conv_rows_supported(d)) return conv_rows_run(d, x, wpk, scale, shift, res, y, st);
     if (!use_v1 && (d->Ci >= 32) && (d->w_kw == 0 || d->w_kw == d->KW) && d->KH == d->KW && d->pad_w1 == 0)

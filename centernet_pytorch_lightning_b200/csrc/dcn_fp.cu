@@ -80,6 +80,8 @@ struct FArgs {
   int nb;          // weight-tile slots in shared memory; K block j of the CTA's stream uses slot j % nb
   int b_resident;  // nb >= nkb: the 9 * Ci/64 weight tiles are loaded once and stay
   u32 b_bytes, tmem_cols, acc_stride, a_col0, idesc;
+  int kps;         // K blocks per A stage: 1, or 3 in plain mode with N <= 64 (a group samples a whole filter row per handshake)
+  int plain;       // 1: plain 3x3 / stride 1 / pad 1 convolution through the same machinery (no offsets, no table, R = 0)
   int debug;       // timing experiments (-DCNB_DCN_EXPERIMENTS): 1 no corner loads, 2 no blend, 4 no tcgen05.st, 8 no table read
 };
 
@@ -125,6 +127,13 @@ __device__ __forceinline__ uint4 ldgen128(u64 addr) {   // generic address: shar
 __device__ __forceinline__ void tmem_st4(u32 taddr, const uint4 v) {   // 32 lanes x 4 columns: lane = tile row
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
+}
+__device__ __forceinline__ void tmem_st16(u32 taddr, const uint4 a, const uint4 b, const uint4 c, const uint4 d) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w), "r"(c.x), "r"(c.y), "r"(c.z), "r"(c.w),
+      "r"(d.x), "r"(d.y), "r"(d.z), "r"(d.w)
+      : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // D[tmem] (+)= A[tmem] * B[smem]: the A operand (128 rows x 16 bf16 = 8 packed columns) is read from tensor memory
@@ -216,10 +225,11 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
   unsigned char* smem_al = smem_dyn + (smem_base - smem_u32(smem_dyn));
   const u32 fp_s = smem_base + (u32)a.nb * a.bstage;                                 // two footprint boxes
   unsigned char* after_fp = smem_al + (size_t)a.nb * a.bstage + 2 * (size_t)a.fp_stride;
+  const int ntab2 = a.plain ? 0 : 2 * NTAB;                                         // (no table / offsets in plain mode)
   float4* s_tabw = reinterpret_cast<float4*>(after_fp);                              // [2][NTAB]
-  u32* s_tabb = reinterpret_cast<u32*>(s_tabw + 2 * NTAB);                           // [2][NTAB]
-  float* s_om = reinterpret_cast<float*>(s_tabb + 2 * NTAB);                         // [BM][OM_CS]
-  float* s_scale = s_om + BM * OM_CS;
+  u32* s_tabb = reinterpret_cast<u32*>(s_tabw + ntab2);                              // [2][NTAB]
+  float* s_om = reinterpret_cast<float*>(s_tabb + ntab2);                            // [BM][OM_CS]
+  float* s_scale = s_om + (a.plain ? 0 : BM * OM_CS);
   float* s_shift = s_scale + a.BN;
 
   if (tid == 0) {
@@ -233,7 +243,7 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_tfull[i], 1);
-      mbar_init(&s_tempty[i], 4);
+      mbar_init(&s_tempty[i], a.plain ? 8 : 4);   // one arrival per epilogue warp (plain mode: the setup warps join)
       mbar_init(&s_tabfull[i], NSETUP_WARPS);
       mbar_init(&s_tabempty[i], NPROD_WARPS);
       mbar_init(&s_fpfull[i], 1);
@@ -265,6 +275,34 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
   const int tile_begin = (int)((long long)blockIdx.x * a.m_tiles / gridDim.x);
   const int tile_end = (int)((long long)(blockIdx.x + 1) * a.m_tiles / gridDim.x);
 
+  // TMEM -> scale/shift (bias or folded BN) -> (+residual) -> ReLU -> NHWC bf16 | NHWC fp32; warp `half` of `nhalves` per TMEM
+  // lane quarter takes every nhalves-th 16-column group
+  auto run_epilogue = [&](int half, int nhalves) {
+    const int q = warp & 3;
+    u32 t = 0;
+    for (int tile = tile_begin; tile < tile_end; ++tile, ++t) {
+      const u32 acc = a.nacc == 2 ? (t & 1u) : 0u, acc_ph = (a.nacc == 2 ? (t >> 1) : t) & 1u;
+      const TileXY tc = tile_xy(a, tile);
+      const int r = 32 * q + lane;
+      const int oy = tc.y0 + (r >> a.tw_shift), ox = tc.x0 + (r & (TW - 1));
+      const int m = (tc.n * d.Hi + oy) * d.Wi + ox;
+      mbar_wait_parked(&s_tfull[acc], acc_ph);
+      tc_fence_after();
+      const u32 taddr = tmem_base + acc * a.acc_stride + ((u32)(32 * q) << 16);
+      const int ngroups = a.BN / 16;
+      for (int g = half; g < ngroups; g += nhalves) {
+        u32 v[16];
+        tmem_ld16_nowait(taddr + (u32)(g * 16), v);
+        tmem_ld_wait();
+        const int co0 = g * 16;
+        if (oy < d.Hi && co0 < d.Co) epilogue_store(a, s_scale, s_shift, v, m, co0, co0, d.Hi * d.Wi, 0, 0);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_tempty[acc]);
+    }
+  };
+
   if (warp < NPROD_WARPS) {
     // =============================== samplers ===============================================================
     // Group g = warp / 4 takes the K blocks k = g, g + 4, ... of the CTA's stream (tile-major, slab-major, tap-minor);
@@ -279,6 +317,76 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
     const u32 ta_row = tmem_base + ((u32)((warp & 3) << 5) << 16) + a.a_col0;   // this warp's lanes, first A stage
     u32 s = (u32)grp % (u32)a.stages, ph = ((u32)grp / (u32)a.stages) & 1u, t = 0, u = 0;
     int tap = grp;
+    if (a.plain) {
+      // Plain 3x3 convolution: the A row of tap (kh, kw) is box pixel (ty + kh, tx + kw) as it is -- 8 shared-memory
+      // loads and two 16-column tcgen05.st per row and K block.  The box is read 9 times from shared memory instead of 9
+      // times from L2 (TMA im2col), and tcgen05.mma with A in tensor memory costs about half of the both-in-shared-memory
+      // form at small N.
+      const int ty = row >> a.tw_shift, tx = row & (TW - 1);
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        for (int slab = 0; slab < nslabs; ++slab, ++u) {
+          const u32 fb = u & 1u;
+          const u32 fpb = fp_s + fb * a.fp_stride;
+          mbar_wait_parked(&s_fpfull[fb], (u >> 1) & 1u);
+          if (a.kps == 3) {
+            // `tap` counts filter ROWS here: one handshake per three K blocks (the lone MMA warp spends ~500 clocks of
+            // bookkeeping per handshake, which is what bounds a convolution whose sampler does no arithmetic)
+            for (; tap < 3; tap += NG) {
+              const u32 pix = (u32)((ty + tap) * a.FW + tx);
+              const u32 fa = fpb + pix * 128u;
+              mbar_wait_parked(&s_empty[s], ph ^ 1u);
+              tc_fence_after();
+              const u32 ta = ta_row + s * (3 * A_COLS);
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw) {
+                const u32 e = (fa + (u32)kw * 128u) | (((pix + (u32)kw) & 7u) << 4);
+                const uint4 q0 = lds128(e), q1 = lds128(e ^ 16u), q2 = lds128(e ^ 32u), q3 = lds128(e ^ 48u);
+                const uint4 q4 = lds128(e ^ 64u), q5 = lds128(e ^ 80u), q6 = lds128(e ^ 96u), q7 = lds128(e ^ 112u);
+                tmem_st16(ta + (u32)(kw * A_COLS), q0, q1, q2, q3);
+                tmem_st16(ta + (u32)(kw * A_COLS) + 16u, q4, q5, q6, q7);
+              }
+              tmem_st_wait();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&s_full[s]);
+              s += (u32)NG;
+              if (s >= (u32)a.stages) {
+                s -= (u32)a.stages;
+                ph ^= 1u;
+              }
+            }
+            tap -= 3;
+          } else {
+          for (; tap < 9; tap += NG) {
+            const int kh = (tap * 11) >> 5, kw = tap - 3 * kh;     // tap / 3 for tap < 9
+            const u32 pix = (u32)((ty + kh) * a.FW + tx + kw);
+            const u32 e = (fpb + pix * 128u) | ((pix & 7u) << 4);
+            mbar_wait_parked(&s_empty[s], ph ^ 1u);
+            tc_fence_after();
+            const u32 ta = ta_row + s * A_COLS;
+            {
+              const uint4 q0 = lds128(e), q1 = lds128(e ^ 16u), q2 = lds128(e ^ 32u), q3 = lds128(e ^ 48u);
+              const uint4 q4 = lds128(e ^ 64u), q5 = lds128(e ^ 80u), q6 = lds128(e ^ 96u), q7 = lds128(e ^ 112u);
+              tmem_st16(ta, q0, q1, q2, q3);
+              tmem_st16(ta + 16u, q4, q5, q6, q7);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_full[s]);
+            s += (u32)NG;
+            if (s >= (u32)a.stages) {
+              s -= (u32)a.stages;
+              ph ^= 1u;
+            }
+          }
+          tap -= 9;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_fpempty[fb]);
+        }
+      }
+    } else
     for (int tile = tile_begin; tile < tile_end; ++tile, ++t) {
       const u32 tb = t & 1u;
       mbar_wait_parked(&s_tabfull[tb], (t >> 1) & 1u);
@@ -372,6 +480,9 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
     // item per thread and step, the buffer refilled after the table was written: a serial chain of load latency +
     // lone-warp arithmetic of ~10000 clocks per tile, which bounded the whole kernel.)
     const int r = tid - W_SETUP0 * 32;                 // tile row 0..127
+    if (a.plain) {
+      run_epilogue(1, 2);   // nothing to set up: these warps (TMEM lane quarters 0..3) take every other column group
+    } else {
     if (r == 0 && tile_begin < tile_end) {
       const TileXY tc = tile_xy(a, tile_begin);
       mbar_expect_tx(&s_omfull, BM * OM_CS * 4u);
@@ -457,69 +568,67 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_tabfull[tb]);
     }
+    }
   } else if (warp == W_MMA) {
     // =============================== MMA issuer ==============================================================
-    u32 s = 0, ph = 0, t = 0, sb = 0, phb = 0;
+    // A lone warp executes ~1 dependent instruction per 5-8 clocks, and in plain mode this loop is what bounds the kernel
+    // (first version: ~120 instructions per K block = 650 clocks): barrier addresses, the weight-tile descriptor and the
+    // A-stage address are loop-carried state advanced by adds, everything else is hoisted.
+    const u32 full0 = smem_u32(&s_full[0]), empty0 = smem_u32(&s_empty[0]);
+    const u32 bfull0 = smem_u32(&s_bfull[0]), bempty0 = smem_u32(&s_bempty[0]);
+    const u32 tfull0 = smem_u32(&s_tfull[0]), tempty0 = smem_u32(&s_tempty[0]);
+    const u32 s_wrap = (u32)a.stages * 8u, sb_wrap = (u32)(a.b_resident ? a.nkb : a.nb) * 8u;
+    const bool resident = a.b_resident != 0;
+    const u32 idesc = a.idesc, ta0 = tmem_base + a.a_col0, acc_stride = a.acc_stride;
+    const bool two_acc = a.nacc == 2;
+    const int nkb = a.nkb, kps = a.kps;
     const u64 db0 = make_sdesc(smem_base, 16, 1024, 2);
-    const u32 bstage16 = a.bstage >> 4;
+    const u64 bstage16 = (u64)(a.bstage >> 4);
+    u32 s8 = 0, ph = 0, sb8 = 0, phb = 0, ta = ta0, t = 0;
+    u64 db = db0;
     for (int tile = tile_begin; tile < tile_end; ++tile, ++t) {
-      const u32 acc = a.nacc == 2 ? (t & 1u) : 0u, acc_ph = (a.nacc == 2 ? (t >> 1) : t) & 1u;
-      mbar_wait_parked(&s_tempty[acc], acc_ph ^ 1u);
+      const u32 acc = two_acc ? (t & 1u) : 0u, acc_ph = (two_acc ? (t >> 1) : t) & 1u;
+      mbar_wait_parked_a(tempty0 + acc * 8u, acc_ph ^ 1u);
       tc_fence_after();
-      const u32 tmem_d = tmem_base + acc * a.acc_stride;
+      const u32 tmem_d = tmem_base + acc * acc_stride;
+      const bool wait_b = !resident || t == 0;
       u32 accumulate = 0;
-      for (int kb = 0; kb < a.nkb; ++kb) {
-        if (!a.b_resident || t == 0) mbar_wait_parked(&s_bfull[sb], phb);   // the weight tile (prefetched far ahead)
-        mbar_wait_parked(&s_full[s], ph);                                   // the sampled rows
-        tc_fence_after();
-        if (elect_one()) {
-          const u64 db = db0 + (u64)(sb * bstage16);
-          const u32 ta = tmem_base + a.a_col0 + s * A_COLS;
+      for (int kb = 0; kb < nkb; kb += kps) {
+        mbar_wait_parked_a(full0 + s8, ph);                  // the sampled rows of kps K blocks
+        for (int j = 0; j < kps; ++j) {
+          if (wait_b) mbar_wait_parked_a(bfull0 + sb8, phb);   // the weight tile (prefetched far ahead)
+          tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)   // K = 16: 8 packed columns of A, +32 bytes of B inside the swizzle atom
-            if (!(FP_DBG(a) & 32)) umma_bf16_ts(tmem_d, ta + (u32)(8 * kk), db + (u64)(2 * kk), a.idesc, kk == 0 ? accumulate : 1u);
-          umma_commit(&s_empty[s]);
-          if (!a.b_resident) umma_commit(&s_bempty[sb]);
+            for (int kk = 0; kk < 4; ++kk)   // K = 16: 8 packed columns of A, +32 bytes of B inside the swizzle atom
+              if (!(FP_DBG(a) & 32)) umma_bf16_ts(tmem_d, ta + (u32)(8 * kk), db + (u64)(2 * kk), idesc, kk == 0 ? accumulate : 1u);
+            if (j == kps - 1) umma_commit_a(empty0 + s8);
+            if (!resident) umma_commit_a(bempty0 + sb8);
+          }
+          __syncwarp();
+          accumulate = 1;
+          ta += A_COLS;
+          sb8 += 8u;
+          db += bstage16;
+          if (sb8 == sb_wrap) {
+            sb8 = 0;
+            db = db0;
+            phb ^= 1u;
+          }
         }
-        __syncwarp();
-        accumulate = 1;
-        if (++s == (u32)a.stages) {
-          s = 0;
+        s8 += 8u;
+        if (s8 == s_wrap) {
+          s8 = 0;
+          ta = ta0;
           ph ^= 1u;
         }
-        if (++sb == (u32)a.nb || (a.b_resident && sb == (u32)a.nkb)) {
-          sb = 0;
-          phb ^= 1u;
-        }
       }
-      if (elect_one()) umma_commit(&s_tfull[acc]);
+      if (elect_one()) umma_commit_a(tfull0 + acc * 8u);
       __syncwarp();
     }
   } else if (warp < W_LOAD) {
     // =============================== epilogue ================================================================
-    const int q = warp & 3;
-    u32 t = 0;
-    for (int tile = tile_begin; tile < tile_end; ++tile, ++t) {
-      const u32 acc = a.nacc == 2 ? (t & 1u) : 0u, acc_ph = (a.nacc == 2 ? (t >> 1) : t) & 1u;
-      const TileXY tc = tile_xy(a, tile);
-      const int r = 32 * q + lane;
-      const int oy = tc.y0 + (r >> a.tw_shift), ox = tc.x0 + (r & (TW - 1));
-      const int m = (tc.n * d.Hi + oy) * d.Wi + ox;
-      mbar_wait_parked(&s_tfull[acc], acc_ph);
-      tc_fence_after();
-      const u32 taddr = tmem_base + acc * a.acc_stride + ((u32)(32 * q) << 16);
-      const int ngroups = a.BN / 16;
-      for (int g = 0; g < ngroups; ++g) {
-        u32 v[16];
-        tmem_ld16_nowait(taddr + (u32)(g * 16), v);
-        tmem_ld_wait();
-        const int co0 = g * 16;
-        if (oy < d.Hi && co0 < d.Co) epilogue_store(a, s_scale, s_shift, v, m, co0, co0, d.Hi * d.Wi, 0, 0);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_tempty[acc]);
-    }
+    run_epilogue(0, a.plain ? 2 : 1);
   } else if (warp == W_LOAD) {
     // =============================== loader: one box per (tile, slab), two in flight ===========================
     // Boxes and weight tiles share the SM's TMA queue; each is requested as early as its slot allows (a weight tile
@@ -580,7 +689,7 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 struct Plan {
-  int tw_shift, R, stages, nb, BN;
+  int tw_shift, R, stages, nb, BN, kps;
   u32 bstage, fp_bytes, fp_stride;
   size_t smem;
 };
@@ -588,7 +697,7 @@ struct Plan {
 // Shared memory: tables + offset staging (fixed), two boxes of reach R, nb weight-tile slots.  All 9 * Ci/64 weight tiles
 // resident (no reloads at all) is worth one pixel of reach; otherwise >= 4 slots, then the largest reach.  The A ring lives
 // in the tensor-memory columns the two accumulators leave free (>= NG stages: a group must not lap the ring).
-bool make_plan(const cnb_conv_desc* d, Plan* p) {
+bool make_plan(const cnb_conv_desc* d, Plan* p, bool plain = false) {
   static const int env_r = [] { const char* e = getenv("CNB_DCN_REACH"); return e ? atoi(e) : 0; }();
   static const int env_stages = [] { const char* e = getenv("CNB_DCN_STAGES"); return e ? atoi(e) : 0; }();
   static const int env_nb = [] { const char* e = getenv("CNB_DCN_NB"); return e ? atoi(e) : 0; }();
@@ -597,17 +706,25 @@ bool make_plan(const cnb_conv_desc* d, Plan* p) {
   p->BN = round_up(d->Co, 16);
   p->bstage = ((u32)p->BN * 128u + 1023u) & ~1023u;
   const int nkb = 9 * (d->Ci / 64);
-  int st = (512 - (p->BN > 128 ? 1 : 2) * round_up(p->BN, 32)) / A_COLS;
+  // K blocks per A stage: in plain mode with N <= 64 a sampler group fills a whole filter row per handshake
+  const int kps = (plain && p->BN <= 64) ? 3 : 1;
+  p->kps = kps;
+  int st = (512 - (p->BN > 128 ? 1 : 2) * round_up(p->BN, 32)) / (A_COLS * kps);
   if (st > MAX_STAGES) st = MAX_STAGES;
   if (env_stages > 0 && st > env_stages) st = env_stages;
   if (st < NG) return false;
   p->stages = st;
-  const size_t fixed = (size_t)2 * NTAB * (sizeof(float4) + sizeof(u32)) + (size_t)BM * OM_CS * 4 + (size_t)p->BN * 8 + 1024;
+  const size_t fixed = (plain ? 0 : (size_t)2 * NTAB * (sizeof(float4) + sizeof(u32)) + (size_t)BM * OM_CS * 4) +
+                       (size_t)p->BN * 8 + 1024;
   const size_t budget = 226 * 1024;
-  static const int pref[][2] = {{3, -1}, {2, -1}, {3, 4}, {2, 4}, {2, 2}, {1, 2}};   // (R, minimum slots; -1 = all tiles resident)
-  for (const auto& c : pref) {
-    const int R = env_r > 0 ? env_r : c[0];
-    const int FW = TW + 2 * R + 3, FH = TH + 2 * R + 3;
+  static const int pref[6][2] = {{3, -1}, {2, -1}, {3, 4}, {2, 4}, {2, 2}, {1, 2}};   // (R, minimum slots; -1 = all tiles resident)
+  static const int pref_plain[1][2] = {{0, 2}};
+  const int (*cands)[2] = plain ? pref_plain : pref;
+  const int ncand = plain ? 1 : 6;
+  for (int ci = 0; ci < ncand; ++ci) {
+    const int* c = cands[ci];
+    const int R = plain ? 0 : (env_r > 0 ? env_r : c[0]);
+    const int FW = plain ? TW + 2 : TW + 2 * R + 3, FH = plain ? TH + 2 : TH + 2 * R + 3;
     const u32 fpb = (u32)FW * FH * 128u;
     const u32 fps = (fpb + 1023u) & ~1023u;
     if (fixed + 2 * (size_t)fps + 2 * (size_t)p->bstage > budget) continue;
@@ -637,15 +754,15 @@ bool dcn_fp_supported(const cnb_conv_desc* d, int om_cstride) {
          d->x_cstride % 8 == 0 && d->x_coffset % 8 == 0 && make_plan(d, &p);
 }
 
-int dcn_fp_run(const cnb_conv_desc* d, const void* x, const float* om, int om_cstride, const void* wpk,
-               const float* scale, const float* shift, void* y, cudaStream_t st) {
+static int fp_run(const cnb_conv_desc* d, const void* x, const float* om, const void* wpk, const float* scale,
+                  const float* shift, const void* res, void* y, cudaStream_t st, bool plain) {
   TmaDriver& drv = tma_driver();
   if (!drv.ok) {
     set_error("dcnv2: cuTensorMapEncodeTiled entry point unavailable (driver too old?)");
     return CNB_ERR_CUDA;
   }
   Plan p;
-  if (!make_plan(d, &p)) {
+  if (!make_plan(d, &p, plain)) {
     set_error("dcnv2: no shared-memory plan for Co=%d", d->Co);
     return CNB_ERR_INVALID;
   }
@@ -655,16 +772,17 @@ int dcn_fp_run(const cnb_conv_desc* d, const void* x, const float* om, int om_cs
   a.om = om;
   a.scale = scale;
   a.shift = shift;
-  a.res = nullptr;
+  a.res = (const __nv_bfloat16*)res;
   a.y = y;
+  a.plain = plain ? 1 : 0;
   a.tw_shift = p.tw_shift;
   const int TW = 1 << p.tw_shift, TH = BM >> p.tw_shift;
   a.tiles_x = d->Wi / TW;
   a.tiles_y = (d->Hi + TH - 1) / TH;
   a.m_tiles = d->B * a.tiles_x * a.tiles_y;
   a.R = p.R;
-  a.FW = TW + 2 * p.R + 3;
-  a.FH = TH + 2 * p.R + 3;
+  a.FW = plain ? TW + 2 : TW + 2 * p.R + 3;
+  a.FH = plain ? TH + 2 : TH + 2 * p.R + 3;
   a.fp_bytes = p.fp_bytes;
   a.fp_stride = p.fp_stride;
   a.BN = p.BN;
@@ -672,6 +790,7 @@ int dcn_fp_run(const cnb_conv_desc* d, const void* x, const float* om, int om_cs
   a.b_bytes = (u32)a.BN * 128u;
   a.bstage = p.bstage;
   a.stages = p.stages;
+  a.kps = p.kps;
   a.nb = p.nb;
   a.b_resident = p.nb >= a.nkb ? 1 : 0;
   a.acc_stride = (u32)round_up(a.BN, 32);
@@ -711,7 +830,9 @@ int dcn_fp_run(const cnb_conv_desc* d, const void* x, const float* om, int om_cs
       return CNB_ERR_CUDA;
     }
   }
-  {
+  if (plain) {
+    tmO = tmX;   // unused
+  } else {
     // the offset/mask map as {32 floats, W, H, N}: one box = the tile's TW x TH pixels, 128 bytes each, 128-byte swizzle;
     // rows below the image are zero-filled (their table entries are never used)
     cuuint64_t dims[4] = {(cuuint64_t)OM_CS, (cuuint64_t)d->Wi, (cuuint64_t)d->Hi, (cuuint64_t)d->B};
@@ -742,6 +863,32 @@ int dcn_fp_run(const cnb_conv_desc* d, const void* x, const float* om, int om_cs
     CNB_CUDA(launch_pdl(dcn_fp_kernel<false>, dim3(grid), dim3(NTHREADS), p.smem, st, tmB, tmX, tmO, a));
   CNB_LAUNCH_CHECK();
   return CNB_OK;
+}
+
+int dcn_fp_run(const cnb_conv_desc* d, const void* x, const float* om, int om_cstride, const void* wpk,
+               const float* scale, const float* shift, void* y, cudaStream_t st) {
+  (void)om_cstride;
+  return fp_run(d, x, om, wpk, scale, shift, nullptr, y, st, false);
+}
+
+// Plain 3x3 / stride 1 / pad 1 convolutions with Ci % 64 == 0 and N <= 128 through the same kernel (`plain` mode: input
+// box in shared memory read 9 times by the sampler threads, A operand in tensor memory).  Opt-in (CNB_CONV_FP=1), parity
+// tested, NOT the default: measured against conv_rows / conv_tma (B=32, us) 64->64@128x128 66 vs 54, 64->27@128x128 64 vs 59,
+// 128->27@64x64 33 vs 34, 128->64@64x64 34 vs 41 -- every small-N tcgen05 GEMM of this library lands at 440-550 clocks per
+// (128 rows x K=64) whether A comes from shared memory rows, TMA im2col tiles or tensor memory (fewer handshakes per K
+// block, a leaner issue loop, partial accumulators against the dependent-accumulator latency: each moved it by < 15 %).
+bool conv_fp_supported(const cnb_conv_desc* d) {
+  static const bool on = [] { const char* e = getenv("CNB_CONV_FP"); return e && e[0] == '1'; }();
+  Plan p;
+  return on && d->KH == 3 && d->KW == 3 && d->stride == 1 && d->pad == 1 && d->dil == 1 && d->pad_w1 == 0 &&
+         (d->w_kw == 0 || d->w_kw == 3) && d->Ho == d->Hi && d->Wo == d->Wi && d->Ci % 64 == 0 && round_up(d->Co, 16) <= 128 &&
+         d->Wi % 8 == 0 && d->out_nchw_f32 != 1 && d->x_cstride % 8 == 0 && d->x_coffset % 8 == 0 &&
+         (long long)d->B * d->Hi * d->Wi < (1ll << 29) && make_plan(d, &p, true);
+}
+
+int conv_fp_run(const cnb_conv_desc* d, const void* x, const void* wpk, const float* scale, const float* shift,
+                const void* res, void* y, cudaStream_t st) {
+  return fp_run(d, x, nullptr, wpk, scale, shift, res, y, st, true);
 }
 
 }  // namespace cnb

@@ -35,6 +35,9 @@ __device__ __forceinline__ void umma_commit(void* bar) {
                    smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void umma_commit_a(u32 bar_addr) {   // ... on a precomputed shared-memory address
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+}
 // the same, arriving on the barrier at this shared-memory offset in EVERY CTA of the cluster named by cta_mask
 __device__ __forceinline__ void umma_commit_mc(void* bar, unsigned short cta_mask) {
   asm volatile(

@@ -10,6 +10,7 @@ from centernet_pytorch_lightning_b200 import ops  # noqa: E402
 CASES = {  # name: (Ci, Co, H, k)
     "c256": (256, 256, 32, 3), "c128": (128, 128, 64, 3), "c512": (512, 512, 16, 3), "head": (64, 768, 128, 3),
     "off128": (128, 27, 64, 3), "off256": (256, 27, 32, 3), "root448": (448, 128, 64, 1), "c64": (64, 64, 64, 3),
+    "c64_128": (64, 64, 128, 3), "off64": (64, 27, 128, 3), "off512": (512, 27, 16, 3), "c128_64o": (128, 64, 64, 3),
 }
 dev = torch.device("cuda:0")
 B = 32
@@ -30,5 +31,5 @@ for name in (sys.argv[1:] or list(CASES)):
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / 10 * 1e3
     tf = 2.0 * B * hw * hw * co * ci * k * k / us * 1e-6
-    kblocks = (B * hw * hw / 128) * ((co + 255) // 256) * (ci * k * k / 64) / 148
+    kblocks = (B * hw * hw / 128) * ((co + 255) // 256) * (max(ci, 64) * k * k / 64) / 148
     print(f"{name:8s} {us:8.1f} us  {tf:7.1f} TF/s  {us * 1e-6 * 1.965e9 / kblocks:7.0f} clk per K block per SM")
