@@ -242,7 +242,7 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
       mbar_init(&s_bempty[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_tfull[i], 1);
+      mbar_init(&s_tfull[i], a.plain ? NG : 1);     // plain mode: one commit per issuing group
       mbar_init(&s_tempty[i], a.plain ? 8 : 4);   // one arrival per epilogue warp (plain mode: the setup warps join)
       mbar_init(&s_tabfull[i], NSETUP_WARPS);
       mbar_init(&s_tabempty[i], NPROD_WARPS);
@@ -280,6 +280,17 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
   auto run_epilogue = [&](int half, int nhalves) {
     const int q = warp & 3;
     u32 t = 0;
+    if (a.plain) {   // every MMA of this mode accumulates: hand the accumulators over zeroed
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      for (int i = 0; i < a.nacc; ++i) {
+        for (int g = half; g < a.BN / 16; g += nhalves)
+          tmem_st16(tmem_base + (u32)i * a.acc_stride + ((u32)(32 * q) << 16) + (u32)(g * 16), z, z, z, z);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_tempty[i]);
+      }
+    }
     for (int tile = tile_begin; tile < tile_end; ++tile, ++t) {
       const u32 acc = a.nacc == 2 ? (t & 1u) : 0u, acc_ph = (a.nacc == 2 ? (t >> 1) : t) & 1u;
       const TileXY tc = tile_xy(a, tile);
@@ -295,8 +306,13 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
         tmem_ld16_nowait(taddr + (u32)(g * 16), v);
         tmem_ld_wait();
         const int co0 = g * 16;
+        if (a.plain) {
+          const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+          tmem_st16(taddr + (u32)(g * 16), z, z, z, z);
+        }
         if (oy < d.Hi && co0 < d.Co) epilogue_store(a, s_scale, s_shift, v, m, co0, co0, d.Hi * d.Wi, 0, 0);
       }
+      if (a.plain) tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_tempty[acc]);
@@ -319,49 +335,33 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
     int tap = grp;
     if (a.plain) {
       // Plain 3x3 convolution: the A row of tap (kh, kw) is box pixel (ty + kh, tx + kw) as it is -- 8 shared-memory
-      // loads and two 16-column tcgen05.st per row and K block.  The box is read 9 times from shared memory instead of 9
-      // times from L2 (TMA im2col), and tcgen05.mma with A in tensor memory costs about half of the both-in-shared-memory
-      // form at small N.
+      // loads and two 16-column tcgen05.st per row and K block; the box is read 9 times from shared memory instead of 9
+      // times from L2 (TMA im2col).  With no arithmetic in the sampler the kernel is bound by the lone MMA warp's
+      // bookkeeping (~500 clocks per K block, measured), so in this mode there is none: the four warps of a group meet
+      // at a named barrier and the group's first warp issues the K block's MMAs itself -- four issuers in parallel.
+      // Their MMAs may reach the tensor core in any order, so every one of them accumulates (the epilogue hands each
+      // accumulator back ZEROED instead of the first MMA of a tile overwriting it).
       const int ty = row >> a.tw_shift, tx = row & (TW - 1);
-      for (int tile = tile_begin; tile < tile_end; ++tile) {
+      const bool issuer = (warp & 3) == 0;
+      const u32 bar_id = 2u + (u32)grp;                    // named barriers 2..5 (1: setup warps in DCN mode)
+      const u64 db0 = make_sdesc(smem_base, 16, 1024, 2);
+      const u32 bstage16 = a.bstage >> 4;
+      const bool two_acc = a.nacc == 2;
+      const u32 wrapb = a.b_resident ? (u32)a.nkb : (u32)a.nb;
+      u32 sb = (u32)grp % wrapb, useb = (u32)grp / wrapb;   // weight-tile slot of this group's next K block, and its use count
+      for (int tile = tile_begin; tile < tile_end; ++tile, ++t) {
+        const u32 acc = two_acc ? (t & 1u) : 0u, acc_ph = (two_acc ? (t >> 1) : t) & 1u;
+        const u32 tmem_d = tmem_base + acc * a.acc_stride;
+        bool first = true;                                 // first K block of this group in this tile
         for (int slab = 0; slab < nslabs; ++slab, ++u) {
           const u32 fb = u & 1u;
           const u32 fpb = fp_s + fb * a.fp_stride;
           mbar_wait_parked(&s_fpfull[fb], (u >> 1) & 1u);
-          if (a.kps == 3) {
-            // `tap` counts filter ROWS here: one handshake per three K blocks (the lone MMA warp spends ~500 clocks of
-            // bookkeeping per handshake, which is what bounds a convolution whose sampler does no arithmetic)
-            for (; tap < 3; tap += NG) {
-              const u32 pix = (u32)((ty + tap) * a.FW + tx);
-              const u32 fa = fpb + pix * 128u;
-              mbar_wait_parked(&s_empty[s], ph ^ 1u);
-              tc_fence_after();
-              const u32 ta = ta_row + s * (3 * A_COLS);
-#pragma unroll
-              for (int kw = 0; kw < 3; ++kw) {
-                const u32 e = (fa + (u32)kw * 128u) | (((pix + (u32)kw) & 7u) << 4);
-                const uint4 q0 = lds128(e), q1 = lds128(e ^ 16u), q2 = lds128(e ^ 32u), q3 = lds128(e ^ 48u);
-                const uint4 q4 = lds128(e ^ 64u), q5 = lds128(e ^ 80u), q6 = lds128(e ^ 96u), q7 = lds128(e ^ 112u);
-                tmem_st16(ta + (u32)(kw * A_COLS), q0, q1, q2, q3);
-                tmem_st16(ta + (u32)(kw * A_COLS) + 16u, q4, q5, q6, q7);
-              }
-              tmem_st_wait();
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&s_full[s]);
-              s += (u32)NG;
-              if (s >= (u32)a.stages) {
-                s -= (u32)a.stages;
-                ph ^= 1u;
-              }
-            }
-            tap -= 3;
-          } else {
           for (; tap < 9; tap += NG) {
             const int kh = (tap * 11) >> 5, kw = tap - 3 * kh;     // tap / 3 for tap < 9
             const u32 pix = (u32)((ty + kh) * a.FW + tx + kw);
             const u32 e = (fpb + pix * 128u) | ((pix & 7u) << 4);
-            mbar_wait_parked(&s_empty[s], ph ^ 1u);
+            mbar_wait_parked(&s_empty[s], ph ^ 1u);        // the MMAs that read this A stage last time have completed
             tc_fence_after();
             const u32 ta = ta_row + s * A_COLS;
             {
@@ -372,16 +372,36 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
             }
             tmem_st_wait();
             tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_full[s]);
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // the group's 128 rows are in tensor memory
+            if (issuer) {
+              if (first) mbar_wait_parked(&s_tempty[acc], acc_ph);       // the accumulator is drained and zeroed
+              if (!a.b_resident || useb == 0) mbar_wait_parked(&s_bfull[sb], useb & 1u);
+              tc_fence_after();
+              const bool last = slab == nslabs - 1 && tap + NG >= 9;     // this group's last K block of the tile
+              if (elect_one()) {
+                const u64 db = db0 + (u64)(sb * bstage16);
+                const u32 tam = tmem_base + a.a_col0 + s * A_COLS;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) umma_bf16_ts(tmem_d, tam + (u32)(8 * kk), db + (u64)(2 * kk), a.idesc, 1u);
+                umma_commit(&s_empty[s]);
+                if (!a.b_resident) umma_commit(&s_bempty[sb]);
+                if (last) umma_commit(&s_tfull[acc]);
+              }
+              __syncwarp();
+            }
+            first = false;
             s += (u32)NG;
             if (s >= (u32)a.stages) {
               s -= (u32)a.stages;
               ph ^= 1u;
             }
+            sb += (u32)NG;
+            while (sb >= wrapb) {
+              sb -= wrapb;
+              ++useb;
+            }
           }
           tap -= 9;
-          }
           __syncwarp();
           if (lane == 0) mbar_arrive(&s_fpempty[fb]);
         }
@@ -574,6 +594,7 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
     // A lone warp executes ~1 dependent instruction per 5-8 clocks, and in plain mode this loop is what bounds the kernel
     // (first version: ~120 instructions per K block = 650 clocks): barrier addresses, the weight-tile descriptor and the
     // A-stage address are loop-carried state advanced by adds, everything else is hoisted.
+    if (!a.plain) {   // (plain mode: the sampler groups issue their own MMAs)
     const u32 full0 = smem_u32(&s_full[0]), empty0 = smem_u32(&s_empty[0]);
     const u32 bfull0 = smem_u32(&s_bfull[0]), bempty0 = smem_u32(&s_bempty[0]);
     const u32 tfull0 = smem_u32(&s_tfull[0]), tempty0 = smem_u32(&s_tempty[0]);
@@ -625,6 +646,7 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
       }
       if (elect_one()) umma_commit_a(tfull0 + acc * 8u);
       __syncwarp();
+    }
     }
   } else if (warp < W_LOAD) {
     // =============================== epilogue ================================================================
@@ -707,7 +729,7 @@ bool make_plan(const cnb_conv_desc* d, Plan* p, bool plain = false) {
   p->bstage = ((u32)p->BN * 128u + 1023u) & ~1023u;
   const int nkb = 9 * (d->Ci / 64);
   // K blocks per A stage: in plain mode with N <= 64 a sampler group fills a whole filter row per handshake
-  const int kps = (plain && p->BN <= 64) ? 3 : 1;
+  const int kps = 1;
   p->kps = kps;
   int st = (512 - (p->BN > 128 ? 1 : 2) * round_up(p->BN, 32)) / (A_COLS * kps);
   if (st > MAX_STAGES) st = MAX_STAGES;
@@ -872,18 +894,24 @@ int dcn_fp_run(const cnb_conv_desc* d, const void* x, const float* om, int om_cs
 }
 
 // Plain 3x3 / stride 1 / pad 1 convolutions with Ci % 64 == 0 and N <= 128 through the same kernel (`plain` mode: input
-// box in shared memory read 9 times by the sampler threads, A operand in tensor memory).  Opt-in (CNB_CONV_FP=1), parity
-// tested, NOT the default: measured against conv_rows / conv_tma (B=32, us) 64->64@128x128 66 vs 54, 64->27@128x128 64 vs 59,
-// 128->27@64x64 33 vs 34, 128->64@64x64 34 vs 41 -- every small-N tcgen05 GEMM of this library lands at 440-550 clocks per
-// (128 rows x K=64) whether A comes from shared memory rows, TMA im2col tiles or tensor memory (fewer handshakes per K
-// block, a leaner issue loop, partial accumulators against the dependent-accumulator latency: each moved it by < 15 %).
+// box in shared memory read 9 times by the sampler threads, A operand in tensor memory, the sampler groups issue their own
+// MMAs).  Measured against conv_rows / conv_tma (B=32, us): 128->27@64x64 28.8 vs 35.3, 128->64@64x64 28.6 vs 40.6,
+// 64->64@64x64 23.8 vs 25.7; 64->64@128x128 57.9 vs 53.7, 64->27@128x128 60.5 vs 58.3, 256->27@32x32 26.4 vs 23.4 -- every
+// small-N tcgen05 GEMM of this library lands at 420-480 clocks per (128 rows x K = 64), i.e. ~112 clocks per M = 128 / K = 16
+// MMA whatever N <= 64 is and wherever A comes from, so only the layers whose im2col traffic or tile count hurt the other
+// kernels gain.  Default: Ci >= 128, N <= 64, at least 4 tiles per SM.  CNB_CONV_FP=1 forces it for every eligible
+// geometry (the parity tests run that), =0 disables it.
 bool conv_fp_supported(const cnb_conv_desc* d) {
-  static const bool on = [] { const char* e = getenv("CNB_CONV_FP"); return e && e[0] == '1'; }();
+  static const int env = [] { const char* e = getenv("CNB_CONV_FP"); return e ? atoi(e) : -1; }();
+  if (env == 0) return false;
   Plan p;
-  return on && d->KH == 3 && d->KW == 3 && d->stride == 1 && d->pad == 1 && d->dil == 1 && d->pad_w1 == 0 &&
-         (d->w_kw == 0 || d->w_kw == 3) && d->Ho == d->Hi && d->Wo == d->Wi && d->Ci % 64 == 0 && round_up(d->Co, 16) <= 128 &&
-         d->Wi % 8 == 0 && d->out_nchw_f32 != 1 && d->x_cstride % 8 == 0 && d->x_coffset % 8 == 0 &&
-         (long long)d->B * d->Hi * d->Wi < (1ll << 29) && make_plan(d, &p, true);
+  const bool ok = d->KH == 3 && d->KW == 3 && d->stride == 1 && d->pad == 1 && d->dil == 1 && d->pad_w1 == 0 &&
+                  (d->w_kw == 0 || d->w_kw == 3) && d->Ho == d->Hi && d->Wo == d->Wi && d->Ci % 64 == 0 &&
+                  round_up(d->Co, 16) <= 128 && d->Wi % 8 == 0 && d->out_nchw_f32 != 1 && d->x_cstride % 8 == 0 &&
+                  d->x_coffset % 8 == 0 && (long long)d->B * d->Hi * d->Wi < (1ll << 29) && make_plan(d, &p, true);
+  if (!ok || env == 1) return ok;
+  const long long m_tiles = ((long long)d->B * d->Hi * d->Wi + BM - 1) / BM;
+  return d->Ci >= 128 && round_up(d->Co, 16) <= 64 && m_tiles >= 4LL * sm_count();
 }
 
 int conv_fp_run(const cnb_conv_desc* d, const void* x, const void* wpk, const float* scale, const float* shift,

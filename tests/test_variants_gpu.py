@@ -19,7 +19,8 @@ VARIANTS = [
     ({"CNB_CONV_ROWS": "0"}, "test_conv_matches_torch"),
     ({"CNB_CONV_PAIR": "1"}, "test_conv_matches_torch or test_conv_concat_slices or head"),   # CTA pairs for every eligible N
     ({"CNB_CONV_PAIR": "0"}, "test_conv_matches_torch or test_conv_concat_slices"),
-    ({"CNB_CONV_FP": "1"}, "test_conv_matches_torch or test_conv_concat_slices or dcn_module"),   # 3x3 convs through the footprint kernel
+    ({"CNB_CONV_FP": "1"}, "test_conv_matches_torch or test_conv_concat_slices or dcn_module"),   # every eligible 3x3 conv through the footprint kernel
+    ({"CNB_CONV_FP": "0"}, "test_conv_matches_torch or dcn_module"),
     ({"CNB_DCN_BLEND": "bf16"}, "dcn"),
     ({"CNB_DCN_GROUPS": "1"}, "dcn"),
     ({"CNB_DCN_GROUPS": "4"}, "dcn"),
