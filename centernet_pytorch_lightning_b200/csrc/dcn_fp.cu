@@ -147,12 +147,32 @@ __device__ __forceinline__ void umma_bf16_ts(u32 tmem_d, u32 tmem_a, u64 desc_b,
 }
 
 // 4-corner blend of one 16-byte chunk (8 channels): fp32 (packed FFMA2), one rounding to bf16
-template <bool BLEND_BF16>
+template <int BLEND_BF16>   // 0: fp32 blend; 1: bf16x2 blend; 2: fp32 accumulation of bf16 x bf16(weight) products
 __device__ __forceinline__ uint4 blend4(const float4 w, const uint4 c0, const uint4 c1, const uint4 c2, const uint4 c3) {
   const u32 q0[4] = {c0.x, c0.y, c0.z, c0.w}, q1[4] = {c1.x, c1.y, c1.z, c1.w}, q2[4] = {c2.x, c2.y, c2.z, c2.w},
             q3[4] = {c3.x, c3.y, c3.z, c3.w};
   u32 o[4];
-  if constexpr (BLEND_BF16) {
+  if constexpr (BLEND_BF16 == 2) {
+    // Mixed-precision FMA (SASS FHFMA.BF16: bf16 x bf16 + f32 -> f32, operand halves selected for free): no unpack
+    // instructions at all -- 4 per element instead of 6.  The products are exact and the sums fp32; the only difference
+    // to the fp32 blend is that the four bilinear weights are rounded to bf16 (relative 2^-9, i.e. a sampling-position
+    // error below 0.002 pixel).
+    const unsigned short w0 = __bfloat16_as_ushort(__float2bfloat16_rn(w.x)), w1 = __bfloat16_as_ushort(__float2bfloat16_rn(w.y)),
+                         w2 = __bfloat16_as_ushort(__float2bfloat16_rn(w.z)), w3 = __bfloat16_as_ushort(__float2bfloat16_rn(w.w));
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float lo, hi;
+      asm("{\n\t.reg .b16 a0, a1, b0, b1, c0, c1, d0, d1;\n\t"
+          "mov.b32 {a0, a1}, %2;\n\tmov.b32 {b0, b1}, %3;\n\tmov.b32 {c0, c1}, %4;\n\tmov.b32 {d0, d1}, %5;\n\t"
+          "fma.rn.f32.bf16 %0, a0, %6, 0f00000000;\n\tfma.rn.f32.bf16 %1, a1, %6, 0f00000000;\n\t"
+          "fma.rn.f32.bf16 %0, b0, %7, %0;\n\tfma.rn.f32.bf16 %1, b1, %7, %1;\n\t"
+          "fma.rn.f32.bf16 %0, c0, %8, %0;\n\tfma.rn.f32.bf16 %1, c1, %8, %1;\n\t"
+          "fma.rn.f32.bf16 %0, d0, %9, %0;\n\tfma.rn.f32.bf16 %1, d1, %9, %1;\n\t}"
+          : "=&f"(lo), "=&f"(hi)
+          : "r"(q0[e]), "r"(q1[e]), "r"(q2[e]), "r"(q3[e]), "h"(w0), "h"(w1), "h"(w2), "h"(w3));
+      o[e] = pack_bf16x2(lo, hi);
+    }
+  } else if constexpr (BLEND_BF16 == 1) {
     const u32 wh0 = pack_bf16x2(w.x, w.x), wh1 = pack_bf16x2(w.y, w.y), wh2 = pack_bf16x2(w.z, w.z),
               wh3 = pack_bf16x2(w.w, w.w);
 #pragma unroll
@@ -201,7 +221,7 @@ __device__ __forceinline__ TileXY tile_xy(const FArgs& a, int tile) {
 #define FP_DBG(a) 0
 #endif
 
-template <bool BLEND_BF16>
+template <int BLEND_BF16>
 __global__ void __launch_bounds__(NTHREADS, 1)
 dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmX,
               const __grid_constant__ CUtensorMap tmO, const FArgs a) {
@@ -343,7 +363,6 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
       // accumulator back ZEROED instead of the first MMA of a tile overwriting it).
       const int ty = row >> a.tw_shift, tx = row & (TW - 1);
       const bool issuer = (warp & 3) == 0;
-      const u32 bar_id = 2u + (u32)grp;                    // named barriers 2..5 (1: setup warps in DCN mode)
       const u64 db0 = make_sdesc(smem_base, 16, 1024, 2);
       const u32 bstage16 = a.bstage >> 4;
       const bool two_acc = a.nacc == 2;
@@ -372,7 +391,12 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
             }
             tmem_st_wait();
             tc_fence_before();
-            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // the group's 128 rows are in tensor memory
+            // the group's 128 rows are in tensor memory (named barrier 2 + group, as an immediate: a register id makes
+            // ptxas reserve all 16 barriers)
+            if (grp == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
+            else if (grp == 1) asm volatile("bar.sync 3, 128;" ::: "memory");
+            else if (grp == 2) asm volatile("bar.sync 4, 128;" ::: "memory");
+            else asm volatile("bar.sync 5, 128;" ::: "memory");
             if (issuer) {
               if (first) mbar_wait_parked(&s_tempty[acc], acc_ph);       // the accumulator is drained and zeroed
               if (!a.b_resident || useb == 0) mbar_wait_parked(&s_bfull[sb], useb & 1u);
@@ -489,6 +513,7 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_fpempty[fb]);   // the group leaves this (tile, slab) box
       }
+      __syncwarp();
       if (lane == 0) mbar_arrive(&s_tabempty[tb]);    // ... and this tile
     }
   } else if (warp < W_MMA) {
@@ -869,20 +894,24 @@ static int fp_run(const cnb_conv_desc* d, const void* x, const float* om, const 
       return CNB_ERR_CUDA;
     }
   }
-  static const bool blend_bf16 = [] { const char* e = getenv("CNB_DCN_BLEND"); return e && e[0] == 'b'; }();
+  // CNB_DCN_BLEND: fp32 (default) | wbf16 (bilinear weights rounded to bf16, mixed-precision FMAs) | bf16 (bf16x2 blend)
+  static const int blend_mode = [] { const char* e = getenv("CNB_DCN_BLEND"); return !e ? 0 : e[0] == 'w' ? 2 : e[0] == 'b' ? 1 : 0; }();
   static const int env_dbg = [] { const char* e = getenv("CNB_DCN_DEBUG"); return e ? atoi(e) : 0; }();
   a.debug = env_dbg;
   static PerDeviceOnce once;
   if (once.need()) {
-    CNB_CUDA(cudaFuncSetAttribute(dcn_fp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    CNB_CUDA(cudaFuncSetAttribute(dcn_fp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    CNB_CUDA(cudaFuncSetAttribute(dcn_fp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    CNB_CUDA(cudaFuncSetAttribute(dcn_fp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    CNB_CUDA(cudaFuncSetAttribute(dcn_fp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     once.mark();
   }
   const int grid = a.m_tiles < drv.num_sms ? a.m_tiles : drv.num_sms;
-  if (blend_bf16)
-    CNB_CUDA(launch_pdl(dcn_fp_kernel<true>, dim3(grid), dim3(NTHREADS), p.smem, st, tmB, tmX, tmO, a));
+  if (blend_mode == 1 && !plain)
+    CNB_CUDA(launch_pdl(dcn_fp_kernel<1>, dim3(grid), dim3(NTHREADS), p.smem, st, tmB, tmX, tmO, a));
+  else if (blend_mode == 2 && !plain)
+    CNB_CUDA(launch_pdl(dcn_fp_kernel<2>, dim3(grid), dim3(NTHREADS), p.smem, st, tmB, tmX, tmO, a));
   else
-    CNB_CUDA(launch_pdl(dcn_fp_kernel<false>, dim3(grid), dim3(NTHREADS), p.smem, st, tmB, tmX, tmO, a));
+    CNB_CUDA(launch_pdl(dcn_fp_kernel<0>, dim3(grid), dim3(NTHREADS), p.smem, st, tmB, tmX, tmO, a));
   CNB_LAUNCH_CHECK();
   return CNB_OK;
 }

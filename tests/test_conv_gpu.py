@@ -181,6 +181,22 @@ def test_dcnv2_matches_torchvision(cuda_dev, B, Ci, Co, H, W, sliced):
     _check(y.permute(0, 3, 1, 2).cpu(), ref, 2e-2)
 
 
+@pytest.mark.parametrize("B,Ci,Co,H", [(8, 64, 64, 128), (8, 128, 64, 64), (4, 256, 256, 32)])
+def test_dcnv2_repeats_are_bit_identical(cuda_dev, B, Ci, Co, H):
+    """The footprint kernel is a web of mbarrier hand-offs (table, boxes, A ring in tensor memory, weight slots, two
+    accumulators) with several tiles per CTA at these sizes and no atomics: a lost ordering anywhere shows up as a
+    run-to-run difference.  (compute-sanitizer racecheck does not follow the table's full/empty mbarriers in this kernel
+    and reports its reads against its writes -- profiles/r02u_sanitizers.txt; this is the direct check.)"""
+    g = torch.Generator().manual_seed(11)
+    x = ops.to_nhwc_bf16(torch.randn(B, Ci, H, H, generator=g).to(cuda_dev))
+    om = (torch.randn(B, H, H, 32, generator=g) * 0.7).to(cuda_dev)
+    wpk = ops.pack_conv_weights((torch.randn(Co, Ci, 3, 3, generator=g) * 0.05).to(cuda_dev))
+    bias = torch.zeros(Co, device=cuda_dev)
+    first = ops.dcnv2(x, om, wpk, Co, None, bias, act=0).clone()
+    for _ in range(60):
+        assert torch.equal(ops.dcnv2(x, om, wpk, Co, None, bias, act=0), first)
+
+
 def test_dcn_module_matches_torchvision(cuda_dev):
     """The drop-in `DCN.dcn_v2.DCN` module end to end (offset conv + sampler + GEMM) with non-zero
     conv_offset_mask weights (zero init would make DCN == 0.5 * conv)."""

@@ -22,6 +22,7 @@ VARIANTS = [
     ({"CNB_CONV_FP": "1"}, "test_conv_matches_torch or test_conv_concat_slices or dcn_module"),   # every eligible 3x3 conv through the footprint kernel
     ({"CNB_CONV_FP": "0"}, "test_conv_matches_torch or dcn_module"),
     ({"CNB_DCN_BLEND": "bf16"}, "dcn"),
+    ({"CNB_DCN_BLEND": "wbf16"}, "dcn"),
     ({"CNB_DCN_GROUPS": "1"}, "dcn"),
     ({"CNB_DCN_GROUPS": "4"}, "dcn"),
     ({"CNB_DCN_IMPL": "v1"}, "dcn"),
