@@ -69,7 +69,7 @@ struct FArgs {
   int tiles_x, tiles_y;
   int tw_shift;    // tile = (128 >> tw_shift) rows x (1 << tw_shift) columns
   int R;           // offsets up to +-R stay inside the staged box
-  int FW, FH;      // box: (TW + 2R + 3) x (TH + 2R + 3) pixels
+  int FW, FH;      // box: (TW + 2R + 3, rounded up to a multiple of 8) x (TH + 2R + 3) pixels
   u32 fp_bytes;    // FW * FH * 128
   u32 fp_stride;   // fp_bytes rounded up to 1 KB
   int BN;          // = Co rounded up to 16, <= 256
@@ -735,6 +735,12 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+static int box_width(int TW, int R, bool plain) {
+  static const bool exact = [] { const char* e = getenv("CNB_DCN_BOXW"); return e && e[0] == 'e'; }();   // A/B: exact width
+  const int w = plain ? TW + 2 : TW + 2 * R + 3;
+  return exact ? w : (w + 7) / 8 * 8;
+}
+
 struct Plan {
   int tw_shift, R, stages, nb, BN, kps;
   u32 bstage, fp_bytes, fp_stride;
@@ -771,7 +777,10 @@ bool make_plan(const cnb_conv_desc* d, Plan* p, bool plain = false) {
   for (int ci = 0; ci < ncand; ++ci) {
     const int* c = cands[ci];
     const int R = plain ? 0 : (env_r > 0 ? env_r : c[0]);
-    const int FW = plain ? TW + 2 : TW + 2 * R + 3, FH = plain ? TH + 2 : TH + 2 * R + 3;
+    // box width rounded up to a multiple of 8 pixels: a row step then leaves the swizzle (box pixel index mod 8) unchanged,
+    // so lanes that sample distinct columns mod 8 never share a bank group however their rows jitter (with 23 columns a
+    // neighbour one row down and one column right collided: measured 2-way conflicts on the network's offset fields)
+    const int FW = box_width(TW, R, plain), FH = plain ? TH + 2 : TH + 2 * R + 3;
     const u32 fpb = (u32)FW * FH * 128u;
     const u32 fps = (fpb + 1023u) & ~1023u;
     if (fixed + 2 * (size_t)fps + 2 * (size_t)p->bstage > budget) continue;
@@ -828,7 +837,7 @@ static int fp_run(const cnb_conv_desc* d, const void* x, const float* om, const 
   a.tiles_y = (d->Hi + TH - 1) / TH;
   a.m_tiles = d->B * a.tiles_x * a.tiles_y;
   a.R = p.R;
-  a.FW = plain ? TW + 2 : TW + 2 * p.R + 3;
+  a.FW = box_width(TW, p.R, plain);
   a.FH = plain ? TH + 2 : TH + 2 * p.R + 3;
   a.fp_bytes = p.fp_bytes;
   a.fp_stride = p.fp_stride;
