@@ -449,6 +449,15 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
           if (tap + NG < 9) {
             w_next = tw[tap + NG];
             b_next = tbs[tap + NG];
+            if (b_next >> 31) {   // a far sample of the next K block: pull its four corner lines into L1 now (the generic
+                                  // loads below would otherwise each wait for L2)
+              const u64 pb = xg + (u64)(slab * 128) + (u64)(b_next & 0x1FFFFFFFu) * cs2;
+              const u32 pd1 = ((b_next >> 29) & 1u) ? cs2 : 0u, pd2 = ((b_next >> 30) & 1u) ? rowb : 0u;
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(pb));
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(pb + pd1));
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(pb + pd2));
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(pb + pd2 + pd1));
+            }
           }
           if (FP_DBG(a) & 128) mbar_wait_spin(&s_empty[s], ph ^ 1u); else mbar_wait_parked(&s_empty[s], ph ^ 1u);
           tc_fence_after();

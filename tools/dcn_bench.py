@@ -18,7 +18,13 @@ for name in (sys.argv[1:] or list(CASES)):
     x = torch.randn(B, hw, hw, ci, device=dev).to(torch.bfloat16)
     w = ops.pack_conv_weights(torch.randn(co, ci, 3, 3, device=dev) * 0.05)
     sc, sh = torch.ones(co, device=dev), torch.zeros(co, device=dev)
-    if os.environ.get("DCN_BENCH_OFFSETS", "smooth") == "random":
+    mode = os.environ.get("DCN_BENCH_OFFSETS", "smooth")
+    if mode.startswith("far"):   # far:S -- a smooth field with per-tap displacements of std S pixels (what the deep layers of
+        sdev = float(mode.split(":")[1]) if ":" in mode else 1.2   # the randomly initialised network produce)
+        low = torch.randn(B, max(hw // 16, 1), max(hw // 16, 1), 32, device=dev) * sdev
+        om = torch.nn.functional.interpolate(low.permute(0, 3, 1, 2), size=(hw, hw), mode="bilinear", align_corners=False)
+        om = om.permute(0, 2, 3, 1).contiguous()
+    elif mode == "random":
         om = torch.randn(B, hw, hw, 32, device=dev) * 0.5
     else:
         om = (torch.rand(1, 1, 1, 32, device=dev) * 2 - 1) * 0.8 + torch.randn(B, hw, hw, 32, device=dev) * 0.05
