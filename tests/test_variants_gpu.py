@@ -37,6 +37,9 @@ VARIANTS = [
 def test_kernel_variant(cuda_dev, env, select):
     e = dict(os.environ)
     e.update(env)
+    import torch
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()      # the child gets its own context: give back what this process's allocator has cached
     cmd = [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_conv_gpu.py"), "-x", "-q",
            "-m", "gpu", "-k", select, "-p", "no:cacheprovider"]
     r = subprocess.run(cmd, cwd=ROOT, env=e, capture_output=True, text=True, timeout=600)
