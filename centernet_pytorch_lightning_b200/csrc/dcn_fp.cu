@@ -555,7 +555,11 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
         om[4 * j] = __uint_as_float(v.x); om[4 * j + 1] = __uint_as_float(v.y);
         om[4 * j + 2] = __uint_as_float(v.z); om[4 * j + 3] = __uint_as_float(v.w);
       }
-      // all 128 rows are in registers: refill the staging buffer for the next tile
+      // All 128 rows are in registers -- once the loads have actually RETURNED: the copy that refills the buffer is an
+      // async-proxy write, and a barrier alone does not hold it behind shared-memory loads that are still in flight
+      // (nothing has consumed their registers yet).  Without this fence one run in ~500 computed a tile row of table
+      // entries from the NEXT tile's offsets (found by tests/test_conv_gpu.py::test_dcnv2_repeats_are_bit_identical).
+      fence_proxy_async_smem();
       asm volatile("bar.sync 1, %0;" ::"n"(NSETUP) : "memory");
       if (r == 0 && tile + 1 < tile_end) {
         const TileXY tn = tile_xy(a, tile + 1);
