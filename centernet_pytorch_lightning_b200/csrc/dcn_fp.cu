@@ -950,11 +950,13 @@ int dcn_fp_run(const cnb_conv_desc* d, const void* x, const float* om, int om_cs
 // 64->64@64x64 23.8 vs 25.7; 64->64@128x128 57.9 vs 53.7, 64->27@128x128 60.5 vs 58.3, 256->27@32x32 26.4 vs 23.4 -- every
 // small-N tcgen05 GEMM of this library lands at 420-480 clocks per (128 rows x K = 64), i.e. ~112 clocks per M = 128 / K = 16
 // MMA whatever N <= 64 is and wherever A comes from, so only the layers whose im2col traffic or tile count hurt the other
-// kernels gain.  Default: Ci >= 128, N <= 64, at least 4 tiles per SM.  CNB_CONV_FP=1 forces it for every eligible
-// geometry (the parity tests run that), =0 disables it.
+// kernels gain (Ci >= 128, N <= 64, at least 4 tiles per SM: CNB_CONV_FP=2 selects exactly those).  OFF by default: four
+// groups issuing into one accumulator in whatever order they get there makes the fp32 summation order, hence the last
+// bits of the result, vary from run to run (tools/conv_race_hunt.py: every repeat differs), and everything else in this
+// library is bit-reproducible.  CNB_CONV_FP=1 forces the mode for every eligible geometry (the parity tests run that).
 bool conv_fp_supported(const cnb_conv_desc* d) {
-  static const int env = [] { const char* e = getenv("CNB_CONV_FP"); return e ? atoi(e) : -1; }();
-  if (env == 0) return false;
+  static const int env = [] { const char* e = getenv("CNB_CONV_FP"); return e ? atoi(e) : 0; }();
+  if (env <= 0) return false;
   Plan p;
   const bool ok = d->KH == 3 && d->KW == 3 && d->stride == 1 && d->pad == 1 && d->dil == 1 && d->pad_w1 == 0 &&
                   (d->w_kw == 0 || d->w_kw == 3) && d->Ho == d->Hi && d->Wo == d->Wi && d->Ci % 64 == 0 &&
