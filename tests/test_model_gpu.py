@@ -186,3 +186,29 @@ def test_hourglass_backbone_matches_oracle(cuda_dev):
         for k in HEADS:
             l2, mx = _rel(got_heads[s][k], ref_heads[s][k])
             assert l2 <= 3e-2 and mx <= 8e-2, (s, k, l2, mx)
+
+
+def test_network_repeats_are_bit_identical(cuda_dev):
+    """Every kernel on the inference path is deterministic (no atomics in the forward, fixed accumulation orders), so a
+    repeated step must reproduce every head map and every detection bit for bit; a lost hand-off in one of the
+    warp-specialised kernels shows up here as a run-to-run difference (tools/net_race_hunt.py is the long version:
+    0 differing runs in 1500 steps at batch 32)."""
+    torch.manual_seed(3)
+    model = create_model("dla_34")
+    heads = {"heatmap": 80, "width_height": 2, "regression": 2}
+    head = CenterHead(heads, model.out_channels, 256)
+    randomize_(model.state_dict(), 7)
+    randomize_(head.state_dict(), 8)
+    model, head = model.to(cuda_dev).eval(), head.to(cuda_dev).eval()
+    x = torch.rand(8, 3, 512, 512, device=cuda_dev)
+
+    def step():
+        with torch.no_grad():
+            o = head(model(x)[-1], sigmoid=("heatmap",))
+            det = ctdet_decode(o["heatmap"], o["width_height"], reg=o["regression"])
+        return [o["heatmap"].clone(), o["width_height"].clone(), o["regression"].clone(), det.clone()]
+
+    first = step()
+    for _ in range(40):
+        for a, b in zip(step(), first):
+            assert torch.equal(a, b)
