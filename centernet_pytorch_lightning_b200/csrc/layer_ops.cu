@@ -343,6 +343,88 @@ dw_deconv_phase3d_kernel(const __nv_bfloat16* __restrict__ x, const float* __res
   }
 }
 
+// Tile kernel.  What bounds the kernels above is memory-level parallelism, not bandwidth: a thread has 3 x 16 bytes in
+// flight and waits a full DRAM latency per output row (768 threads x 48 B = 37 KB per SM, i.e. ~2.5 TB/s at ~2 us loaded
+// latency -- where every variant sat; torch's copy_ of the same bytes runs at 5.4 TB/s).  Here a CTA requests everything
+// its tile needs up front with cp.async -- the (tqh + 1) x 17 input pixels and the tqh*f x 16*f pixels of the `add` map,
+// ~43 KB -- five such CTAs per SM keep > 200 KB in flight, and the blend then runs out of shared memory.  A thread keeps
+// (8-channel group, phase) fixed (its 4 x 8 taps in registers); same tap order as the kernels above: bit-identical results.
+constexpr int UPT_W = 16;
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__global__ void __launch_bounds__(256)
+dw_deconv_tile_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wt,
+                      const __nv_bfloat16* __restrict__ add, __nv_bfloat16* __restrict__ y, int B, int H, int W, int C,
+                      int f, int tqh) {
+  extern __shared__ __align__(16) unsigned char up_smem[];
+  const int Ho = H * f, Wo = W * f, groups = C / 8, ks = 2 * f, pad = f / 2;
+  const int npix = (tqh + 1) * (UPT_W + 1);                // input pixels of the tile
+  const int arows = tqh * f, acols = UPT_W * f;            // output / add pixels of the tile
+  uint4* s_in = reinterpret_cast<uint4*>(up_smem);         // [npix][groups]
+  uint4* s_add = s_in + npix * groups;                     // [arows][acols][groups]
+  const int b = blockIdx.z, qy0 = blockIdx.y * tqh, qx0 = blockIdx.x * UPT_W;
+  const int oy0 = qy0 * f - pad, ox0 = qx0 * f - pad;      // first output pixel of the tile (may be -pad)
+  // ---- everything the tile reads, requested at once ------------------------------------------------------
+  for (int i = threadIdx.x; i < npix * groups; i += 256) {
+    const int p = i / groups, gg = i - p * groups;
+    const int ry = p / (UPT_W + 1), rx = p - ry * (UPT_W + 1);
+    const int iy = qy0 - 1 + ry, ix = qx0 - 1 + rx;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) cp_async16(s_in + i, x + ((size_t)(b * H + iy) * W + ix) * C + gg * 8);
+    else s_in[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (add) {
+    for (int i = threadIdx.x; i < arows * acols * groups; i += 256) {
+      const int p = i / groups, gg = i - p * groups;
+      const int ry = p / acols, rx = p - ry * acols;
+      const int oy = oy0 + ry, ox = ox0 + rx;
+      if (oy >= 0 && oy < Ho && ox >= 0 && ox < Wo) cp_async16(s_add + i, add + ((size_t)(b * Ho + oy) * Wo + ox) * C + gg * 8);
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  // ---- this thread's taps while the copies fly ---------------------------------------------------------------
+  const int per = groups * f * f;                          // threads per cell: (phase, channel group)
+  const int idx = threadIdx.x % per, slot = threadIdx.x / per, nslot = 256 / per;
+  const int phase = idx / groups, g = idx - phase * groups;
+  const int py = phase / f, px = phase - py * f;
+  float w[4][8];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {                            // tap (ky, kx) = (py + a f, px + c f) reads input (qy - a, qx - c)
+    const int ky = py + (t >> 1) * f, kx = px + (t & 1) * f;
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(wt + (size_t)(ky * ks + kx) * C + g * 8));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(wt + (size_t)(ky * ks + kx) * C + g * 8 + 4));
+    w[t][0] = w0.x; w[t][1] = w0.y; w[t][2] = w0.z; w[t][3] = w0.w;
+    w[t][4] = w1.x; w[t][5] = w1.y; w[t][6] = w1.z; w[t][7] = w1.w;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  for (int c = slot; c < tqh * UPT_W; c += nslot) {
+    const int cy = c / UPT_W, cx = c - cy * UPT_W;
+    const int qy = qy0 + cy, qx = qx0 + cx;
+    const int ry = cy * f + py, rx = cx * f + px;          // position inside the tile's output block
+    const int oy = oy0 + ry, ox = ox0 + rx;
+    if (qy > H || qx > W || oy < 0 || oy >= Ho || ox < 0 || ox >= Wo) continue;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const uint4 v = s_in[((cy + 1 - (t >> 1)) * (UPT_W + 1) + (cx + 1 - (t & 1))) * groups + g];
+      const float2 a0 = bf2_to_f2(v.x), a1 = bf2_to_f2(v.y), a2 = bf2_to_f2(v.z), a3 = bf2_to_f2(v.w);
+      acc[0] += w[t][0] * a0.x; acc[1] += w[t][1] * a0.y; acc[2] += w[t][2] * a1.x; acc[3] += w[t][3] * a1.y;
+      acc[4] += w[t][4] * a2.x; acc[5] += w[t][5] * a2.y; acc[6] += w[t][6] * a3.x; acc[7] += w[t][7] * a3.y;
+    }
+    if (add) {
+      const uint4 av = s_add[(ry * acols + rx) * groups + g];
+      const float2 a0 = bf2_to_f2(av.x), a1 = bf2_to_f2(av.y), a2 = bf2_to_f2(av.z), a3 = bf2_to_f2(av.w);
+      acc[0] += a0.x; acc[1] += a0.y; acc[2] += a1.x; acc[3] += a1.y;
+      acc[4] += a2.x; acc[5] += a2.y; acc[6] += a3.x; acc[7] += a3.y;
+    }
+    *reinterpret_cast<uint4*>(y + ((size_t)(b * Ho + oy) * Wo + ox) * C + g * 8) =
+        make_uint4(f2_to_bf2(acc[0], acc[1]), f2_to_bf2(acc[2], acc[3]), f2_to_bf2(acc[4], acc[5]), f2_to_bf2(acc[6], acc[7]));
+  }
+}
+
 // f == 2 (every large up-sampling of the DLA-34 / ResNet nets): a thread owns (8-channel group, input column qx, output
 // row phase py) and walks down the rows.  Its 2 x 4 x 8 taps sit in registers, the two input rows of a cell roll
 // through registers, and each cell yields the two horizontally adjacent outputs: 2 input loads + 2 (add) loads +
@@ -502,6 +584,29 @@ extern "C" int cnb_dw_deconv_up(const void* x, const float* wt, const void* add,
   CNB_CHECK_ARG(x && wt && y && B >= 1 && H >= 1 && W >= 1, "dw_deconv_up: bad argument");
   CNB_CHECK_ARG(C % 8 == 0 && f >= 1 && f % 2 == 0, "dw_deconv_up: C %% 8 == 0 and even upsampling factor required");
   const int groups = C / 8;
+  static const int up_tile = [] { const char* e = getenv("CNB_DW_DECONV_IMPL"); return e ? atoi(e) : 4; }();
+  {
+    const int per = groups * f * f;
+    const int tqh = 128 / (f * f * groups);   // add tile (tqh f) x (16 f) pixels x C channels <= 32 KB
+    // cp.async tile kernel: default for the large outputs, where it measured faster (B=32: 64x64 -> 128x128 59.7 -> 53.4 us,
+    // 32x32 -> 128x128 (f=4) 65.2 -> 54.0 us; 33 vs 33 us and 24 vs 22 us at 64x64 / 32x32 outputs); CNB_DW_DECONV_IMPL=5
+    // forces it everywhere, =3 / =2 select the phase kernels
+    if ((up_tile == 5 || (up_tile == 4 && (long long)H * f >= 128)) && per <= 256 && 256 % per == 0 && tqh >= 1 && B <= 65535) {
+      const size_t smem = ((size_t)(tqh + 1) * (UPT_W + 1) + (size_t)tqh * f * UPT_W * f) * groups * 16;
+      static PerDeviceOnce once;
+      if (once.need()) {
+        CNB_CUDA(cudaFuncSetAttribute(dw_deconv_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        once.mark();
+      }
+      if (smem <= 64 * 1024) {
+        dim3 grid((unsigned)((W + 1 + UPT_W - 1) / UPT_W), (unsigned)((H + 1 + tqh - 1) / tqh), (unsigned)B);
+        dw_deconv_tile_kernel<<<grid, 256, smem, (cudaStream_t)s>>>((const __nv_bfloat16*)x, wt, (const __nv_bfloat16*)add,
+                                                                    (__nv_bfloat16*)y, B, H, W, C, f, tqh);
+        CNB_LAUNCH_CHECK();
+        return CNB_OK;
+      }
+    }
+  }
   static const bool no_f2 = [] { const char* e = getenv("CNB_DW_DECONV_F2"); return e && e[0] == '0'; }();
   static const int up_impl0 = [] { const char* e = getenv("CNB_DW_DECONV_IMPL"); return e ? atoi(e) : 3; }();
   if (f == 2 && !no_f2 && B <= 32767 && H >= 64 && up_impl0 == 2) {   // measured: 71 vs 78 us at 64x64 -> 128x128, no gain on small maps

@@ -219,6 +219,22 @@ def test_dcn_module_matches_torchvision(cuda_dev):
     _check(got.cpu(), ref, 3e-2)
 
 
+@pytest.mark.parametrize("C,H,W,f", [(64, 64, 64, 2), (64, 32, 48, 4), (128, 64, 80, 2), (256, 72, 64, 2)])
+def test_upsample_tile_kernel(cuda_dev, C, H, W, f):
+    """Depthwise ConvTranspose2d(2f, stride f, pad f/2) + skip add at the sizes that take the cp.async tile kernel
+    (outputs of 128 rows and more; pose_dla_dcn.py:466-488), incl. tiles cut by the right / bottom image border."""
+    g = torch.Generator().manual_seed(C + f)
+    x = _bf(torch.randn(2, C, H, W, generator=g)).to(cuda_dev)
+    w = torch.randn(C, 1, 2 * f, 2 * f, generator=g).to(cuda_dev)
+    add = _bf(torch.randn(2, C, H * f, W * f, generator=g)).to(cuda_dev)
+    ref = F.conv_transpose2d(x, w, stride=f, padding=f // 2, groups=C)
+    wt = ops.relayout_dw_weights(w, f)
+    got = ops.dw_deconv_up(ops.to_nhwc_bf16(x), wt, f, add=ops.to_nhwc_bf16(add))
+    _check(got.permute(0, 3, 1, 2), ref + add, 1e-2)
+    got = ops.dw_deconv_up(ops.to_nhwc_bf16(x), wt, f)
+    _check(got.permute(0, 3, 1, 2), ref, 1e-2)
+
+
 def test_maxpool_and_upsample(cuda_dev):
     g = torch.Generator().manual_seed(3)
     x = _bf(torch.randn(2, 64, 16, 24, generator=g)).to(cuda_dev)

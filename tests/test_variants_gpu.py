@@ -29,6 +29,8 @@ VARIANTS = [
     ({"CNB_DCN_IMPL": "ws"}, "dcn"),
     ({"CNB_DCN_REACH": "1"}, "dcn"),
     ({"CNB_DCN_REACH": "1", "CNB_DCN_STAGES": "2", "CNB_DCN_GROUPS": "1"}, "dcn"),
+    ({"CNB_DW_DECONV_IMPL": "5"}, "upsample"),     # cp.async tile kernel at every size
+    ({"CNB_DW_DECONV_IMPL": "3"}, "upsample"),     # phase kernel at every size
     ({"CNB_PDL": "0"}, "test_conv_matches_torch or dcn"),
 ]
 
