@@ -264,8 +264,8 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_tfull[i], a.plain ? NG : 1);     // plain mode: one commit per issuing group
       mbar_init(&s_tempty[i], a.plain ? 8 : 4);   // one arrival per epilogue warp (plain mode: the setup warps join)
-      mbar_init(&s_tabfull[i], NSETUP_WARPS);
-      mbar_init(&s_tabempty[i], NPROD_WARPS);
+      mbar_init(&s_tabfull[i], NSETUP);           // every setup thread releases its own table rows
+      mbar_init(&s_tabempty[i], NPROD_WARPS * 32);  // every sampler thread: it is the thread that read them
       mbar_init(&s_fpfull[i], 1);
       mbar_init(&s_fpempty[i], NPROD_WARPS);
     }
@@ -522,8 +522,7 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_fpempty[fb]);   // the group leaves this (tile, slab) box
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_tabempty[tb]);    // ... and this tile
+      mbar_arrive(&s_tabempty[tb]);                   // ... and this tile (per thread: each read its own table row)
     }
   } else if (warp < W_MMA) {
     // =============================== setup: (pixel, tap) -> weights + corner index ============================
@@ -623,8 +622,7 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
           ob[tap] = 0x80000000u | ((u32)(y1c - y0c) << 30) | ((u32)(x1c - x0c) << 29) | (gbase + (u32)(y0c * d.Wi + x0c));
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_tabfull[tb]);
+      mbar_arrive(&s_tabfull[tb]);
     }
     }
   } else if (warp == W_MMA) {

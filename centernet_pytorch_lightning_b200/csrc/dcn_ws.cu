@@ -128,8 +128,8 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_tfull[i], 1);
       mbar_init(&s_tempty[i], 4);
-      mbar_init(&s_tabfull[i], NSETUP_WARPS);
-      mbar_init(&s_tabempty[i], NPROD_WARPS);
+      mbar_init(&s_tabfull[i], NSETUP);     // every setup thread releases the entries it wrote ...
+      mbar_init(&s_tabempty[i], NPROD);     // ... and every sampler thread the rows it read
       mbar_init(&s_omfull[i], 1);
     }
     fence_mbar_init();
@@ -275,7 +275,7 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
         if (++slab == nslabs) {   // the group leaves this tile
           slab = 0;
           __syncwarp();
-          if (lane == 0) mbar_arrive(&s_tabempty[tb]);
+          mbar_arrive(&s_tabempty[tb]);
           ++t;
           have_tab = false;
         }
@@ -343,7 +343,7 @@ dcn_ws_kernel(const __grid_constant__ CUtensorMap tmB, const DArgs a) {
         s_tabb[tb * NTAB + item] = b;
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_tabfull[tb]);
+      mbar_arrive(&s_tabfull[tb]);
       if (stid == 0) DCN_STAMP(5, (int)t);
       // all setup warps are done with this om buffer: refill it for tile + 2
       asm volatile("bar.sync 1, %0;" ::"n"(NSETUP) : "memory");
@@ -464,6 +464,10 @@ int dcn_ws_run(const cnb_conv_desc* d, const void* x, const float* om, int om_cs
   if (a.stages > MAX_STAGES) a.stages = MAX_STAGES;
   while (a.stages > 2 && (size_t)a.stages * a.stage_bytes + fixed > 220 * 1024) --a.stages;
   while (a.ngroups > a.stages) a.ngroups >>= 1;   // a group must not lap the ring (mbarrier phase parity)
+  // a ring depth that is a multiple of the group count gives every stage ONE owner group: the same threads rewrite the
+  // same shared-memory rows each time round (their hand-off to the tensor core is tcgen05.commit -> mbarrier, which
+  // compute-sanitizer racecheck cannot see and reported as a write-after-write hazard between the groups)
+  if (a.stages % a.ngroups != 0 && a.stages - a.stages % a.ngroups >= 2) a.stages -= a.stages % a.ngroups;
   a.acc_stride = (u32)round_up(a.BN, 32);
   a.tmem_cols = 32;
   while (a.tmem_cols < 2 * a.acc_stride) a.tmem_cols <<= 1;
