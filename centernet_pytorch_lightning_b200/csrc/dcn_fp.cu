@@ -79,7 +79,7 @@ struct FArgs {
   int stages;      // A ring depth: stage i = tensor-memory columns a_col0 + 32 i
   int nb;          // weight-tile slots in shared memory; K block j of the CTA's stream uses slot j % nb
   int b_resident;  // nb >= nkb: the 9 * Ci/64 weight tiles are loaded once and stay
-  u32 b_bytes, tmem_cols, acc_stride, a_col0, idesc;
+  u32 b_bytes, tmem_cols, acc_stride, part_stride, a_col0, idesc;
   int kps;         // K blocks per A stage: 1, or 3 in plain mode with N <= 64 (a group samples a whole filter row per handshake)
   int plain;       // 1: plain 3x3 / stride 1 / pad 1 convolution through the same machinery (no offsets, no table, R = 0)
   int debug;       // timing experiments (-DCNB_DCN_EXPERIMENTS): 1 no corner loads, 2 no blend, 4 no tcgen05.st, 8 no table read
@@ -300,17 +300,6 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
   auto run_epilogue = [&](int half, int nhalves) {
     const int q = warp & 3;
     u32 t = 0;
-    if (a.plain) {   // every MMA of this mode accumulates: hand the accumulators over zeroed
-      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-      for (int i = 0; i < a.nacc; ++i) {
-        for (int g = half; g < a.BN / 16; g += nhalves)
-          tmem_st16(tmem_base + (u32)i * a.acc_stride + ((u32)(32 * q) << 16) + (u32)(g * 16), z, z, z, z);
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_tempty[i]);
-      }
-    }
     for (int tile = tile_begin; tile < tile_end; ++tile, ++t) {
       const u32 acc = a.nacc == 2 ? (t & 1u) : 0u, acc_ph = (a.nacc == 2 ? (t >> 1) : t) & 1u;
       const TileXY tc = tile_xy(a, tile);
@@ -326,13 +315,17 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
         tmem_ld16_nowait(taddr + (u32)(g * 16), v);
         tmem_ld_wait();
         const int co0 = g * 16;
-        if (a.plain) {
-          const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-          tmem_st16(taddr + (u32)(g * 16), z, z, z, z);
+        if (a.plain) {   // one partial sum per issuing group, added in group order
+          for (int pg = 1; pg < NG; ++pg) {
+            u32 w[16];
+            tmem_ld16_nowait(taddr + (u32)pg * a.part_stride + (u32)(g * 16), w);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w[i]));
+          }
         }
         if (oy < d.Hi && co0 < d.Co) epilogue_store(a, s_scale, s_shift, v, m, co0, co0, d.Hi * d.Wi, 0, 0);
       }
-      if (a.plain) tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_tempty[acc]);
@@ -359,8 +352,9 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
       // times from L2 (TMA im2col).  With no arithmetic in the sampler the kernel is bound by the lone MMA warp's
       // bookkeeping (~500 clocks per K block, measured), so in this mode there is none: the four warps of a group meet
       // at a named barrier and the group's first warp issues the K block's MMAs itself -- four issuers in parallel.
-      // Their MMAs may reach the tensor core in any order, so every one of them accumulates (the epilogue hands each
-      // accumulator back ZEROED instead of the first MMA of a tile overwriting it).
+      // MMAs of different issuers reach the tensor core in any order, so each group accumulates into its OWN partial
+      // accumulator (one thread issues all of a partial's MMAs, in program order: the result is reproducible bit for bit)
+      // and the epilogue adds the four partials in group order.
       const int ty = row >> a.tw_shift, tx = row & (TW - 1);
       const bool issuer = (warp & 3) == 0;
       const u64 db0 = make_sdesc(smem_base, 16, 1024, 2);
@@ -370,7 +364,7 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
       u32 sb = (u32)grp % wrapb, useb = (u32)grp / wrapb;   // weight-tile slot of this group's next K block, and its use count
       for (int tile = tile_begin; tile < tile_end; ++tile, ++t) {
         const u32 acc = two_acc ? (t & 1u) : 0u, acc_ph = (two_acc ? (t >> 1) : t) & 1u;
-        const u32 tmem_d = tmem_base + acc * a.acc_stride;
+        const u32 tmem_d = tmem_base + acc * a.acc_stride + (u32)grp * a.part_stride;
         bool first = true;                                 // first K block of this group in this tile
         for (int slab = 0; slab < nslabs; ++slab, ++u) {
           const u32 fb = u & 1u;
@@ -398,7 +392,7 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
             else if (grp == 2) asm volatile("bar.sync 4, 128;" ::: "memory");
             else asm volatile("bar.sync 5, 128;" ::: "memory");
             if (issuer) {
-              if (first) mbar_wait_parked(&s_tempty[acc], acc_ph);       // the accumulator is drained and zeroed
+              if (first) mbar_wait_parked(&s_tempty[acc], acc_ph ^ 1u);  // the accumulator is drained
               if (!a.b_resident || useb == 0) mbar_wait_parked(&s_bfull[sb], useb & 1u);
               tc_fence_after();
               const bool last = slab == nslabs - 1 && tap + NG >= 9;     // this group's last K block of the tile
@@ -406,7 +400,8 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
                 const u64 db = db0 + (u64)(sb * bstage16);
                 const u32 tam = tmem_base + a.a_col0 + s * A_COLS;
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) umma_bf16_ts(tmem_d, tam + (u32)(8 * kk), db + (u64)(2 * kk), a.idesc, 1u);
+                for (int kk = 0; kk < 4; ++kk)
+                  umma_bf16_ts(tmem_d, tam + (u32)(8 * kk), db + (u64)(2 * kk), a.idesc, (first && kk == 0) ? 0u : 1u);
                 umma_commit(&s_empty[s]);
                 if (!a.b_resident) umma_commit(&s_bempty[sb]);
                 if (last) umma_commit(&s_tfull[acc]);
@@ -773,7 +768,10 @@ bool make_plan(const cnb_conv_desc* d, Plan* p, bool plain = false) {
   // K blocks per A stage: in plain mode with N <= 64 a sampler group fills a whole filter row per handshake
   const int kps = 1;
   p->kps = kps;
-  int st = (512 - (p->BN > 128 ? 1 : 2) * round_up(p->BN, 32)) / (A_COLS * kps);
+  // plain mode: NG partial accumulators per tile (double buffered while they fit)
+  if (plain && round_up(p->BN, 32) > 64) return false;
+  const int acc_cols = plain ? (p->BN > 32 ? 1 : 2) * NG * round_up(p->BN, 32) : (p->BN > 128 ? 1 : 2) * round_up(p->BN, 32);
+  int st = (512 - acc_cols) / (A_COLS * kps);
   if (st > MAX_STAGES) st = MAX_STAGES;
   if (env_stages > 0 && st > env_stages) st = env_stages;
   if (st < NG) return false;
@@ -860,8 +858,9 @@ static int fp_run(const cnb_conv_desc* d, const void* x, const float* om, const 
   a.kps = p.kps;
   a.nb = p.nb;
   a.b_resident = p.nb >= a.nkb ? 1 : 0;
-  a.acc_stride = (u32)round_up(a.BN, 32);
-  a.nacc = a.BN > 128 ? 1 : 2;
+  a.part_stride = (u32)round_up(a.BN, 32);
+  a.acc_stride = plain ? (u32)NG * a.part_stride : a.part_stride;
+  a.nacc = plain ? (a.BN > 32 ? 1 : 2) : (a.BN > 128 ? 1 : 2);
   a.a_col0 = (u32)a.nacc * a.acc_stride;
   a.tmem_cols = 512;   // one CTA per SM: two accumulators + the A ring
   a.idesc = make_idesc_bf16(BM, a.BN);
@@ -953,16 +952,19 @@ int dcn_fp_run(const cnb_conv_desc* d, const void* x, const float* om, int om_cs
 // bits of the result, vary from run to run (tools/conv_race_hunt.py: every repeat differs), and everything else in this
 // library is bit-reproducible.  CNB_CONV_FP=1 forces the mode for every eligible geometry (the parity tests run that).
 bool conv_fp_supported(const cnb_conv_desc* d) {
-  static const int env = [] { const char* e = getenv("CNB_CONV_FP"); return e ? atoi(e) : 0; }();
-  if (env <= 0) return false;
+  // CNB_CONV_FP: 0 = never, 1 = every geometry the mode covers, 2 = the policy below with N <= 64; unset = the policy:
+  // deep thin layers (Ci >= 128, N <= 32: the offset/mask convolutions at 64x64 and up) with >= 4 tiles per SM, where it
+  // measured faster than the TMA-im2col kernel
+  static const int env = [] { const char* e = getenv("CNB_CONV_FP"); return e ? atoi(e) : -1; }();
+  if (env == 0) return false;
   Plan p;
   const bool ok = d->KH == 3 && d->KW == 3 && d->stride == 1 && d->pad == 1 && d->dil == 1 && d->pad_w1 == 0 &&
                   (d->w_kw == 0 || d->w_kw == 3) && d->Ho == d->Hi && d->Wo == d->Wi && d->Ci % 64 == 0 &&
-                  round_up(d->Co, 16) <= 128 && d->Wi % 8 == 0 && d->out_nchw_f32 != 1 && d->x_cstride % 8 == 0 &&
+                  round_up(d->Co, 16) <= 64 && d->Wi % 8 == 0 && d->out_nchw_f32 != 1 && d->x_cstride % 8 == 0 &&
                   d->x_coffset % 8 == 0 && (long long)d->B * d->Hi * d->Wi < (1ll << 29) && make_plan(d, &p, true);
   if (!ok || env == 1) return ok;
   const long long m_tiles = ((long long)d->B * d->Hi * d->Wi + BM - 1) / BM;
-  return d->Ci >= 128 && round_up(d->Co, 16) <= 64 && m_tiles >= 4LL * sm_count();
+  return d->Ci >= 128 && round_up(d->Co, 16) <= (env == 2 ? 64 : 32) && m_tiles >= 4LL * sm_count();
 }
 
 int conv_fp_run(const cnb_conv_desc* d, const void* x, const void* wpk, const float* scale, const float* shift,
