@@ -53,6 +53,7 @@ constexpr int NG = 4;                                // sampler groups: K block 
 constexpr int WPG = NPROD_WARPS / NG;                // 4 warps per group = the 4 TMEM lane quarters
 constexpr int MAX_STAGES = 12;
 constexpr int MAX_B = 18;
+constexpr int MAX_FP = 6;          // boxes in flight (plain mode)
 constexpr int A_COLS = 32;                           // TMEM columns of one K block of A: 64 bf16 per row
 constexpr int NTAB = BM * 9;                         // (pixel, tap) entries per tile
 constexpr int OM_CS = 32;                            // channel stride of the offset/mask map this kernel takes
@@ -72,6 +73,7 @@ struct FArgs {
   int FW, FH;      // box: (TW + 2R + 3, rounded up to a multiple of 8) x (TH + 2R + 3) pixels
   u32 fp_bytes;    // FW * FH * 128
   u32 fp_stride;   // fp_bytes rounded up to 1 KB
+  int nfp;         // boxes in the ring: 2 (DCN mode: shared memory is full), up to MAX_FP in plain mode
   int BN;          // = Co rounded up to 16, <= 256
   int nacc;        // accumulators in tensor memory: 2 (epilogue of tile i overlaps tile i+1), 1 for BN > 128
   int nkb;         // 9 * Ci/64
@@ -217,8 +219,10 @@ __device__ __forceinline__ TileXY tile_xy(const FArgs& a, int tile) {
 
 #ifdef CNB_DCN_EXPERIMENTS
 #define FP_DBG(a) ((a).debug)
+#define PLAIN_WAIT(bar, par) do { if (FP_DBG(a) & 128) mbar_wait_spin(bar, par); else mbar_wait_parked(bar, par); } while (0)
 #else
 #define FP_DBG(a) 0
+#define PLAIN_WAIT(bar, par) mbar_wait_parked(bar, par)
 #endif
 
 template <int BLEND_BF16>
@@ -234,8 +238,8 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
   __shared__ __align__(8) u64 s_tempty[2];
   __shared__ __align__(8) u64 s_tabfull[2];
   __shared__ __align__(8) u64 s_tabempty[2];
-  __shared__ __align__(8) u64 s_fpfull[2];
-  __shared__ __align__(8) u64 s_fpempty[2];
+  __shared__ __align__(8) u64 s_fpfull[MAX_FP];
+  __shared__ __align__(8) u64 s_fpempty[MAX_FP];
   __shared__ __align__(8) u64 s_omfull;
   __shared__ u32 s_tmem;
 
@@ -244,7 +248,7 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
   const u32 smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* smem_al = smem_dyn + (smem_base - smem_u32(smem_dyn));
   const u32 fp_s = smem_base + (u32)a.nb * a.bstage;                                 // two footprint boxes
-  unsigned char* after_fp = smem_al + (size_t)a.nb * a.bstage + 2 * (size_t)a.fp_stride;
+  unsigned char* after_fp = smem_al + (size_t)a.nb * a.bstage + (size_t)a.nfp * a.fp_stride;
   const int ntab2 = a.plain ? 0 : 2 * NTAB;                                         // (no table / offsets in plain mode)
   float4* s_tabw = reinterpret_cast<float4*>(after_fp);                              // [2][NTAB]
   u32* s_tabb = reinterpret_cast<u32*>(s_tabw + ntab2);                              // [2][NTAB]
@@ -266,6 +270,8 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
       mbar_init(&s_tempty[i], a.plain ? 8 : 4);   // one arrival per epilogue warp (plain mode: the setup warps join)
       mbar_init(&s_tabfull[i], NSETUP);           // every setup thread releases its own table rows
       mbar_init(&s_tabempty[i], NPROD_WARPS * 32);  // every sampler thread: it is the thread that read them
+    }
+    for (int i = 0; i < a.nfp; ++i) {
       mbar_init(&s_fpfull[i], 1);
       mbar_init(&s_fpempty[i], NPROD_WARPS);
     }
@@ -324,7 +330,7 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
             for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w[i]));
           }
         }
-        if (oy < d.Hi && co0 < d.Co) epilogue_store(a, s_scale, s_shift, v, m, co0, co0, d.Hi * d.Wi, 0, 0);
+        if (oy < d.Hi && co0 < d.Co && !(FP_DBG(a) & 64)) epilogue_store(a, s_scale, s_shift, v, m, co0, co0, d.Hi * d.Wi, 0, 0);
       }
       tc_fence_before();
       __syncwarp();
@@ -345,6 +351,7 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
     const u64 xg = reinterpret_cast<u64>(a.x + d.x_coffset);
     const u32 ta_row = tmem_base + ((u32)((warp & 3) << 5) << 16) + a.a_col0;   // this warp's lanes, first A stage
     u32 s = (u32)grp % (u32)a.stages, ph = ((u32)grp / (u32)a.stages) & 1u, t = 0, u = 0;
+    u32 fb = 0, fph = 0;   // box of the current (tile, slab) and its barrier parity
     int tap = grp;
     if (a.plain) {
       // Plain 3x3 convolution: the A row of tap (kh, kw) is box pixel (ty + kh, tx + kw) as it is -- 8 shared-memory
@@ -367,17 +374,22 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
         const u32 tmem_d = tmem_base + acc * a.acc_stride + (u32)grp * a.part_stride;
         bool first = true;                                 // first K block of this group in this tile
         for (int slab = 0; slab < nslabs; ++slab, ++u) {
-          const u32 fb = u & 1u;
           const u32 fpb = fp_s + fb * a.fp_stride;
-          mbar_wait_parked(&s_fpfull[fb], (u >> 1) & 1u);
+          PLAIN_WAIT(&s_fpfull[fb], fph);
           for (; tap < 9; tap += NG) {
             const int kh = (tap * 11) >> 5, kw = tap - 3 * kh;     // tap / 3 for tap < 9
             const u32 pix = (u32)((ty + kh) * a.FW + tx + kw);
             const u32 e = (fpb + pix * 128u) | ((pix & 7u) << 4);
-            mbar_wait_parked(&s_empty[s], ph ^ 1u);        // the MMAs that read this A stage last time have completed
+            PLAIN_WAIT(&s_empty[s], ph ^ 1u);        // the MMAs that read this A stage last time have completed
             tc_fence_after();
             const u32 ta = ta_row + s * A_COLS;
-            {
+            if (FP_DBG(a) & 1) {   // experiment: no shared-memory reads
+              const uint4 z = make_uint4(e, e, e, e);
+              if (!(FP_DBG(a) & 2)) {
+                tmem_st16(ta, z, z, z, z);
+                tmem_st16(ta + 16u, z, z, z, z);
+              }
+            } else {
               const uint4 q0 = lds128(e), q1 = lds128(e ^ 16u), q2 = lds128(e ^ 32u), q3 = lds128(e ^ 48u);
               const uint4 q4 = lds128(e ^ 64u), q5 = lds128(e ^ 80u), q6 = lds128(e ^ 96u), q7 = lds128(e ^ 112u);
               tmem_st16(ta, q0, q1, q2, q3);
@@ -392,8 +404,8 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
             else if (grp == 2) asm volatile("bar.sync 4, 128;" ::: "memory");
             else asm volatile("bar.sync 5, 128;" ::: "memory");
             if (issuer) {
-              if (first) mbar_wait_parked(&s_tempty[acc], acc_ph ^ 1u);  // the accumulator is drained
-              if (!a.b_resident || useb == 0) mbar_wait_parked(&s_bfull[sb], useb & 1u);
+              if (first) PLAIN_WAIT(&s_tempty[acc], acc_ph ^ 1u);  // the accumulator is drained
+              if (!a.b_resident || useb == 0) PLAIN_WAIT(&s_bfull[sb], useb & 1u);
               tc_fence_after();
               const bool last = slab == nslabs - 1 && tap + NG >= 9;     // this group's last K block of the tile
               if (elect_one()) {
@@ -401,7 +413,7 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
                 const u32 tam = tmem_base + a.a_col0 + s * A_COLS;
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
-                  umma_bf16_ts(tmem_d, tam + (u32)(8 * kk), db + (u64)(2 * kk), a.idesc, (first && kk == 0) ? 0u : 1u);
+                  if (!(FP_DBG(a) & 4)) umma_bf16_ts(tmem_d, tam + (u32)(8 * kk), db + (u64)(2 * kk), a.idesc, (first && kk == 0) ? 0u : 1u);
                 umma_commit(&s_empty[s]);
                 if (!a.b_resident) umma_commit(&s_bempty[sb]);
                 if (last) umma_commit(&s_tfull[acc]);
@@ -423,6 +435,10 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
           tap -= 9;
           __syncwarp();
           if (lane == 0) mbar_arrive(&s_fpempty[fb]);
+          if (++fb == (u32)a.nfp) {
+            fb = 0;
+            fph ^= 1u;
+          }
         }
       }
     } else
@@ -433,9 +449,8 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
       const u32* tbs = s_tabb + tb * NTAB + row * 9;
       for (int slab = 0; slab < nslabs; ++slab, ++u) {
         // this group's taps of the (tile, slab) box: tap, tap + 4, ... < 9
-        const u32 fb = u & 1u;
         const u32 fpb = fp_s + fb * a.fp_stride;
-        mbar_wait_parked(&s_fpfull[fb], (u >> 1) & 1u);
+        mbar_wait_parked(&s_fpfull[fb], fph);
         float4 w_next = tw[tap];          // the table entry of the next K block is read one K block ahead
         u32 b_next = tbs[tap];
         for (; tap < 9; tap += NG) {
@@ -516,6 +531,10 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
         tap -= 9;
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_fpempty[fb]);   // the group leaves this (tile, slab) box
+        if (++fb == (u32)a.nfp) {
+          fb = 0;
+          fph ^= 1u;
+        }
       }
       mbar_arrive(&s_tabempty[tb]);                   // ... and this tile (per thread: each read its own table row)
     }
@@ -692,7 +711,7 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
     const long long j_total = a.b_resident ? (ntiles > 0 ? a.nkb : 0) : (long long)ntiles * a.nkb;
     long long u = 0, j = 0;
     int utile = tile_begin, uslab = 0, jtap = 0, jslab = 0;
-    u32 jslot = 0, juse = 0;
+    u32 jslot = 0, juse = 0, ufb = 0, uuse = 0;
     while (u < u_total || j < j_total) {
       bool progressed = false;
       if (j < j_total && (juse == 0 || mbar_test_wait(&s_bempty[jslot], (juse - 1u) & 1u))) {
@@ -712,9 +731,9 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
         ++j;
         progressed = true;
       }
-      if (u < u_total && (u < 2 || mbar_test_wait(&s_fpempty[u & 1], (u32)((u >> 1) - 1) & 1u))) {
+      if (u < u_total && (uuse == 0 || mbar_test_wait(&s_fpempty[ufb], (uuse - 1u) & 1u))) {
         const TileXY tc = tile_xy(a, utile);
-        const u32 fb = (u32)(u & 1);
+        const u32 fb = ufb;
         if (elect_one()) {
           if (FP_DBG(a) & 256) {
             mbar_arrive(&s_fpfull[fb]);   // experiment: no box load
@@ -727,6 +746,10 @@ dcn_fp_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
         if (++uslab == nslabs) {
           uslab = 0;
           ++utile;
+        }
+        if (++ufb == (u32)a.nfp) {
+          ufb = 0;
+          ++uuse;
         }
         ++u;
         progressed = true;
@@ -748,7 +771,7 @@ static int box_width(int TW, int R, bool plain) {
 }
 
 struct Plan {
-  int tw_shift, R, stages, nb, BN, kps;
+  int tw_shift, R, stages, nb, BN, kps, nfp;
   u32 bstage, fp_bytes, fp_stride;
   size_t smem;
 };
@@ -760,6 +783,7 @@ bool make_plan(const cnb_conv_desc* d, Plan* p, bool plain = false) {
   static const int env_r = [] { const char* e = getenv("CNB_DCN_REACH"); return e ? atoi(e) : 0; }();
   static const int env_stages = [] { const char* e = getenv("CNB_DCN_STAGES"); return e ? atoi(e) : 0; }();
   static const int env_nb = [] { const char* e = getenv("CNB_DCN_NB"); return e ? atoi(e) : 0; }();
+  static const int env_nfp = [] { const char* e = getenv("CNB_CONV_FP_BOXES"); return e ? atoi(e) : 0; }();
   p->tw_shift = d->Wi % 16 == 0 ? 4 : 3;
   const int TW = 1 << p->tw_shift, TH = BM >> p->tw_shift;
   p->BN = round_up(d->Co, 16);
@@ -800,7 +824,17 @@ bool make_plan(const cnb_conv_desc* d, Plan* p, bool plain = false) {
     const int need = env_nb > 0 ? 2 : (c[1] < 0 ? nkb : c[1]);
     if (nb >= need && nb >= 2) {
       p->R = R; p->nb = nb; p->fp_bytes = fpb; p->fp_stride = fps;
-      p->smem = fixed + 2 * (size_t)fps + (size_t)nb * p->bstage;
+      // plain mode: CNB_CONV_FP_BOXES > 2 puts what the weights leave into a deeper box ring (measured: no gain, the
+      // samplers' own instruction stream bounds this mode, profiles/r03f_plain_conv_stage_skipping.txt)
+      int nfp = 2;
+      if (plain && env_nfp > 2) {
+        nfp = (int)((budget - fixed - (size_t)nb * p->bstage) / fps);
+        if (nfp > MAX_FP) nfp = MAX_FP;
+        if (nfp > env_nfp) nfp = env_nfp;
+        if (nfp < 2) nfp = 2;
+      }
+      p->nfp = nfp;
+      p->smem = fixed + (size_t)nfp * fps + (size_t)nb * p->bstage;
       return true;
     }
   }
@@ -850,6 +884,7 @@ static int fp_run(const cnb_conv_desc* d, const void* x, const float* om, const 
   a.FH = plain ? TH + 2 : TH + 2 * p.R + 3;
   a.fp_bytes = p.fp_bytes;
   a.fp_stride = p.fp_stride;
+  a.nfp = p.nfp;
   a.BN = p.BN;
   a.nkb = 9 * (d->Ci / 64);
   a.b_bytes = (u32)a.BN * 128u;

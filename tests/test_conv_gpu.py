@@ -49,6 +49,10 @@ CONV_CASES = [
     (1, 64, 27, 6, 256, 3, 1, False, False),     # offset/mask conv geometry, two strips per row, fp32 out
     (1, 8, 16, 12, 128, 7, 1, True, False),      # stem: taps paired along kw (weights packed 7x8)
     (2, 8, 16, 40, 256, 7, 1, True, False),
+    # footprint kernel, plain 3x3 mode by default (dcn_fp.cu: Ci >= 128, N <= 32, >= 4 tiles per SM): box staging, four
+    # issuing groups with one partial accumulator each, summed in the epilogue
+    (20, 128, 27, 64, 64, 3, 1, False, False),
+    (20, 128, 24, 64, 64, 3, 1, True, True),     # bf16 output with residual through the same mode
 ]
 
 
@@ -197,6 +201,21 @@ def test_dcnv2_repeats_are_bit_identical(cuda_dev, B, Ci, Co, H):
     first = ops.dcnv2(x, om, wpk, Co, None, bias, act=0).clone()
     for _ in range(60):
         assert torch.equal(ops.dcnv2(x, om, wpk, Co, None, bias, act=0), first)
+
+
+def test_plain_conv_mode_repeats_are_bit_identical(cuda_dev):
+    """Plain 3x3 mode of the footprint kernel (default for Ci >= 128, N <= 32, >= 4 tiles per SM): the four sampler groups
+    issue their own MMAs, whose order at the tensor core varies from run to run -- each group accumulates into its own
+    partial accumulator and the epilogue adds them in group order, so the result must not (tools/conv_race_hunt.py is
+    the long version; the first version of the mode, one shared accumulator, differed on every run)."""
+    g = torch.Generator().manual_seed(13)
+    B, Ci, Co, H = 20, 128, 27, 64
+    x = ops.to_nhwc_bf16(torch.randn(B, Ci, H, H, generator=g).to(cuda_dev))
+    wpk = ops.pack_conv_weights((torch.randn(Co, Ci, 3, 3, generator=g) * 0.05).to(cuda_dev))
+    sc, sh = torch.ones(Co, device=cuda_dev), torch.zeros(Co, device=cuda_dev)
+    first = ops.conv2d(x, wpk, Co, 3, 1, 1, sc, sh, act=0, out_mode=2).clone()
+    for _ in range(100):
+        assert torch.equal(ops.conv2d(x, wpk, Co, 3, 1, 1, sc, sh, act=0, out_mode=2), first)
 
 
 def test_dcn_module_matches_torchvision(cuda_dev):

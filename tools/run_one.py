@@ -76,7 +76,7 @@ elif what == "s2d":
         ops.stem_s2d(x4, wpk, geom, 16, sc, sh)
 else:
     ci, co, hw, k = {"conv64": (64, 64, 128, 3), "dcn64": (64, 64, 128, 3), "head": (64, 768, 128, 3),
-                     "conv256": (256, 256, 32, 3), "conv128": (128, 128, 64, 3), "conv16": (16, 16, 512, 3), "stem": (8, 16, 512, 7)}[what]
+                     "conv256": (256, 256, 32, 3), "conv128": (128, 128, 64, 3), "conv16": (16, 16, 512, 3), "stem": (8, 16, 512, 7), "off128": (128, 27, 64, 3)}[what]
     x = torch.randn(B, hw, hw, ci, device=dev).to(torch.bfloat16)
     w = ops.pack_conv_weights(torch.randn(co, ci, k, k, device=dev) * 0.05)
     sc, sh = torch.ones(co, device=dev), torch.zeros(co, device=dev)
@@ -85,5 +85,5 @@ else:
         if om is not None:
             ops.dcnv2(x, om, w, co, sc, sh, act=1)
         else:
-            ops.conv2d(x, w, co, k, 1, k // 2, sc, sh, act=1)
+            ops.conv2d(x, w, co, k, 1, k // 2, sc, sh, act=1, out_mode=2 if co % 8 else 0)
 torch.cuda.synchronize()

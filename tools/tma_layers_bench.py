@@ -11,6 +11,7 @@ CASES = {  # name: (Ci, Co, H, k)
     "c256": (256, 256, 32, 3), "c128": (128, 128, 64, 3), "c512": (512, 512, 16, 3), "head": (64, 768, 128, 3),
     "off128": (128, 27, 64, 3), "off256": (256, 27, 32, 3), "root448": (448, 128, 64, 1), "c64": (64, 64, 64, 3),
     "c64_128": (64, 64, 128, 3), "off64": (64, 27, 128, 3), "off512": (512, 27, 16, 3), "c128_64o": (128, 64, 64, 3),
+    "c16": (16, 16, 512, 3), "c32": (32, 32, 256, 3),
 }
 dev = torch.device("cuda:0")
 B = 32
