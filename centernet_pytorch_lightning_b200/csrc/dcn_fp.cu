@@ -50,6 +50,7 @@ constexpr int W_EPI0 = W_MMA + 1;                    // warps 21..24 (TMEM lane 
 constexpr int W_LOAD = W_EPI0 + 4;                   // warp 25: footprint boxes
 constexpr int NTHREADS = (W_LOAD + 1) * 32;          // 832
 constexpr int NG = 4;                                // sampler groups: K block k of the CTA's stream belongs to group k % NG
+                                                     // (5 groups = 960 threads at 64 registers measured slower: 64->64@128x128 149 -> 162 us)
 constexpr int WPG = NPROD_WARPS / NG;                // 4 warps per group = the 4 TMEM lane quarters
 constexpr int MAX_STAGES = 12;
 constexpr int MAX_B = 18;
@@ -798,6 +799,10 @@ bool make_plan(const cnb_conv_desc* d, Plan* p, bool plain = false) {
   int st = (512 - acc_cols) / (A_COLS * kps);
   if (st > MAX_STAGES) st = MAX_STAGES;
   if (env_stages > 0 && st > env_stages) st = env_stages;
+  // a stage must always come back to the SAME group (depth a multiple of NG): a group is then ordered behind its own
+  // previous use of the stage, and no group can run two rounds ahead of another one's pending commit on a stage (the
+  // parity wait cannot tell round r+1 from round r-1)
+  st -= st % NG;
   if (st < NG) return false;
   p->stages = st;
   const size_t fixed = (plain ? 0 : (size_t)2 * NTAB * (sizeof(float4) + sizeof(u32)) + (size_t)BM * OM_CS * 4) +

@@ -154,6 +154,7 @@ def test_conv_nchw_f32_head_output(cuda_dev):
                                                  (1, 256, 256, 8, 8, False),
                                                  (1, 128, 128, 20, 24, False),   # BN=128: two taps per stage, 18 K blocks
                                                  (2, 64, 24, 12, 40, False),     # Co not a multiple of 16
+                                                 (2, 64, 96, 24, 32, False),     # BN = 96: 10 tensor-memory stages fit, 8 are used (a multiple of the 4 groups)
                                                  (2, 64, 64, 24, 32, False),     # 8 x 16 pixel tiles (W % 16 == 0)
                                                  (1, 128, 64, 20, 16, False),    # ... last tile row cut by the image
                                                  (1, 128, 128, 16, 48, False),   # two slabs, BN = 128

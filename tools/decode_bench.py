@@ -24,14 +24,24 @@ for kind in ("uniform", "bumps", "saturated"):
         heat, wh, reg = (torch.from_numpy(a).to(dev) for a in (heat, wh, reg))
     for _ in range(3):
         ctdet_decode(heat, wh, reg)
-    ts = []
-    for _ in range(10):
-        flush.fill_(1)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        ctdet_decode(heat, wh, reg)
-        e1.record()
-        torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
-    ms = sorted(ts)[len(ts) // 2]
-    print(f"{kind:10s} decode ms median {ms:.4f} min {min(ts):.4f}  {167.9e6 / ms / 1e6:.0f} GB/s (events around memset+kernel)")
+    # three ways of making the reads cold: (w) write a 256 MB buffer -- leaves L2 full of DIRTY lines whose write-back
+    # then competes with the scan's reads; (r) read a 256 MB buffer -- clean lines; (x) rotate three distinct copies of
+    # the maps (3 x 168 MB, each larger than L2), no flush at all
+    copies = [(heat, wh, reg)] + [(heat.clone(), wh.clone(), reg.clone()) for _ in range(2)]
+    for mode in ("w", "r", "x"):
+        ts = []
+        for it in range(12):
+            if mode == "w":
+                flush.fill_(1)
+            elif mode == "r":
+                flush.sum()
+            h, w_, r_ = copies[it % 3] if mode == "x" else copies[0]
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ctdet_decode(h, w_, r_)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts = ts[2:]
+        ms = sorted(ts)[len(ts) // 2]
+        print(f"{kind:10s} cold-by-{mode} decode ms median {ms:.4f} min {min(ts):.4f}  {167.9e6 / ms / 1e6:.0f} GB/s (events around memset+kernels)")
