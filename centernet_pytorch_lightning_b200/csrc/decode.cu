@@ -970,8 +970,11 @@ __global__ void __launch_bounds__(SNT, 2) decode_stream_kernel(const ScanArgs a)
     fence_proxy_async_smem();
   }
   if (tid < SW) s_wcnt[tid] = 0;
+  if (a.debug && tid == 0 && blockIdx.x < 1024)
+    for (int i = 0; i < DBG_SLOTS; ++i) g_dbg[blockIdx.x * DBG_SLOTS + i] = 0;
   __syncthreads();
   if (c_begin >= c_end) return;
+  DBG_MARK(0);
 
   int g = c_begin / a.cpg, pg, band;
   {
@@ -994,7 +997,11 @@ __global__ void __launch_bounds__(SNT, 2) decode_stream_kernel(const ScanArgs a)
     if (lane == 0) {
       for (int c = c_begin; c < c_end; ++c) {
         const int k = c - c_begin, stage = k & (NST - 1);
-        if (k >= NST) mbar_wait(&s_empty[stage], (u32)((k / NST) - 1) & 1u);
+        if (k >= NST) {
+          const unsigned long long tw0 = a.debug ? gtimer() : 0ull;
+          mbar_wait(&s_empty[stage], (u32)((k / NST) - 1) & 1u);
+          if (a.debug && blockIdx.x < 1024) g_dbg[blockIdx.x * DBG_SLOTS + 6] += gtimer() - tw0;   // producer: ring full
+        }
         u32 fb;
         const float* plane = plane_ptr(a, g, pg, &fb);
         const int r0 = band * a.R, r1 = min(r0 + a.R, a.H);
@@ -1023,6 +1030,8 @@ __global__ void __launch_bounds__(SNT, 2) decode_stream_kernel(const ScanArgs a)
 
   // hand the warp's list to the group: histogram increments, new bound, append
   auto warp_flush = [&](int fg) {
+    const unsigned long long tf0 = a.debug ? gtimer() : 0ull;
+    DBG_ADD(5, 1);
     int* oct = a.goct + (size_t)fg * OCT_PAD;
     int* hist = a.ghist + (size_t)fg * NCB_PAD;
     int* fine = a.gfine ? a.gfine + (size_t)fg * NBF : nullptr;
@@ -1098,6 +1107,7 @@ __global__ void __launch_bounds__(SNT, 2) decode_stream_kernel(const ScanArgs a)
     n = 0;
     if (lane == 0) *wcnt = 0;
     __syncwarp();
+    if (a.debug) DBG_ADD(4, gtimer() - tf0);
   };
 
   for (int c = c_begin; c < c_end; ++c) {
@@ -1124,7 +1134,11 @@ __global__ void __launch_bounds__(SNT, 2) decode_stream_kernel(const ScanArgs a)
     const int re = min(rs + a.rpt, r1);
     const int n_before = n;
 
-    mbar_wait(&s_full[stage], (u32)(k / NST) & 1u);
+    {
+      const unsigned long long tw0 = a.debug ? gtimer() : 0ull;
+      mbar_wait(&s_full[stage], (u32)(k / NST) & 1u);
+      if (a.debug) DBG_ADD(7, gtimer() - tw0);
+    }
 
     // one look at the thread's rows: largest value against the bound, one vote per warp
     float mt = 0.f;
@@ -1170,9 +1184,12 @@ __global__ void __launch_bounds__(SNT, 2) decode_stream_kernel(const ScanArgs a)
     if (lane == 0) mbar_arrive(&s_empty[stage]);   // this warp is done with the tile
     // flush when the list fills up, and right after a chunk scanned without any bound (the group needs one)
     if (n >= a.wflush || (n > 0 && thr == 0ull)) warp_flush(g);
+    if (k == 0) DBG_MARK(1);
+    if (c + 1 == c_end) DBG_MARK(2);
     advance(g, pg, band);
   }
   if (n > 0) warp_flush(cur_g);
+  DBG_MARK(3);
 }
 
 // one CTA per group: the exact, sorted top-K of the candidates the streaming scan appended

@@ -36,7 +36,7 @@ for name, col in (("start", 0), ("first chunk done", 1), ("last chunk scanned", 
     v = us(a[:, col])
     print(f"  {name:22s} min {v.min():7.1f}  median {np.median(v):7.1f}  max {v.max():7.1f} us")
 print(f"  flushes per CTA: mean {a[:, 5].mean():.1f} max {a[:, 5].max()};  time in flushes per CTA: mean {a[:, 4].mean() / 1e3:.1f} us max {a[:, 4].max() / 1e3:.1f} us")
-print(f"  chunks with hits per CTA: mean {a[:, 6].mean():.1f}")
+print(f"  slot 6 (scan kernel: chunks with hits; stream kernel: ns the producer waited for a free ring slot): mean {a[:, 6].mean():.1f} max {a[:, 6].max()}")
 print(f"  time blocked on tile data per CTA (thread 0): mean {a[:, 7].mean() / 1e3:.1f} us max {a[:, 7].max() / 1e3:.1f} us")
 mer = us(a[:, 3]) - us(a[:, 2])
 print(f"  tail after last scan (group accounting + merge): median {np.median(mer):.1f} max {mer.max():.1f} us; CTAs with tail > 5us: {(mer > 5).sum()}")
