@@ -389,8 +389,14 @@ def test_graphed_training_step_equals_eager(cuda_dev):
 
 def test_multi_pose_training_step(cuda_dev):
     """CenterNetMultiPose's 6-head loss (centernet_multi_pose.py:97-155) through the restated task on this package's
-    modules in train mode: forward -> loss -> backward; head gradients vs the CPU oracle evaluated on the ENGINE's own
-    feature map (so that only the heads + losses are compared: <= 6 % per tensor), every head parameter gets a gradient."""
+    modules in train mode: forward -> loss -> backward.  (1) The whole step: finite loss with the reference's stat keys,
+    equal within 1 % to the CPU oracle's heads + loss evaluated on the ENGINE's own feature map, a gradient for every head
+    parameter and for the backbone.  (2) Head gradients against the oracle, per tensor <= 6 %, on a feature map that is
+    the same in every run (the eval-mode backbone, bit-reproducible): the train-mode backbone at random init amplifies
+    the last-bit noise of its BatchNorm atomics ~130-400x per unit of relative perturbation (measured on the fp32
+    oracle), so its features differ by ~17 % in L2 from run to run (tools/train_fwd_repeat.py) and with them the
+    conditioning of this comparison (keypoints.fc.0.weight: 2.9-6.2 % over four runs); the heads' own backward is
+    reproducible to 1e-7 on fixed inputs (tools/head_grad_repeat.py)."""
     from centernet_pytorch_lightning_b200.models import create_model
     from centernet_pytorch_lightning_b200.utils.synthetic import randomize_
     from oracle import net_torch, task_torch
@@ -399,30 +405,52 @@ def test_multi_pose_training_step(cuda_dev):
     task = task_torch.MultiPoseTask(ns, "dla_34")
     randomize_(task.backbone.state_dict(), 3, offset_gain=0.02)
     hd = {k: v.clone() for k, v in task.heads[0].state_dict().items()}
-    task = task.to(cuda_dev).train()
+    task = task.to(cuda_dev)
     x = torch.rand(2, 3, 128, 128, generator=torch.Generator().manual_seed(1)).to(cuda_dev)
     _, tgt = task_torch.task_inputs("pose", B=2, H=32, W=32)
+    tgt_dev = {k: v.to(cuda_dev) for k, v in tgt.items()}
+    ref_task = _pose_loss_task()
+
+    def oracle_on(feat):
+        """oracle heads + loss on a feature map of the engine (bf16-rounded, as the heads consume it)"""
+        f = feat.detach().float().cpu().to(BF).float()
+        h = {k: v.clone().requires_grad_(True) for k, v in hd.items()}
+        o = net_torch.center_head_forward(h, f, task_torch.POSE_HEADS)
+        ref_loss, _ = ref_task.loss([o], tgt)
+        ref_loss.backward()
+        return ref_loss, h
+
+    # (2) first, before any running statistic moves: fixed features, train-mode heads
+    task.eval()
+    with torch.no_grad():
+        feat_fixed = task.backbone(x)[0].clone()     # a plain NCHW fp32 tensor (the inference path tags its output with an NHWC view)
+    task.train()
+    loss_f, _ = task.loss([task.heads[0](feat_fixed)], tgt_dev)
+    loss_f.backward()
+    torch.cuda.synchronize()
+    ref_loss_f, h = oracle_on(feat_fixed)
+    print(f"multi-pose loss on fixed features: engine {loss_f.item():.5f} oracle {ref_loss_f.item():.5f}")
+    assert abs(loss_f.item() - ref_loss_f.item()) <= 1e-2 * abs(ref_loss_f.item())
+    for name, p in task.heads[0].named_parameters():
+        assert p.grad is not None, name
+        rg = h[name].grad
+        rel = ((p.grad.float().cpu() - rg).norm() / (rg.norm() + 1e-20)).item()
+        print(f"  {name}: rel {rel:.4f} (|grad| max {rg.abs().max().item():.2e})")
+        assert rel <= 6e-2 or rg.abs().max() < 1e-7, (name, rel)   # mid activations are bf16 on the GPU side (measured <= 4.0e-2, the same in every run)
+    task.zero_grad(set_to_none=True)
+
+    # (1) the whole training step
     feat = task.backbone(x)
     outs = [task.heads[0](feat[0])]
-    loss, stats = task.loss(outs, {k: v.to(cuda_dev) for k, v in tgt.items()})
+    loss, stats = task.loss(outs, tgt_dev)
     loss.backward()
     torch.cuda.synchronize()
     assert torch.isfinite(loss) and set(stats) == {"loss", "hm_loss", "kp_loss", "hm_kp_loss", "hm_offset_loss", "wh_loss", "off_loss"}
-    # oracle heads + loss on the engine's feature map (bf16-rounded, as the heads consume it)
-    f = feat[0].detach().float().cpu().to(BF).float()
-    for v in hd.values():
-        v.requires_grad_(True)
-    o = net_torch.center_head_forward(hd, f, task_torch.POSE_HEADS)
-    ref_task = _pose_loss_task()
-    ref_loss, _ = ref_task.loss([o], tgt)
-    ref_loss.backward()
+    ref_loss, _ = oracle_on(feat[0])
     print(f"multi-pose loss engine {loss.item():.5f} oracle-on-engine-features {ref_loss.item():.5f}")
     assert abs(loss.item() - ref_loss.item()) <= 1e-2 * abs(ref_loss.item())
     for name, p in task.heads[0].named_parameters():
-        assert p.grad is not None, name
-        rg = hd[name].grad
-        rel = ((p.grad.float().cpu() - rg).norm() / (rg.norm() + 1e-20)).item()
-        assert rel <= 6e-2 or rg.abs().max() < 1e-7, (name, rel)   # mid activations are bf16 on the GPU side (measured <= 3.5e-2)
+        assert p.grad is not None and torch.isfinite(p.grad).all(), name
     assert any(p.grad is not None for p in task.backbone.parameters())
 
 
