@@ -981,16 +981,13 @@ int dcn_fp_run(const cnb_conv_desc* d, const void* x, const float* om, int om_cs
   return fp_run(d, x, om, wpk, scale, shift, nullptr, y, st, false);
 }
 
-// Plain 3x3 / stride 1 / pad 1 convolutions with Ci % 64 == 0 and N <= 128 through the same kernel (`plain` mode: input
+// Plain 3x3 / stride 1 / pad 1 convolutions with Ci % 64 == 0 and N <= 64 through the same kernel (`plain` mode: input
 // box in shared memory read 9 times by the sampler threads, A operand in tensor memory, the sampler groups issue their own
-// MMAs).  Measured against conv_rows / conv_tma (B=32, us): 128->27@64x64 28.8 vs 35.3, 128->64@64x64 28.6 vs 40.6,
-// 64->64@64x64 23.8 vs 25.7; 64->64@128x128 57.9 vs 53.7, 64->27@128x128 60.5 vs 58.3, 256->27@32x32 26.4 vs 23.4 -- every
-// small-N tcgen05 GEMM of this library lands at 420-480 clocks per (128 rows x K = 64), i.e. ~112 clocks per M = 128 / K = 16
-// MMA whatever N <= 64 is and wherever A comes from, so only the layers whose im2col traffic or tile count hurt the other
-// kernels gain (Ci >= 128, N <= 64, at least 4 tiles per SM: CNB_CONV_FP=2 selects exactly those).  OFF by default: four
-// groups issuing into one accumulator in whatever order they get there makes the fp32 summation order, hence the last
-// bits of the result, vary from run to run (tools/conv_race_hunt.py: every repeat differs), and everything else in this
-// library is bit-reproducible.  CNB_CONV_FP=1 forces the mode for every eligible geometry (the parity tests run that).
+// MMAs, each into its own partial accumulator; the epilogue adds the partials in group order, so the result is
+// bit-reproducible -- tools/conv_race_hunt.py).  Measured against conv_rows / conv_tma (B=32, us,
+// profiles/r03a_plain_conv_partials.txt): 128->27@64x64 33.8 vs 37.9, 128->64@64x64 39.3 vs 41.9; 64->27@128x128 64.4 vs
+// 58.9 -- only the layers whose im2col traffic or tile count hurt the other kernels gain (Ci >= 128, at least 4 tiles per
+// SM).  What bounds the mode is the sampler groups' own instruction stream (profiles/r03f_plain_conv_stage_skipping.txt).
 bool conv_fp_supported(const cnb_conv_desc* d) {
   // CNB_CONV_FP: 0 = never, 1 = every geometry the mode covers, 2 = the policy below with N <= 64; unset = the policy:
   // deep thin layers (Ci >= 128, N <= 32: the offset/mask convolutions at 64x64 and up) with >= 4 tiles per SM, where it
