@@ -830,7 +830,7 @@ bool make_plan(const cnb_conv_desc* d, Plan* p, bool plain = false) {
     if (nb >= need && nb >= 2) {
       p->R = R; p->nb = nb; p->fp_bytes = fpb; p->fp_stride = fps;
       // plain mode: CNB_CONV_FP_BOXES > 2 puts what the weights leave into a deeper box ring (measured: no gain, the
-      // samplers' own instruction stream bounds this mode, profiles/r03f_plain_conv_stage_skipping.txt)
+      // samplers' own instruction stream bounds this mode, profiles/r02s3f_plain_conv_stage_skipping.txt)
       int nfp = 2;
       if (plain && env_nfp > 2) {
         nfp = (int)((budget - fixed - (size_t)nb * p->bstage) / fps);
@@ -985,9 +985,9 @@ int dcn_fp_run(const cnb_conv_desc* d, const void* x, const float* om, int om_cs
 // box in shared memory read 9 times by the sampler threads, A operand in tensor memory, the sampler groups issue their own
 // MMAs, each into its own partial accumulator; the epilogue adds the partials in group order, so the result is
 // bit-reproducible -- tools/conv_race_hunt.py).  Measured against conv_rows / conv_tma (B=32, us,
-// profiles/r03a_plain_conv_partials.txt): 128->27@64x64 33.8 vs 37.9, 128->64@64x64 39.3 vs 41.9; 64->27@128x128 64.4 vs
+// profiles/r02s3a_plain_conv_partials.txt): 128->27@64x64 33.8 vs 37.9, 128->64@64x64 39.3 vs 41.9; 64->27@128x128 64.4 vs
 // 58.9 -- only the layers whose im2col traffic or tile count hurt the other kernels gain (Ci >= 128, at least 4 tiles per
-// SM).  What bounds the mode is the sampler groups' own instruction stream (profiles/r03f_plain_conv_stage_skipping.txt).
+// SM).  What bounds the mode is the sampler groups' own instruction stream (profiles/r02s3f_plain_conv_stage_skipping.txt).
 bool conv_fp_supported(const cnb_conv_desc* d) {
   // CNB_CONV_FP: 0 = never, 1 = every geometry the mode covers, 2 = the policy below with N <= 64; unset = the policy:
   // deep thin layers (Ci >= 128, N <= 32: the offset/mask convolutions at 64x64 and up) with >= 4 tiles per SM, where it

@@ -1,7 +1,7 @@
 #!/bin/bash
 # plain mode: box ring depth
 mkdir -p gpurun_out
-o=gpurun_out/r03e.txt; : > $o
+o=gpurun_out/r02s3e.txt; : > $o
 CNB_CONV_FP=1 timeout 300 python -m pytest tests/test_conv_gpu.py -q -x 2>&1 | tail -n 4 >> $o
 if grep -q "failed\|rror" $o; then cat $o; exit 1; fi
 for nfp in 2 3 4 6; do
