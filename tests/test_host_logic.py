@@ -23,3 +23,24 @@ def test_stem_space_to_depth_filter(K):
     y = F.conv2d(xs, ws.double(), padding=(K // 2, D)).permute(0, 2, 3, 1).reshape(B, H, W, Co)
     ref = F.conv2d(x, w.float().double(), padding=K // 2).permute(0, 2, 3, 1)
     assert torch.allclose(y, ref, atol=1e-12)
+
+
+def test_standalone_probes_compile_for_sm100a(tmp_path):
+    """tools/*.cu (tcgen05.mma issue-rate probe, TMA feed probe) are standalone nvcc programs against csrc/umma.cuh: they
+    must keep compiling for sm_100a as the PTX wrappers change (nvcc cross-compiles without a GPU)."""
+    import glob
+    import os
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not found")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    srcs = sorted(glob.glob(os.path.join(root, "tools", "*.cu")))
+    assert any(s.endswith("mma_probe.cu") for s in srcs)
+    for src in srcs:
+        out = tmp_path / (os.path.basename(src) + ".o")
+        r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-c", src, "-o", str(out),
+                            "-I", os.path.join(root, "centernet_pytorch_lightning_b200", "csrc"), "-I", os.path.join(root, "include")],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, f"{src}:\n{r.stderr[-2000:]}"
